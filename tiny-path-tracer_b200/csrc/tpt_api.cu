@@ -1,0 +1,615 @@
+// csrc/tpt_api.cu -- the extern "C" layer of include/tpt.h: scene upload, render dispatch,
+// resolve/quantise kernel, statistics. Compiled with -fmad=false (the resolve kernel restates
+// main.cpp:135-139 exactly). No CPU fallback anywhere: without a device every compute entry
+// point returns TPT_ERR_NO_DEVICE.
+#include "tpt.h"
+#include "tpt_launch.h"
+
+#include <chrono>
+#include <climits>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace tptd;
+
+namespace {
+
+thread_local std::string g_error;
+
+int fail(int code, const std::string &msg) {
+  g_error = msg;
+  return code;
+}
+int cuda_fail(cudaError_t e, const char *what) {
+  int code = (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) ? TPT_ERR_NO_DEVICE : TPT_ERR_CUDA;
+  return fail(code, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) return cuda_fail(e_, #call);                                            \
+  } while (0)
+
+struct ResolveArgs {
+  const float *acc; // [n_ranges][npix][3]
+  int n_ranges, npix, ns, slices, per_slice;
+  int slice_last_range[TPT_MAX_RANGES];
+  float *sum_rgb;       // [slices][npix][3] or null
+  uint8_t *rgb8;        // [npix][3] or null
+  uint8_t *rgb8_slices; // [slices][npix][3] or null
+};
+
+// int(255.99f * c) with x86 cvttss2si semantics for out-of-range / NaN (-> INT_MIN), then the
+// writer's clamp to [0,255] (main.cpp:137-139, 176-182)
+__device__ __forceinline__ uint8_t quantise(float sum, float denom) {
+  float c = sum / denom;  // col /= float(ns)           main.cpp:135
+  c = sqrtf(c);           // sqrt gamma                 main.cpp:136
+  float v = 255.99f * c;  //                            main.cpp:137
+  int q = (v >= -2147483648.f && v < 2147483648.f) ? (int)v : INT_MIN;
+  q = q < 0 ? 0 : (q > 255 ? 255 : q);
+  return (uint8_t)q;
+}
+
+__global__ void resolve_kernel(const __grid_constant__ ResolveArgs R) {
+  int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= R.npix) return;
+  float rx = 0.f, ry = 0.f, rz = 0.f;
+  int slice = 0;
+  for (int r = 0; r < R.n_ranges; r++) {
+    const float *a = R.acc + ((size_t)r * R.npix + pix) * 3;
+    rx += a[0];
+    ry += a[1];
+    rz += a[2];
+    if (slice < R.slices && r == R.slice_last_range[slice]) {
+      size_t o = ((size_t)slice * R.npix + pix) * 3;
+      if (R.sum_rgb) {
+        R.sum_rgb[o] = rx;
+        R.sum_rgb[o + 1] = ry;
+        R.sum_rgb[o + 2] = rz;
+      }
+      if (R.rgb8_slices) { // main.cpp:205-209
+        float den = float(R.per_slice * (slice + 1));
+        R.rgb8_slices[o] = quantise(rx, den);
+        R.rgb8_slices[o + 1] = quantise(ry, den);
+        R.rgb8_slices[o + 2] = quantise(rz, den);
+      }
+      slice++;
+    }
+  }
+  if (R.rgb8) {
+    float den = float(R.ns);
+    R.rgb8[(size_t)pix * 3] = quantise(rx, den);
+    R.rgb8[(size_t)pix * 3 + 1] = quantise(ry, den);
+    R.rgb8[(size_t)pix * 3 + 2] = quantise(rz, den);
+  }
+}
+
+double now_ms() {
+  using namespace std::chrono;
+  return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+} // namespace
+
+struct tpt_scene {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaDeviceProp prop{};
+  SceneLayout layout{};
+  float4 *d_blob = nullptr;
+  size_t blob_bytes = 0;
+  bool use_smem = false;
+  std::vector<cudaArray_t> arrays;
+  std::vector<cudaTextureObject_t> textures;
+  bool has_lights = false;
+  // render products (device)
+  float *d_acc = nullptr;
+  size_t acc_bytes = 0;
+  unsigned long long *d_counters = nullptr;
+  float *d_sum = nullptr;
+  uint8_t *d_rgb8 = nullptr, *d_rgb8_slices = nullptr;
+  size_t sum_bytes = 0, rgb8_bytes = 0, rgb8_slices_bytes = 0;
+  int last_nx = 0, last_ny = 0, last_slices = 0;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  tpt_stats stats{};
+};
+
+namespace {
+
+template <typename T> void append(std::vector<unsigned char> &blob, const T *src, size_t count, size_t pad_to = 16) {
+  size_t bytes = sizeof(T) * count;
+  size_t at = blob.size();
+  blob.resize(at + ((bytes + pad_to - 1) / pad_to) * pad_to, 0);
+  if (bytes) std::memcpy(blob.data() + at, src, bytes);
+}
+
+int validate_desc(const tpt_scene_desc *d, int &depth_out) {
+  if (!d) return fail(TPT_ERR_INVALID, "null scene description");
+  if (d->api_version != TPT_API_VERSION) return fail(TPT_ERR_INVALID, "api_version mismatch");
+  if (d->n_nodes <= 0 || !d->nodes) return fail(TPT_ERR_INVALID, "scene has no nodes");
+  if (d->n_prims <= 0 || !d->prims) return fail(TPT_ERR_INVALID, "scene has no primitives");
+  if (d->n_chains <= 0 || !d->chains) return fail(TPT_ERR_INVALID, "chain 0 (identity) is required");
+  if (d->n_materials <= 0 || !d->materials) return fail(TPT_ERR_INVALID, "scene has no materials");
+  if (d->n_images > TPT_MAX_IMAGES) return fail(TPT_ERR_UNSUPPORTED, "too many image textures");
+  if (d->n_lights < 0 || (d->n_lights > 0 && !d->lights)) return fail(TPT_ERR_INVALID, "bad light list");
+  // structural walk: every group's end must nest properly
+  std::vector<int> ends;
+  int depth = 0;
+  for (int i = 0; i < d->n_nodes; i++) {
+    while (!ends.empty() && ends.back() == i) ends.pop_back();
+    const tpt_node &n = d->nodes[i];
+    int k = n.kind & 0xff, chain = n.kind >> 16;
+    if (chain < 0 || chain >= d->n_chains) return fail(TPT_ERR_INVALID, "node chain out of range");
+    if (k == TPT_NODE_LEAF) {
+      if (n.end_or_prim < 0 || n.end_or_prim >= d->n_prims) return fail(TPT_ERR_INVALID, "leaf prim out of range");
+    } else if (k == TPT_NODE_BVH || k == TPT_NODE_LIST) {
+      int limit = ends.empty() ? d->n_nodes : ends.back();
+      if (n.end_or_prim <= i || n.end_or_prim > limit) return fail(TPT_ERR_INVALID, "group end does not nest");
+      ends.push_back(n.end_or_prim);
+      if ((int)ends.size() > depth) depth = (int)ends.size();
+    } else {
+      return fail(TPT_ERR_INVALID, "unknown node kind");
+    }
+  }
+  if (depth + 2 > TPT_MAX_FRAMES) return fail(TPT_ERR_UNSUPPORTED, "hitable tree nests deeper than TPT_MAX_FRAMES");
+  depth_out = depth;
+  for (int i = 0; i < d->n_prims; i++) {
+    const tpt_prim &p = d->prims[i];
+    if (p.kind < TPT_PRIM_SPHERE || p.kind > TPT_PRIM_YZ_RECT) return fail(TPT_ERR_UNSUPPORTED, "unknown primitive kind");
+    if (p.material < 0 || p.material >= d->n_materials) return fail(TPT_ERR_INVALID, "prim material out of range");
+    if (p.chain < 0 || p.chain >= d->n_chains) return fail(TPT_ERR_INVALID, "prim chain out of range");
+  }
+  for (int i = 0; i < d->n_chains; i++) {
+    const tpt_chain &c = d->chains[i];
+    if (c.n_ops < 0 || c.first_op < 0 || c.first_op + c.n_ops > d->n_xform_ops)
+      return fail(TPT_ERR_INVALID, "chain ops out of range");
+  }
+  bool needs_perlin = false;
+  for (int i = 0; i < d->n_textures; i++) {
+    const tpt_texture &t = d->textures[i];
+    if (t.kind == TPT_TEX_CHECKER && (t.odd < 0 || t.odd >= d->n_textures || t.even < 0 || t.even >= d->n_textures))
+      return fail(TPT_ERR_INVALID, "checker children out of range");
+    if (t.kind == TPT_TEX_IMAGE && (t.image < 0 || t.image >= d->n_images))
+      return fail(TPT_ERR_INVALID, "image index out of range");
+    if (t.kind == TPT_TEX_PERLIN) needs_perlin = true;
+    if (t.kind < TPT_TEX_CONSTANT || t.kind > TPT_TEX_IMAGE) return fail(TPT_ERR_UNSUPPORTED, "unknown texture kind");
+  }
+  if (needs_perlin && !d->perlin) return fail(TPT_ERR_INVALID, "perlin texture without tables");
+  for (int i = 0; i < d->n_materials; i++) {
+    const tpt_material &m = d->materials[i];
+    if (m.kind < TPT_MAT_LAMBERTIAN || m.kind > TPT_MAT_ABSORBER) return fail(TPT_ERR_UNSUPPORTED, "unknown material kind");
+    if ((m.kind == TPT_MAT_LAMBERTIAN || m.kind == TPT_MAT_DIFFUSE_LIGHT) && (m.texture < 0 || m.texture >= d->n_textures))
+      return fail(TPT_ERR_INVALID, "material texture out of range");
+  }
+  for (int i = 0; i < d->n_images; i++)
+    if (!d->images[i].rgb || d->images[i].width <= 0 || d->images[i].height <= 0)
+      return fail(TPT_ERR_INVALID, "image without pixels");
+  return TPT_OK;
+}
+
+int ensure(void **p, size_t &have, size_t want) {
+  if (have >= want && *p) return TPT_OK;
+  if (*p) cudaFree(*p);
+  *p = nullptr;
+  have = 0;
+  cudaError_t e = cudaMalloc(p, want);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+  have = want;
+  return TPT_OK;
+}
+
+struct Plan {
+  RenderArgs args;
+  ResolveArgs res;
+  int blocks = 0, blocks_per_sm = 0;
+  bool parity = false;
+  size_t npix = 0;
+};
+
+int make_plan(tpt_scene *s, const tpt_camera *cam, const tpt_render_params *p, Plan &plan) {
+  if (!s || !cam || !p) return fail(TPT_ERR_INVALID, "null argument");
+  if (p->nx <= 0 || p->ny <= 0 || p->ns <= 0 || p->max_depth < 0) return fail(TPT_ERR_INVALID, "bad image/sample parameters");
+  if ((long long)p->nx * p->ny > (1LL << 28)) return fail(TPT_ERR_UNSUPPORTED, "image too large");
+  int slices = p->slices > 0 ? p->slices : 1;
+  int per_slice = p->ns / slices;
+  if (per_slice <= 0) return fail(TPT_ERR_INVALID, "ns < slices (the reference would divide by zero, main.cpp:113,127)");
+  if (p->mode != TPT_MODE_PARITY && p->mode != TPT_MODE_FAST) return fail(TPT_ERR_INVALID, "unknown mode");
+  if (p->kernel != TPT_KERNEL_MEGA) return fail(TPT_ERR_UNSUPPORTED, "kernel variant not built");
+  if (p->part_count <= 0 || p->part_index < 0 || p->part_index >= p->part_count) return fail(TPT_ERR_INVALID, "bad part_index/part_count");
+  if (!s->has_lights) return fail(TPT_ERR_INVALID, "light-sampling list is empty (color() needs light_shape, main.cpp:99-106)");
+  plan.parity = p->mode == TPT_MODE_PARITY;
+  RenderArgs &A = plan.args;
+  std::memset(&A, 0, sizeof(A));
+  A.scene = s->layout;
+  auto v3 = [](const float *f) { return V3{f[0], f[1], f[2]}; };
+  A.cam.origin = v3(cam->origin);
+  A.cam.llc = v3(cam->lower_left_corner);
+  A.cam.vertical = v3(cam->vertical);
+  A.cam.horizontal = v3(cam->horizontal);
+  A.cam.u = v3(cam->u);
+  A.cam.v = v3(cam->v);
+  A.cam.w = v3(cam->w);
+  A.cam.lens_radius = cam->lens_radius;
+  A.cam.time0 = cam->time0;
+  A.cam.time1 = cam->time1;
+  A.nx = p->nx;
+  A.ny = p->ny;
+  A.ns = p->ns;
+  A.max_depth = p->max_depth;
+  A.t_min = p->t_min;
+  A.seed_lo = p->seed_lo;
+  A.seed_hi = p->seed_hi;
+  // sample ranges: each slice is cut into `subs` sub-ranges (finer bins => shorter kernel tail);
+  // samples beyond slices*per_slice (ns not divisible) form one tail range.
+  int subs = p->reserved[1];
+  if (subs <= 0) subs = plan.parity ? 1 : std::max(1, std::min(8, per_slice / 256));
+  int tail = p->ns - slices * per_slice;
+  while (subs > 1 && slices * subs + (tail ? 1 : 0) > TPT_MAX_RANGES) subs--;
+  if (slices * subs + (tail ? 1 : 0) > TPT_MAX_RANGES) return fail(TPT_ERR_UNSUPPORTED, "too many slices");
+  if (subs > per_slice) subs = per_slice;
+  ResolveArgs &R = plan.res;
+  std::memset(&R, 0, sizeof(R));
+  int r = 0;
+  for (int sl = 0; sl < slices; sl++) {
+    for (int q = 0; q < subs; q++) {
+      A.range_bounds[r] = sl * per_slice + (int)((long long)per_slice * q / subs);
+      r++;
+    }
+    R.slice_last_range[sl] = r - 1;
+  }
+  A.range_bounds[r] = slices * per_slice;
+  if (tail) {
+    r++;
+    A.range_bounds[r] = p->ns;
+  }
+  A.n_ranges = r;
+  A.tiles_x = (p->nx + TPT_TILE - 1) / TPT_TILE;
+  A.tiles_y = (p->ny + TPT_TILE - 1) / TPT_TILE;
+  A.part_index = p->part_index;
+  A.part_count = p->part_count;
+  long long n_tiles = (long long)A.tiles_x * A.tiles_y;
+  long long local_tiles = (n_tiles - p->part_index + p->part_count - 1) / p->part_count;
+  if (local_tiles < 0) local_tiles = 0;
+  A.n_bins = (unsigned long long)local_tiles * TPT_TILE * TPT_TILE * (unsigned long long)A.n_ranges;
+  if (A.n_bins >= (1ULL << 32)) return fail(TPT_ERR_UNSUPPORTED, "too many bins for one launch");
+  plan.npix = (size_t)p->nx * p->ny;
+  R.n_ranges = A.n_ranges;
+  R.npix = (int)plan.npix;
+  R.ns = p->ns;
+  R.slices = slices;
+  R.per_slice = per_slice;
+  return TPT_OK;
+}
+
+int run_plan(tpt_scene *s, Plan &plan, bool want_sum, bool want_rgb8, bool want_slices) {
+  CK(cudaSetDevice(s->device));
+  RenderArgs &A = plan.args;
+  ResolveArgs &R = plan.res;
+  int rc;
+  size_t acc_want = (size_t)A.n_ranges * plan.npix * 3 * sizeof(float);
+  if ((rc = ensure((void **)&s->d_acc, s->acc_bytes, acc_want)) != TPT_OK) return rc;
+  size_t sum_want = (size_t)R.slices * plan.npix * 3 * sizeof(float);
+  if ((rc = ensure((void **)&s->d_sum, s->sum_bytes, sum_want)) != TPT_OK) return rc;
+  if ((rc = ensure((void **)&s->d_rgb8, s->rgb8_bytes, plan.npix * 3)) != TPT_OK) return rc;
+  if ((rc = ensure((void **)&s->d_rgb8_slices, s->rgb8_slices_bytes, (size_t)R.slices * plan.npix * 3)) != TPT_OK) return rc;
+  A.acc = s->d_acc;
+  A.counters = s->d_counters;
+  R.acc = s->d_acc;
+  R.sum_rgb = s->d_sum;
+  R.rgb8 = s->d_rgb8;
+  R.rgb8_slices = want_slices ? s->d_rgb8_slices : nullptr;
+  (void)want_sum;
+  (void)want_rgb8;
+
+  size_t smem = s->use_smem ? s->blob_bytes : 0;
+  int bps = 0;
+  CK(plan.parity ? mega_occupancy_parity(s->use_smem, smem, &bps) : mega_occupancy_fast(s->use_smem, smem, &bps));
+  if (bps < 1) return fail(TPT_ERR_CUDA, "megakernel does not fit on an SM");
+  plan.blocks_per_sm = bps;
+  plan.blocks = bps * s->prop.multiProcessorCount;
+
+  CK(cudaMemsetAsync(s->d_counters, 0, 8 * sizeof(unsigned long long), s->stream));
+  CK(cudaMemsetAsync(s->d_acc, 0, acc_want, s->stream));
+  CK(cudaEventRecord(s->ev[0], s->stream));
+  CK(plan.parity ? launch_mega_parity(A, s->use_smem, plan.blocks, s->stream)
+                 : launch_mega_fast(A, s->use_smem, plan.blocks, s->stream));
+  CK(cudaEventRecord(s->ev[1], s->stream));
+  int rb = (int)((plan.npix + 255) / 256);
+  resolve_kernel<<<rb, 256, 0, s->stream>>>(R);
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(s->ev[2], s->stream));
+  CK(cudaStreamSynchronize(s->stream));
+  unsigned long long c[4];
+  CK(cudaMemcpy(c, s->d_counters, sizeof(c), cudaMemcpyDeviceToHost));
+  float ms_render = 0, ms_resolve = 0;
+  CK(cudaEventElapsedTime(&ms_render, s->ev[0], s->ev[1]));
+  CK(cudaEventElapsedTime(&ms_resolve, s->ev[1], s->ev[2]));
+  tpt_stats &st = s->stats;
+  std::memset(&st, 0, sizeof(st));
+  st.paths = c[3];
+  st.rays = c[1];
+  st.nan_samples = c[2];
+  st.render_ms = ms_render;
+  st.resolve_ms = ms_resolve;
+  st.kernel_launches = 2;
+  st.sm_count = s->prop.multiProcessorCount;
+  st.blocks = plan.blocks;
+  st.threads_per_block = TPT_MEGA_THREADS;
+  st.h2d_bytes = sizeof(RenderArgs) + sizeof(ResolveArgs);
+  s->last_nx = A.nx;
+  s->last_ny = A.ny;
+  s->last_slices = R.slices;
+  return TPT_OK;
+}
+
+int fetch(tpt_scene *s, tpt_image *out) {
+  if (!out) return TPT_OK;
+  CK(cudaSetDevice(s->device));
+  size_t npix = (size_t)s->last_nx * s->last_ny;
+  if (npix == 0) return fail(TPT_ERR_INVALID, "nothing rendered yet");
+  double t0 = now_ms();
+  uint64_t bytes = 0;
+  if (out->sum_rgb) {
+    size_t b = (size_t)s->last_slices * npix * 3 * sizeof(float);
+    CK(cudaMemcpy(out->sum_rgb, s->d_sum, b, cudaMemcpyDeviceToHost));
+    bytes += b;
+  }
+  if (out->rgb8) {
+    CK(cudaMemcpy(out->rgb8, s->d_rgb8, npix * 3, cudaMemcpyDeviceToHost));
+    bytes += npix * 3;
+  }
+  if (out->rgb8_slices) {
+    size_t b = (size_t)s->last_slices * npix * 3;
+    CK(cudaMemcpy(out->rgb8_slices, s->d_rgb8_slices, b, cudaMemcpyDeviceToHost));
+    bytes += b;
+  }
+  s->stats.d2h_ms = now_ms() - t0;
+  s->stats.d2h_bytes = bytes;
+  return TPT_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int tpt_api_version(void) { return TPT_API_VERSION; }
+
+int tpt_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+const char *tpt_last_error(void) { return g_error.c_str(); }
+
+int tpt_scene_create(const tpt_scene_desc *d, int device, tpt_scene **out) {
+  if (!out) return fail(TPT_ERR_INVALID, "null out pointer");
+  *out = nullptr;
+  int depth = 0;
+  int rc = validate_desc(d, depth);
+  if (rc != TPT_OK) return rc;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(TPT_ERR_NO_DEVICE, "no CUDA device available (this library has no CPU path)");
+  }
+  if (device < 0 || device >= ndev) return fail(TPT_ERR_INVALID, "device ordinal out of range");
+  CK(cudaSetDevice(device));
+  tpt_scene *s = new tpt_scene();
+  s->device = device;
+  CK(cudaGetDeviceProperties(&s->prop, device));
+  if (s->prop.major < 10) {
+    delete s;
+    return fail(TPT_ERR_NO_DEVICE, "device is not sm_100-class; kernels are built for sm_100a only");
+  }
+  CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+  for (auto &ev : s->ev) CK(cudaEventCreate(&ev));
+
+  // ---- blob: the C structs back to back, each table padded to 16 bytes ----
+  std::vector<unsigned char> blob;
+  SceneLayout &L = s->layout;
+  auto words = [&]() { return (int)(blob.size() / 16); };
+  L.off_nodes = words();
+  append(blob, d->nodes, d->n_nodes);
+  L.off_prims = words();
+  append(blob, d->prims, d->n_prims);
+  L.off_chains = words();
+  {
+    std::vector<int32_t> padded((size_t)d->n_chains * 4, 0);
+    for (int i = 0; i < d->n_chains; i++) {
+      padded[4 * i] = d->chains[i].first_op;
+      padded[4 * i + 1] = d->chains[i].n_ops;
+    }
+    append(blob, padded.data(), padded.size());
+  }
+  L.off_ops = words();
+  append(blob, d->xform_ops, d->n_xform_ops);
+  L.off_mats = words();
+  append(blob, d->materials, d->n_materials);
+  L.off_texs = words();
+  append(blob, d->textures, d->n_textures);
+  L.off_lights = words();
+  append(blob, d->lights, d->n_lights);
+  L.off_perlin = words();
+  if (d->perlin) {
+    std::vector<float> rv(256 * 4, 0.f);
+    for (int i = 0; i < 256; i++)
+      for (int c = 0; c < 3; c++) rv[4 * i + c] = d->perlin->ranvec[i][c];
+    append(blob, rv.data(), rv.size());
+    append(blob, d->perlin->perm_x, 256);
+    append(blob, d->perlin->perm_y, 256);
+    append(blob, d->perlin->perm_z, 256);
+  }
+  L.blob_words = words();
+  L.n_nodes = d->n_nodes;
+  L.n_prims = d->n_prims;
+  L.n_lights = d->n_lights;
+  L.background = d->background;
+  s->has_lights = d->n_lights > 0;
+  s->blob_bytes = blob.size();
+  CK(cudaMalloc((void **)&s->d_blob, blob.size()));
+  CK(cudaMemcpy(s->d_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+  L.blob_global = s->d_blob;
+  s->use_smem = blob.size() <= 64 * 1024;
+
+  // ---- image textures: RGB -> RGBA8 cudaArray, point sampling, clamp, unnormalised coords ----
+  for (int i = 0; i < d->n_images; i++) {
+    const tpt_image_desc &im = d->images[i];
+    std::vector<uchar4> rgba((size_t)im.width * im.height);
+    for (size_t k = 0; k < rgba.size(); k++)
+      rgba[k] = make_uchar4(im.rgb[3 * k], im.rgb[3 * k + 1], im.rgb[3 * k + 2], 255);
+    cudaChannelFormatDesc fmt = cudaCreateChannelDesc<uchar4>();
+    cudaArray_t arr;
+    CK(cudaMallocArray(&arr, &fmt, im.width, im.height));
+    CK(cudaMemcpy2DToArray(arr, 0, 0, rgba.data(), (size_t)im.width * 4, (size_t)im.width * 4, im.height,
+                           cudaMemcpyHostToDevice));
+    cudaResourceDesc rd{};
+    rd.resType = cudaResourceTypeArray;
+    rd.res.array.array = arr;
+    cudaTextureDesc td{};
+    td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
+    td.filterMode = cudaFilterModePoint;
+    td.readMode = cudaReadModeElementType;
+    td.normalizedCoords = 0;
+    cudaTextureObject_t tex;
+    CK(cudaCreateTextureObject(&tex, &rd, &td, nullptr));
+    s->arrays.push_back(arr);
+    s->textures.push_back(tex);
+    L.images[i] = tex;
+    L.image_w[i] = im.width;
+    L.image_h[i] = im.height;
+  }
+  CK(cudaMalloc((void **)&s->d_counters, 8 * sizeof(unsigned long long)));
+  s->stats.h2d_bytes = blob.size();
+  *out = s;
+  return TPT_OK;
+}
+
+void tpt_scene_destroy(tpt_scene *s) {
+  if (!s) return;
+  cudaSetDevice(s->device);
+  for (auto t : s->textures) cudaDestroyTextureObject(t);
+  for (auto a : s->arrays) cudaFreeArray(a);
+  cudaFree(s->d_blob);
+  cudaFree(s->d_acc);
+  cudaFree(s->d_counters);
+  cudaFree(s->d_sum);
+  cudaFree(s->d_rgb8);
+  cudaFree(s->d_rgb8_slices);
+  for (auto ev : s->ev)
+    if (ev) cudaEventDestroy(ev);
+  if (s->stream) cudaStreamDestroy(s->stream);
+  delete s;
+}
+
+int tpt_intersect_batch(const tpt_scene *cs, const tpt_ray *rays, size_t n, float tmin, float tmax, int mode,
+                        tpt_hit *out) {
+  tpt_scene *s = const_cast<tpt_scene *>(cs);
+  if (!s || (!rays && n) || (!out && n)) return fail(TPT_ERR_INVALID, "null argument");
+  if (mode != TPT_MODE_PARITY && mode != TPT_MODE_FAST) return fail(TPT_ERR_INVALID, "unknown mode");
+  if (n == 0) return TPT_OK;
+  static_assert(sizeof(tpt_ray) == 28, "tpt_ray layout");
+  CK(cudaSetDevice(s->device));
+  float *d_rays = nullptr;
+  tpt_hit *d_out = nullptr;
+  CK(cudaMalloc((void **)&d_rays, n * sizeof(tpt_ray)));
+  CK(cudaMalloc((void **)&d_out, n * sizeof(tpt_hit)));
+  CK(cudaMemcpyAsync(d_rays, rays, n * sizeof(tpt_ray), cudaMemcpyHostToDevice, s->stream));
+  IntersectArgs A;
+  A.scene = s->layout;
+  A.rays = d_rays;
+  A.n = n;
+  A.tmin = tmin;
+  A.tmax = tmax;
+  A.out = d_out;
+  cudaError_t e = mode == TPT_MODE_PARITY ? launch_intersect_parity(A, s->use_smem, s->stream)
+                                          : launch_intersect_fast(A, s->use_smem, s->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, n * sizeof(tpt_hit), cudaMemcpyDeviceToHost, s->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+  cudaFree(d_rays);
+  cudaFree(d_out);
+  if (e != cudaSuccess) return cuda_fail(e, "intersect batch");
+  return TPT_OK;
+}
+
+int tpt_render_device(tpt_scene *s, const tpt_camera *cam, const tpt_render_params *p) {
+  Plan plan;
+  int rc = make_plan(s, cam, p, plan);
+  if (rc != TPT_OK) return rc;
+  double t0 = now_ms();
+  rc = run_plan(s, plan, true, true, true);
+  if (rc == TPT_OK) s->stats.wall_ms = now_ms() - t0;
+  return rc;
+}
+
+int tpt_render_fetch(tpt_scene *s, tpt_image *out) {
+  if (!s) return fail(TPT_ERR_INVALID, "null scene");
+  return fetch(s, out);
+}
+
+int tpt_render(tpt_scene *s, const tpt_camera *cam, const tpt_render_params *p, tpt_image *out) {
+  Plan plan;
+  int rc = make_plan(s, cam, p, plan);
+  if (rc != TPT_OK) return rc;
+  double t0 = now_ms();
+  rc = run_plan(s, plan, out && out->sum_rgb, out && out->rgb8, out && out->rgb8_slices);
+  if (rc != TPT_OK) return rc;
+  rc = fetch(s, out);
+  s->stats.wall_ms = now_ms() - t0;
+  return rc;
+}
+
+int tpt_get_stats(const tpt_scene *s, tpt_stats *out) {
+  if (!s || !out) return fail(TPT_ERR_INVALID, "null argument");
+  *out = s->stats;
+  return TPT_OK;
+}
+
+int tpt_debug_philox(int device, const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(TPT_ERR_NO_DEVICE, "no CUDA device available");
+  }
+  CK(cudaSetDevice(device));
+  uint32_t *d = nullptr;
+  CK(cudaMalloc((void **)&d, 16));
+  cudaError_t e = launch_philox_probe(ctr, key, d, 0);
+  if (e == cudaSuccess) e = cudaMemcpy(out, d, 16, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  if (e != cudaSuccess) return cuda_fail(e, "philox probe");
+  return TPT_OK;
+}
+
+int tpt_debug_texture(const tpt_scene *cs, int texture, const float *uvp, size_t n, int mode, float *out_rgb) {
+  tpt_scene *s = const_cast<tpt_scene *>(cs);
+  if (!s || !uvp || !out_rgb) return fail(TPT_ERR_INVALID, "null argument");
+  if (n == 0) return TPT_OK;
+  CK(cudaSetDevice(s->device));
+  float *d_in = nullptr, *d_out = nullptr;
+  CK(cudaMalloc((void **)&d_in, n * 5 * sizeof(float)));
+  CK(cudaMalloc((void **)&d_out, n * 3 * sizeof(float)));
+  CK(cudaMemcpy(d_in, uvp, n * 5 * sizeof(float), cudaMemcpyHostToDevice));
+  TextureProbeArgs A;
+  A.scene = s->layout;
+  A.texture = texture;
+  A.uvp = d_in;
+  A.n = n;
+  A.out = d_out;
+  cudaError_t e = mode == TPT_MODE_PARITY ? launch_texture_probe_parity(A, s->stream)
+                                          : launch_texture_probe_fast(A, s->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+  if (e == cudaSuccess) e = cudaMemcpy(out_rgb, d_out, n * 3 * sizeof(float), cudaMemcpyDeviceToHost);
+  cudaFree(d_in);
+  cudaFree(d_out);
+  if (e != cudaSuccess) return cuda_fail(e, "texture probe");
+  return TPT_OK;
+}
+
+} // extern "C"

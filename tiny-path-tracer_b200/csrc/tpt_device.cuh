@@ -1,0 +1,937 @@
+// csrc/tpt_device.cuh -- device side of the path-tracing core (sm_100a), shared by the
+// megakernel, the wavefront kernels and the intersect-batch kernel.
+//
+// Everything is templated on PAR:
+//   PAR = true  (TPT_MODE_PARITY): the reference's arithmetic, operation by operation -- fp64
+//         exactly where the C++ expression promotes to double, IEEE div/sqrt, no FMA contraction
+//         (the parity translation unit is compiled with -fmad=false), the reference's
+//         comparison forms (NaN behaviour included), the un-shrunk t_max BVH walk with its tie
+//         rules.  Each function cites the reference lines it restates.
+//   PAR = false (TPT_MODE_FAST): the same estimator in fp32 with FMA / fast intrinsics and a
+//         culled stackless traversal.
+// Both consume the SAME Philox stream in the SAME draw order, so a fast render is comparable
+// sample by sample with a parity render (and with the reference under the injected stream).
+#pragma once
+#include <cfloat>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "tpt.h"
+
+namespace tptd {
+
+#define TPT_DEV __device__ __forceinline__
+#define TPT_MAX_FRAMES 32
+#define TPT_MAX_IMAGES 8
+#define TPT_MAX_RANGES 64
+
+// ------------------------------------------------------------------------------------------
+// Scene view: one contiguous blob of 16-byte words (shared memory when it fits, else global),
+// laid out exactly as the C structs of include/tpt.h.
+// ------------------------------------------------------------------------------------------
+struct SceneLayout { // host-computed, lives in kernel parameter (constant) space
+  const float4 *blob_global;
+  int blob_words; // float4 count
+  int off_nodes, off_prims, off_chains, off_ops, off_mats, off_texs, off_lights, off_perlin;
+  int n_nodes, n_prims, n_lights, background;
+  cudaTextureObject_t images[TPT_MAX_IMAGES];
+  int image_w[TPT_MAX_IMAGES], image_h[TPT_MAX_IMAGES];
+};
+
+struct SceneView {
+  const float4 *blob;   // shared-memory copy when it fits, else the global blob
+  const SceneLayout *L; // offsets / counts / texture objects (constant bank)
+};
+
+struct V3 {
+  float x, y, z;
+};
+TPT_DEV V3 mk(float x, float y, float z) { return V3{x, y, z}; }
+TPT_DEV V3 operator+(V3 a, V3 b) { return mk(a.x + b.x, a.y + b.y, a.z + b.z); }
+TPT_DEV V3 operator-(V3 a, V3 b) { return mk(a.x - b.x, a.y - b.y, a.z - b.z); }
+TPT_DEV V3 operator*(V3 a, V3 b) { return mk(a.x * b.x, a.y * b.y, a.z * b.z); }
+TPT_DEV V3 operator*(V3 a, float s) { return mk(a.x * s, a.y * s, a.z * s); }
+TPT_DEV V3 operator*(float s, V3 a) { return mk(a.x * s, a.y * s, a.z * s); }
+TPT_DEV V3 operator/(V3 a, float s) { return mk(a.x / s, a.y / s, a.z / s); }
+TPT_DEV V3 operator-(V3 a) { return mk(-a.x, -a.y, -a.z); }
+// headers/vec3.h:77-84: ((x*x + y*y) + z*z), no contraction in the parity TU
+TPT_DEV float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+TPT_DEV V3 cross(V3 a, V3 b) {
+  return mk(a.y * b.z - b.y * a.z, a.z * b.x - b.z * a.x, a.x * b.y - b.x * a.y);
+}
+TPT_DEV float sqlen(V3 a) { return a.x * a.x + a.y * a.y + a.z * a.z; }
+TPT_DEV float length(V3 a) { return sqrtf(sqlen(a)); } // headers/vec3.h:44-46 (std::sqrt(float))
+template <bool PAR> TPT_DEV V3 unit(V3 a) {         // headers/vec3.h:143-144: v / v.length()
+  if (PAR) return a / length(a);
+  float inv = rsqrtf(sqlen(a));
+  return a * inv;
+}
+
+struct Ray {
+  V3 o, d;
+  float time;
+};
+
+// ------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al., SC'11), counter = (pixel, sample, stage, block),
+// key = (seed_lo, seed_hi); four 24-bit uniforms per block, generated lazily.
+// stage 0 = camera draws (main.cpp:121-124), stage d+1 = draws of color() at depth d.
+// ------------------------------------------------------------------------------------------
+TPT_DEV void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                           uint32_t k1, uint32_t out[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0;
+    c1 = lo1;
+    c2 = n2;
+    c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  out[0] = c0;
+  out[1] = c1;
+  out[2] = c2;
+  out[3] = c3;
+}
+
+struct Rng {
+  uint32_t k0, k1, pixel, sample, stage, ndraw;
+  uint32_t b0, b1, b2, b3;
+  TPT_DEV void begin(uint32_t seed_lo, uint32_t seed_hi, uint32_t pix, uint32_t smp) {
+    k0 = seed_lo;
+    k1 = seed_hi;
+    pixel = pix;
+    sample = smp;
+    stage = 0;
+    ndraw = 0;
+  }
+  TPT_DEV void set_stage(uint32_t s) {
+    stage = s;
+    ndraw = 0;
+  }
+  // next uniform in [0,1): (x >> 8) * 2^-24, exactly representable in fp32
+  TPT_DEV float next() {
+    uint32_t lane = ndraw & 3u;
+    if (lane == 0) {
+      uint32_t o[4];
+      philox4x32_10(pixel, sample, stage, ndraw >> 2, k0, k1, o);
+      b0 = o[0];
+      b1 = o[1];
+      b2 = o[2];
+      b3 = o[3];
+    }
+    uint32_t x = lane == 0 ? b0 : (lane == 1 ? b1 : (lane == 2 ? b2 : b3));
+    ndraw++;
+    return (float)(x >> 8) * 5.9604644775390625e-8f;
+  }
+};
+
+// ------------------------------------------------------------------------------------------
+// Transform chains: translate / rotate_y wrappers between the root and a node, outermost first
+// ------------------------------------------------------------------------------------------
+struct XRay { // the ray expressed in the space of `chain`
+  V3 o, d;
+  V3 inv; // FAST only: 1/d
+  int chain;
+};
+
+template <bool PAR> TPT_DEV void to_chain(const SceneView &S, const Ray &r, int chain, XRay &x) {
+  if (x.chain == chain) return;
+  V3 o = r.o, d = r.d;
+  if (chain != 0) {
+    float4 c = S.blob[S.L->off_chains + chain];
+    int first = __float_as_int(c.x), n = __float_as_int(c.y);
+    for (int i = 0; i < n; i++) {
+      float4 op = S.blob[S.L->off_ops + first + i];
+      if (__float_as_int(op.x) == TPT_XF_TRANSLATE) {
+        // headers/rect_box.h:89: moved_r(origin - offset_, direction)
+        o = o - mk(op.y, op.z, op.w);
+      } else {
+        // src/rect_box.cc:175-179: x' = cos*x - sin*z ; z' = sin*x + cos*z (origin and direction)
+        float s = op.y, co = op.z;
+        float ox = co * o.x - s * o.z, oz = s * o.x + co * o.z;
+        float dx = co * d.x - s * d.z, dz = s * d.x + co * d.z;
+        o.x = ox;
+        o.z = oz;
+        d.x = dx;
+        d.z = dz;
+      }
+    }
+  }
+  x.o = o;
+  x.d = d;
+  x.chain = chain;
+  if (!PAR) x.inv = mk(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+}
+
+// hit point / normal back to world space: wrappers unwind innermost first
+// (src/rect_box.cc:185-189 then headers/rect_box.h:91)
+TPT_DEV void from_chain(const SceneView &S, int chain, V3 &p, V3 &n) {
+  if (chain == 0) return;
+  float4 c = S.blob[S.L->off_chains + chain];
+  int first = __float_as_int(c.x), cnt = __float_as_int(c.y);
+  for (int i = cnt - 1; i >= 0; i--) {
+    float4 op = S.blob[S.L->off_ops + first + i];
+    if (__float_as_int(op.x) == TPT_XF_TRANSLATE) {
+      p = p + mk(op.y, op.z, op.w);
+    } else {
+      float s = op.y, co = op.z;
+      float px = co * p.x + s * p.z, pz = -s * p.x + co * p.z;
+      float nx = co * n.x + s * n.z, nz = -s * n.x + co * n.z;
+      p.x = px;
+      p.z = pz;
+      n.x = nx;
+      n.z = nz;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// AABB slab test. PAR: src/aabb.cc:3-19 verbatim (1.0f/d per axis, swap on negative, ternary
+// updates so NaN keeps the old bound, reject on tmin > tmax).
+// ------------------------------------------------------------------------------------------
+template <bool PAR>
+TPT_DEV bool aabb_hit(const XRay &x, float4 lo, float4 hi, float tmin, float tmax) {
+  if (PAR) {
+    const float o[3] = {x.o.x, x.o.y, x.o.z}, d[3] = {x.d.x, x.d.y, x.d.z};
+    const float mn[3] = {lo.x, lo.y, lo.z}, mx[3] = {hi.x, hi.y, hi.z};
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      float inv_d = 1.0f / d[i];
+      float t0 = (mn[i] - o[i]) * inv_d;
+      float t1 = (mx[i] - o[i]) * inv_d;
+      if (inv_d < 0.0f) {
+        float t = t0;
+        t0 = t1;
+        t1 = t;
+      }
+      tmin = t0 > tmin ? t0 : tmin;
+      tmax = t1 < tmax ? t1 : tmax;
+      if (tmin > tmax) return false;
+    }
+    return true;
+  } else {
+    float ax = (lo.x - x.o.x) * x.inv.x, bx = (hi.x - x.o.x) * x.inv.x;
+    float ay = (lo.y - x.o.y) * x.inv.y, by = (hi.y - x.o.y) * x.inv.y;
+    float az = (lo.z - x.o.z) * x.inv.z, bz = (hi.z - x.o.z) * x.inv.z;
+    float t0 = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), tmin));
+    float t1 = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), tmax));
+    return t0 <= t1;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Primitive tests: return true and the accepted t. `incl` semantics are the primitive's own:
+// rects accept t_min <= t <= t_max (src/rect_box.cc:11,55,78), spheres t_min < t < t_max
+// (src/sphere.cc:24,33).
+// ------------------------------------------------------------------------------------------
+TPT_DEV V3 moving_center(float4 a, float4 b, float4 c, float time) {
+  // headers/sphere.h:28-31: center0 + (time - time0)/(time1 - time0) * (center1 - center0)
+  float f = (time - b.w) / (c.x - b.w);
+  V3 c0 = mk(a.x, a.y, a.z), c1 = mk(b.x, b.y, b.z);
+  return c0 + f * (c1 - c0);
+}
+
+template <bool PAR>
+TPT_DEV bool sphere_test(V3 center, float radius, const XRay &x, float tmin, float tmax, float &t) {
+  // src/sphere.cc:15-41
+  V3 oc = x.o - center;
+  float a = dot(x.d, x.d);
+  float b = 2.0f * dot(x.d, oc);
+  float c = dot(oc, oc) - radius * radius;
+  float disc = b * b - 4 * a * c;
+  if (disc > 0) {
+    if (PAR) {
+      // `sqrt` (unqualified) and the division are evaluated in double, rounded once to float
+      double sq = sqrt((double)disc);
+      float temp = (float)((-(double)b - sq) / (double)(2 * a));
+      if (temp < tmax && temp > tmin) {
+        t = temp;
+        return true;
+      }
+      temp = (float)((-(double)b + sq) / (double)(2 * a));
+      if (temp < tmax && temp > tmin) {
+        t = temp;
+        return true;
+      }
+    } else {
+      float sq = sqrtf(disc);
+      float inv2a = 0.5f / a;
+      float temp = (-b - sq) * inv2a;
+      if (temp < tmax && temp > tmin) {
+        t = temp;
+        return true;
+      }
+      temp = (-b + sq) * inv2a;
+      if (temp < tmax && temp > tmin) {
+        t = temp;
+        return true;
+      }
+    }
+  }
+  return false;
+}
+
+// axis: 0 = xy_rect (plane z=k), 1 = xz_rect (y=k), 2 = yz_rect (x=k); p = a0,a1,b0,b1,k
+template <bool PAR>
+TPT_DEV bool rect_test(int axis, float4 p, float k, const XRay &x, float tmin, float tmax, float &t) {
+  float ok, dk, oa, da, ob, db;
+  if (axis == 0) {
+    ok = x.o.z; dk = x.d.z; oa = x.o.x; da = x.d.x; ob = x.o.y; db = x.d.y;
+  } else if (axis == 1) {
+    ok = x.o.y; dk = x.d.y; oa = x.o.x; da = x.d.x; ob = x.o.z; db = x.d.z;
+  } else {
+    ok = x.o.x; dk = x.d.x; oa = x.o.y; da = x.d.y; ob = x.o.z; db = x.d.z;
+  }
+  float tt = (k - ok) / dk;
+  if (tt > tmax || tt < tmin) return false;
+  float a = oa + tt * da;
+  float b = ob + tt * db;
+  if (a < p.x || a > p.y || b < p.z || b > p.w) return false;
+  t = tt;
+  return true;
+}
+
+template <bool PAR>
+TPT_DEV bool prim_test(const SceneView &S, int prim, const XRay &x, float time, float tmin,
+                       float tmax, float &t) {
+  const float4 *P = S.blob + S.L->off_prims + 4 * prim;
+  float4 h = P[0], a = P[1];
+  int kind = __float_as_int(h.x);
+  if (kind == TPT_PRIM_SPHERE) {
+    return sphere_test<PAR>(mk(a.x, a.y, a.z), a.w, x, tmin, tmax, t);
+  } else if (kind == TPT_PRIM_MOVING_SPHERE) {
+    float4 b = P[2], c = P[3];
+    return sphere_test<PAR>(moving_center(a, b, c, time), a.w, x, tmin, tmax, t);
+  } else {
+    float k = P[2].x;
+    return rect_test<PAR>(kind - TPT_PRIM_XY_RECT, a, k, x, tmin, tmax, t);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Closest hit.
+// PAR: exact emulation of the recursive reference walk on the pre-order node array with a small
+// frame stack. A frame is an open bvh_node or hitable_list:
+//   bvh_node::hit   (src/hitable.cc:63-90): box test with the incoming t_max, BOTH children get
+//                   that same t_max, results merged with `left.t < right.t ? left : right`
+//   hitable_list::hit (src/hitable_list.cc:38-51): children get closest_so_far, any success
+//                   replaces the record.
+// A virtual root LIST frame carries the caller's t_max.
+// FAST: stackless skip-pointer walk, t_max shrinks to the best hit, duplicate sub-trees skipped.
+// ------------------------------------------------------------------------------------------
+struct Frame {
+  float tmax_in, best_t;
+  int best_prim, end_list; // end index | (is_list << 31)
+};
+
+template <bool PAR>
+TPT_DEV bool closest_hit(const SceneView &S, const Ray &r, float tmin, float tmax, float &t_out,
+                         int &prim_out) {
+  XRay x;
+  x.chain = -1;
+  const float4 *N = S.blob + S.L->off_nodes;
+  const int n = S.L->n_nodes;
+  if (PAR) {
+    Frame fr[TPT_MAX_FRAMES];
+    int sp = 1;
+    fr[0].tmax_in = tmax;
+    fr[0].best_t = 0.f;
+    fr[0].best_prim = -1;
+    fr[0].end_list = n | (int)0x80000000;
+    int i = 0;
+    for (;;) {
+      // close finished groups, handing their result to the parent
+      while (sp > 1 && i == (fr[sp - 1].end_list & 0x7fffffff)) {
+        Frame f = fr[--sp];
+        if (f.best_prim >= 0) {
+          Frame &P = fr[sp - 1];
+          bool take = (P.end_list < 0) || (P.best_prim < 0) || !(P.best_t < f.best_t);
+          if (take) {
+            P.best_t = f.best_t;
+            P.best_prim = f.best_prim;
+          }
+        }
+      }
+      if (i >= n) break;
+      Frame &P = fr[sp - 1];
+      float ctx = (P.end_list < 0 && P.best_prim >= 0) ? P.best_t : P.tmax_in;
+      float4 n0 = N[2 * i], n1 = N[2 * i + 1];
+      int kind = __float_as_int(n0.w);
+      int chain = kind >> 16;
+      int k = kind & 0xff;
+      to_chain<PAR>(S, r, chain, x);
+      if (k == TPT_NODE_LEAF) {
+        float t;
+        int prim = __float_as_int(n1.w);
+        if (prim_test<PAR>(S, prim, x, r.time, tmin, ctx, t)) {
+          bool take = (P.end_list < 0) || (P.best_prim < 0) || !(P.best_t < t);
+          if (take) {
+            P.best_t = t;
+            P.best_prim = prim;
+          }
+        }
+        i++;
+      } else {
+        int end = __float_as_int(n1.w);
+        if (k == TPT_NODE_BVH && !aabb_hit<PAR>(x, n0, n1, tmin, ctx)) {
+          i = end;
+        } else {
+          Frame &F = fr[sp++];
+          F.tmax_in = ctx;
+          F.best_t = 0.f;
+          F.best_prim = -1;
+          F.end_list = end | (k == TPT_NODE_LIST ? (int)0x80000000 : 0);
+          i++;
+        }
+      }
+    }
+    t_out = fr[0].best_t;
+    prim_out = fr[0].best_prim;
+    return fr[0].best_prim >= 0;
+  } else {
+    float best = tmax;
+    int best_prim = -1;
+    int i = 0;
+    while (i < n) {
+      float4 n0 = N[2 * i], n1 = N[2 * i + 1];
+      int kind = __float_as_int(n0.w);
+      int k = kind & 0xff;
+      int payload = __float_as_int(n1.w);
+      if (kind & TPT_NODE_DUP) {
+        i = (k == TPT_NODE_LEAF) ? i + 1 : payload;
+        continue;
+      }
+      to_chain<PAR>(S, r, kind >> 16, x);
+      if (k == TPT_NODE_LEAF) {
+        float t;
+        if (prim_test<PAR>(S, payload, x, r.time, tmin, best, t)) {
+          best = t;
+          best_prim = payload;
+        }
+        i++;
+      } else {
+        i = aabb_hit<PAR>(x, n0, n1, tmin, best) ? i + 1 : payload;
+      }
+    }
+    t_out = best;
+    prim_out = best_prim;
+    return best_prim >= 0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// hit_record of the winning leaf, recomputed from (prim, t) with the leaf's own arithmetic
+// ------------------------------------------------------------------------------------------
+struct HitRec {
+  float t, u, v;
+  V3 p, n;
+  int mat, prim;
+};
+
+template <bool PAR> TPT_DEV float round_atan2(float y, float x) {
+  // std::atan2(float,float) -> atan2f. PAR evaluates in double and rounds once (closest
+  // reproducible stand-in for glibc's atan2f; differences are <= 1 ulp).
+  if (PAR) return (float)atan2((double)y, (double)x);
+  return atan2f(y, x);
+}
+template <bool PAR> TPT_DEV float round_asin(float x) {
+  if (PAR) return (float)asin((double)x);
+  return asinf(x);
+}
+
+// headers/utils.h:38-43
+template <bool PAR> TPT_DEV void get_uv_map(V3 p, float &u, float &v) {
+  if (PAR) {
+    u = (float)((double)round_atan2<PAR>(p.z, p.x) / (2 * 3.14159265358979323846));
+    v = (float)((double)round_asin<PAR>(p.y) / 3.14159265358979323846);
+  } else {
+    u = round_atan2<PAR>(p.z, p.x) * 0.15915494309189535f;
+    v = round_asin<PAR>(p.y) * 0.3183098861837907f;
+  }
+  u += 0.5f;
+  v += 0.5f;
+}
+
+template <bool PAR>
+TPT_DEV void fill_hit(const SceneView &S, const Ray &r, int prim, float t, bool want_uv, HitRec &h) {
+  const float4 *P = S.blob + S.L->off_prims + 4 * prim;
+  float4 hd = P[0], a = P[1];
+  int kind = __float_as_int(hd.x);
+  int chain = __float_as_int(hd.z);
+  int flags = __float_as_int(hd.w);
+  XRay x;
+  x.chain = -1;
+  to_chain<PAR>(S, r, chain, x);
+  h.t = t;
+  h.prim = prim;
+  h.mat = __float_as_int(hd.y);
+  h.p = x.o + t * x.d; // ray::point_at_parameter, headers/ray.h:13
+  h.u = 0.f;
+  h.v = 0.f;
+  if (kind == TPT_PRIM_SPHERE || kind == TPT_PRIM_MOVING_SPHERE) {
+    V3 c = mk(a.x, a.y, a.z);
+    V3 cn = c;
+    if (kind == TPT_PRIM_MOVING_SPHERE) cn = moving_center(a, P[2], P[3], r.time);
+    h.n = (h.p - cn) / a.w;                                 // src/sphere.cc:28,59
+    if (want_uv) get_uv_map<PAR>((h.p - c) / a.w, h.u, h.v); // src/sphere.cc:27,60 (center0_)
+  } else {
+    float k = P[2].x;
+    (void)k;
+    if (kind == TPT_PRIM_XY_RECT) { // src/rect_box.cc:13-22
+      h.u = (h.p.x - a.x) / (a.y - a.x);
+      h.v = (h.p.y - a.z) / (a.w - a.z);
+      h.n = mk(0, 0, 1);
+    } else if (kind == TPT_PRIM_XZ_RECT) { // src/rect_box.cc:57-66
+      h.u = (h.p.x - a.x) / (a.y - a.x);
+      h.v = (h.p.z - a.z) / (a.w - a.z);
+      h.n = mk(0, 1, 0);
+    } else { // src/rect_box.cc:80-89
+      h.u = (h.p.y - a.x) / (a.y - a.x);
+      h.v = (h.p.z - a.z) / (a.w - a.z);
+      h.n = mk(1, 0, 0);
+    }
+  }
+  if (flags & TPT_PRIM_FLIP) h.n = -h.n; // headers/rect_box.h:53 (negation commutes with rotate_y)
+  from_chain(S, chain, h.p, h.n);
+}
+
+// ------------------------------------------------------------------------------------------
+// Textures (src/texture.cc, src/utils.cc:160-225)
+// ------------------------------------------------------------------------------------------
+template <bool PAR> TPT_DEV float round_sin(float x) {
+  if (PAR) return (float)sin((double)x); // std::sin(float) -> sinf, correctly-rounded stand-in
+  return __sinf(x);
+}
+template <bool PAR> TPT_DEV float round_cos(float x) {
+  if (PAR) return (float)cos((double)x);
+  return __cosf(x);
+}
+
+template <bool PAR> TPT_DEV float perlin_fade(float t) {
+  // src/utils.cc:207-210: 6 t^5 - 15 t^4 + 10 t^3 with std::pow(float,int) -> double
+  if (PAR) {
+    double d = (double)t;
+    double d3 = d * d * d, d4 = d3 * d, d5 = d4 * d;
+    return (float)(6 * d5 - 15 * d4 + 10 * d3);
+  }
+  return t * t * t * (t * (t * 6.f - 15.f) + 10.f);
+}
+
+template <bool PAR> TPT_DEV float perlin_noise_at(const SceneView &S, V3 p) {
+  // src/utils.cc:160-191 + perlin_interpolate :205-225
+  float fx = floorf(p.x), fy = floorf(p.y), fz = floorf(p.z);
+  float u = p.x - fx, v = p.y - fy, w = p.z - fz;
+  int i = ((int)fx) & 255, j = ((int)fy) & 255, k = ((int)fz) & 255;
+  const float4 *ranvec = S.blob + S.L->off_perlin;
+  const int *perm = reinterpret_cast<const int *>(S.blob + S.L->off_perlin + 256);
+  float uu = perlin_fade<PAR>(u), vv = perlin_fade<PAR>(v), ww = perlin_fade<PAR>(w);
+  float accum = 0.0f;
+#pragma unroll
+  for (int a = 0; a < 2; a++)
+#pragma unroll
+    for (int b = 0; b < 2; b++)
+#pragma unroll
+      for (int c = 0; c < 2; c++) {
+        int idx = perm[(i + a) & 255] ^ perm[256 + ((j + b) & 255)] ^ perm[512 + ((k + c) & 255)];
+        float4 g = ranvec[idx];
+        V3 wv = mk(uu - a, vv - b, ww - c);
+        float wa = a * uu + (1 - a) * (1 - uu);
+        float wb = b * vv + (1 - b) * (1 - vv);
+        float wc = c * ww + (1 - c) * (1 - ww);
+        accum += wa * wb * wc * dot(mk(g.x, g.y, g.z), wv);
+      }
+  return fabsf(accum);
+}
+
+template <bool PAR> TPT_DEV float perlin_turb(const SceneView &S, V3 p) {
+  // src/utils.cc:193-203, depth 5
+  float accum = 0, weight = 1.0f;
+  V3 tmp = p;
+  for (int i = 0; i < 5; i++) {
+    accum += weight * perlin_noise_at<PAR>(S, tmp);
+    weight *= 0.5f;
+    tmp = tmp * 2.0f;
+  }
+  return fabsf(accum);
+}
+
+template <bool PAR> TPT_DEV V3 texture_value(const SceneView &S, int tex, float u, float v, V3 p) {
+  for (int guard = 0; guard < 8; guard++) {
+    float4 t0 = S.blob[S.L->off_texs + 2 * tex], t1 = S.blob[S.L->off_texs + 2 * tex + 1];
+    int kind = __float_as_int(t0.x);
+    if (kind == TPT_TEX_CONSTANT) return mk(t0.y, t0.z, t0.w);
+    if (kind == TPT_TEX_CHECKER) { // src/texture.cc:4-16
+      float s = round_sin<PAR>(10 * p.x) * round_sin<PAR>(10 * p.y) * round_sin<PAR>(10 * p.z);
+      tex = (s < 0.0f) ? __float_as_int(t1.x) : __float_as_int(t1.y);
+      continue;
+    }
+    if (kind == TPT_TEX_PERLIN) { // src/texture.cc:18-25
+      float scale = t1.z;
+      float s = round_sin<PAR>(scale * p.z + 10 * perlin_turb<PAR>(S, p));
+      float g = 0.5f * (1 + s);
+      return mk(g, g, g);
+    }
+    // TPT_TEX_IMAGE: src/texture.cc:27-42, nearest texel, clamp, /255.0f
+    int img = __float_as_int(t1.w);
+    int W = S.L->image_w[img], H = S.L->image_h[img];
+    int i = (int)(u * W);
+    int j = (int)((1 - v) * H);
+    if (i < 0) i = 0;
+    if (i > W - 1) i = W - 1;
+    if (j > H - 1) j = H - 1;
+    if (j < 0) j = 0;
+    uchar4 c = tex2D<uchar4>(S.L->images[img], (float)i, (float)j);
+    return mk((int)c.x / 255.0f, (int)c.y / 255.0f, (int)c.z / 255.0f);
+  }
+  return mk(0, 0, 0);
+}
+
+TPT_DEV bool texture_needs_uv(const SceneView &S, int tex) {
+  // only image textures read (u,v); checker children can be images
+  for (int guard = 0; guard < 4; guard++) {
+    float4 t0 = S.blob[S.L->off_texs + 2 * tex];
+    int kind = __float_as_int(t0.x);
+    if (kind == TPT_TEX_IMAGE) return true;
+    if (kind == TPT_TEX_CHECKER) return true; // conservative
+    return false;
+  }
+  return false;
+}
+
+// ------------------------------------------------------------------------------------------
+// Sampling helpers
+// ------------------------------------------------------------------------------------------
+struct Onb {
+  V3 u, v, w;
+};
+template <bool PAR> TPT_DEV Onb onb_from_w(V3 n) {
+  // src/utils.cc:437-450. `std::abs(normal.x()) > 0.9` compares in double.
+  Onb b;
+  b.w = n;
+  bool x_axis = PAR ? ((double)fabsf(n.x) > 0.9) : (fabsf(n.x) > 0.9f);
+  V3 tmp = x_axis ? mk(0, 1, 0) : mk(1, 0, 0);
+  b.v = unit<PAR>(cross(n, tmp));
+  b.u = cross(b.v, b.w);
+  return b;
+}
+TPT_DEV V3 onb_local(const Onb &b, float x, float y, float z) { return x * b.u + y * b.v + z * b.w; }
+
+#define TPT_PI_D 3.14159265358979323846
+#define TPT_PI_F 3.14159265358979323846f
+
+// src/utils.cc:427-435
+template <bool PAR> TPT_DEV V3 random_on_hemisphere(Rng &g) {
+  float r1 = g.next();
+  float r2 = g.next();
+  float phi = PAR ? (float)(2 * TPT_PI_D * (double)r1) : (2.f * TPT_PI_F) * r1;
+  float sr = sqrtf(r2);
+  float x, y;
+  if (PAR) {
+    x = round_cos<PAR>(phi) * sr;
+    y = round_sin<PAR>(phi) * sr;
+  } else {
+    float s, c;
+    __sincosf(phi, &s, &c);
+    x = c * sr;
+    y = s * sr;
+  }
+  float z = sqrtf(1 - r2);
+  return mk(x, y, z);
+}
+
+// src/utils.cc:21-27 (g++ evaluates the ctor arguments right to left: z, y, x)
+TPT_DEV V3 random_in_unit_sphere(Rng &g) {
+  V3 p;
+  do {
+    float z = g.next();
+    float y = g.next();
+    float x = g.next();
+    p = 2.0f * mk(x, y, z) - mk(1.0f, 1.0f, 1.0f);
+  } while (length(p) >= 1.0f);
+  return p;
+}
+
+// hitable_list::random -> xz_rect::random | sphere::random
+// (src/hitable_list.cc:33-36, src/rect_box.cc:39-43, src/sphere.cc:108-120)
+template <bool PAR> TPT_DEV V3 light_random(const SceneView &S, V3 origin, Rng &g) {
+  float pick = g.next();
+  int index = PAR ? (int)((double)pick * (double)S.L->n_lights) : (int)(pick * (float)S.L->n_lights);
+  float4 l0 = S.blob[S.L->off_lights + 2 * index], l1 = S.blob[S.L->off_lights + 2 * index + 1];
+  int kind = __float_as_int(l0.x);
+  if (kind == TPT_LIGHT_XZ_RECT) {
+    float x0 = l0.y, x1 = l0.z, z0 = l0.w, z1 = l1.x, k = l1.y;
+    float rz = g.next(); // third ctor argument first
+    float rx = g.next();
+    V3 pt;
+    if (PAR) {
+      pt = mk((float)((double)x0 + (double)rx * (double)(x1 - x0)), k,
+              (float)((double)z0 + (double)rz * (double)(z1 - z0)));
+    } else {
+      pt = mk(x0 + rx * (x1 - x0), k, z0 + rz * (z1 - z0));
+    }
+    return pt - origin;
+  } else if (kind == TPT_LIGHT_SPHERE) {
+    V3 c = mk(l0.y, l0.z, l0.w);
+    float radius = l1.x;
+    V3 direction = c - origin;
+    Onb uvw = onb_from_w<PAR>(unit<PAR>(direction));
+    float tmp = (radius * radius) / sqlen(c - origin);
+    float cmax = sqrtf(1 - tmp); // NaN when the origin is inside the sphere
+    float r1 = g.next();
+    float r2 = g.next();
+    float z = 1 + r2 * (cmax - 1);
+    float sq = sqrtf(1 - z * z);
+    float x, y;
+    if (PAR) {
+      x = (float)(cos(2 * TPT_PI_D * (double)r1) * (double)sq);
+      y = (float)(sin(2 * TPT_PI_D * (double)r1) * (double)sq);
+    } else {
+      float s, co;
+      __sincosf((2.f * TPT_PI_F) * r1, &s, &co);
+      x = co * sq;
+      y = s * sq;
+    }
+    return onb_local(uvw, x, y, z);
+  }
+  return mk(1, 0, 0); // hitable::random, headers/hitable.h:38
+}
+
+// hitable_list::pdf_value (src/hitable_list.cc:24-31) over xz_rect::pdf_value
+// (src/rect_box.cc:26-37) and sphere::pdf_value (src/sphere.cc:93-106)
+template <bool PAR> TPT_DEV float light_pdf(const SceneView &S, V3 origin, V3 dir) {
+  float weight = PAR ? (float)(1.0 / (double)S.L->n_lights) : 1.0f / (float)S.L->n_lights;
+  float sum = 0;
+  XRay x;
+  x.o = origin;
+  x.d = dir;
+  x.chain = 0;
+  for (int i = 0; i < S.L->n_lights; i++) {
+    float4 l0 = S.blob[S.L->off_lights + 2 * i], l1 = S.blob[S.L->off_lights + 2 * i + 1];
+    int kind = __float_as_int(l0.x);
+    float pdf = 0.0f;
+    if (kind == TPT_LIGHT_XZ_RECT) {
+      float t;
+      float4 p = make_float4(l0.y, l0.z, l0.w, l1.x);
+      if (rect_test<PAR>(1, p, l1.y, x, 0.0001f, FLT_MAX, t)) {
+        float area = fabsf((p.y - p.x) * (p.w - p.z));
+        float dist2 = sqlen(t * dir);
+        float cosine = fabsf(dot(dir, mk(0, 1, 0)) / length(dir));
+        pdf = dist2 / (cosine * area);
+      }
+    } else if (kind == TPT_LIGHT_SPHERE) {
+      float t;
+      V3 c = mk(l0.y, l0.z, l0.w);
+      float radius = l1.x;
+      if (sphere_test<PAR>(c, radius, x, 0.001f, FLT_MAX, t)) {
+        float tmp = (radius * radius) / sqlen(c - origin);
+        float cmax = sqrtf(1 - tmp);
+        float solid = PAR ? (float)(2 * TPT_PI_D * (double)(1 - cmax)) : (2.f * TPT_PI_F) * (1 - cmax);
+        pdf = isnan(solid) ? 0.0f : 1 / solid;
+      }
+    }
+    sum += weight * pdf;
+  }
+  return sum;
+}
+
+// ------------------------------------------------------------------------------------------
+// Optics (src/utils.cc:34-56)
+// ------------------------------------------------------------------------------------------
+TPT_DEV V3 reflect(V3 v, V3 n) { return v - 2 * dot(v, n) * n; }
+
+template <bool PAR> TPT_DEV bool refract(V3 v, V3 n, float ni_over_nt, V3 &refracted) {
+  V3 uv = unit<PAR>(v);
+  float dt = dot(uv, n);
+  float disc = PAR ? (float)(1.0 - (double)(ni_over_nt * ni_over_nt * (1 - dt * dt)))
+                   : 1.0f - ni_over_nt * ni_over_nt * (1 - dt * dt);
+  if (disc > 0) {
+    refracted = ni_over_nt * (uv - n * dt) - n * sqrtf(disc);
+    return true;
+  }
+  return false;
+}
+
+template <bool PAR> TPT_DEV float schlick(float cosine, float ref_index) {
+  float r0 = (1 - ref_index) / (1 + ref_index);
+  r0 = r0 * r0;
+  if (PAR) return (float)((double)r0 + (double)(1 - r0) * pow((double)(1 - cosine), 5.0));
+  float m = 1 - cosine;
+  float m2 = m * m;
+  return r0 + (1 - r0) * (m2 * m2 * m);
+}
+
+// ------------------------------------------------------------------------------------------
+// Camera (src/camera.cc:23-31) and pixel jitter (main.cpp:121-122)
+// ------------------------------------------------------------------------------------------
+struct CamView {
+  V3 origin, llc, vertical, horizontal, u, v, w;
+  float lens_radius, time0, time1;
+};
+
+template <bool PAR>
+TPT_DEV Ray camera_sample(const CamView &C, int i, int j, int nx, int ny, Rng &g) {
+  float r_u = g.next();
+  float r_v = g.next();
+  float s, t;
+  if (PAR) {
+    s = (float)(((double)(float)i + (double)r_u) / (double)(float)nx);
+    t = (float)(((double)(float)j + (double)r_v) / (double)(float)ny);
+  } else {
+    s = ((float)i + r_u) / (float)nx;
+    t = ((float)j + r_v) / (float)ny;
+  }
+  // random_in_unit_disk, src/utils.cc:13-19: vec3(drand_r(), drand_r(), 0) -> y drawn first
+  float px, py;
+  do {
+    float y = g.next();
+    float x = g.next();
+    px = 2.0f * x - 1.0f;
+    py = 2.0f * y - 1.0f;
+  } while (px * px + py * py >= 1.0f);
+  float rdx = C.lens_radius * px, rdy = C.lens_radius * py;
+  V3 offset = C.u * rdx + C.v * rdy;
+  Ray r;
+  if (C.time1 != C.time0) {
+    float rt = g.next();
+    r.time = PAR ? (float)((double)C.time0 + (double)rt * (double)(C.time1 - C.time0))
+                 : C.time0 + rt * (C.time1 - C.time0);
+  } else {
+    r.time = C.time0; // time0 + drand*0: the draw is the last of its stage, skipping it is exact
+  }
+  r.o = C.origin + offset;
+  r.d = C.llc + s * C.horizontal + t * C.vertical - C.origin - offset;
+  return r;
+}
+
+// ------------------------------------------------------------------------------------------
+// One bounce of color() (src/utils.cc:58-94), iterative form.
+// Path state: ray, throughput T (product of attenuation*scattering_pdf/pdf_value of the
+// diffuse bounces and attenuation of the specular ones), depth. Emission is non-zero only on
+// materials that never scatter (diffuse_light), so `emitted + w*color(next)` collapses to
+// "radiance = T * emitted at the terminal vertex"; a path whose T is 0-or-NaN in every
+// channel can stop: every continuation yields 0 after de_nan (headers/utils.h:100-109).
+// Returns true while the path continues.
+// ------------------------------------------------------------------------------------------
+struct PathState {
+  Ray ray;
+  V3 T;
+  int depth;
+};
+
+TPT_DEV bool dead_channel(float t) { return t == 0.0f || isnan(t); }
+
+template <bool PAR>
+TPT_DEV bool bounce(const SceneView &S, PathState &ps, Rng &g, int max_depth, float t_min, V3 &radiance) {
+  g.set_stage((uint32_t)ps.depth + 1u);
+  float t;
+  int prim;
+  if (!closest_hit<PAR>(S, ps.ray, t_min, FLT_MAX, t, prim)) {
+    if (S.L->background == TPT_BG_SKY) {
+      // the commented gradient src/utils.cc:87-90
+      V3 ud = unit<PAR>(ps.ray.d);
+      float tt = PAR ? (float)(((double)ud.y + 1.0) * 0.5) : (ud.y + 1.0f) * 0.5f;
+      V3 sky = 0.1f * ((1 - tt) * mk(1.0f, 1.0f, 1.0f) + tt * mk(0.5f, 0.7f, 1.0f));
+      radiance = ps.T * sky;
+    } else {
+      radiance = mk(0, 0, 0);
+    }
+    return false;
+  }
+  // tpt_material = {kind, texture, albedo[3], fuzz, ref_idx, pad}
+  const int mat = __float_as_int(S.blob[S.L->off_prims + 4 * prim].y);
+  const float4 m0 = S.blob[S.L->off_mats + 2 * mat];
+  const float4 m1 = S.blob[S.L->off_mats + 2 * mat + 1];
+  const int mkind = __float_as_int(m0.x);
+  const int mtex = __float_as_int(m0.y);
+  bool want_uv = (mkind == TPT_MAT_LAMBERTIAN || mkind == TPT_MAT_DIFFUSE_LIGHT) && texture_needs_uv(S, mtex);
+  HitRec h;
+  fill_hit<PAR>(S, ps.ray, prim, t, want_uv, h);
+
+  if (mkind == TPT_MAT_DIFFUSE_LIGHT) {
+    // src/material.cc:79-86: one-sided; base scatter() is false -> return emitted
+    if (dot(h.n, ps.ray.d) < 0)
+      radiance = ps.T * texture_value<PAR>(S, mtex, h.u, h.v, h.p);
+    else
+      radiance = mk(0, 0, 0);
+    return false;
+  }
+  if (mkind == TPT_MAT_ABSORBER || ps.depth >= max_depth) {
+    radiance = mk(0, 0, 0); // emitted == 0 for every scattering material
+    return false;
+  }
+  if (mkind == TPT_MAT_METAL) { // src/material.cc:88-98
+    V3 reflected = reflect(unit<PAR>(ps.ray.d), h.n);
+    V3 dir = reflected + m1.y * random_in_unit_sphere(g); // fuzz_
+    if (!(dot(dir, h.n) > 0)) {
+      radiance = mk(0, 0, 0);
+      return false;
+    }
+    ps.T = ps.T * mk(m0.z, m0.w, m1.x); // attenuation = albedo_, no emitted term (src/utils.cc:67-72)
+    ps.ray.o = h.p;
+    ps.ray.d = dir;
+  } else if (mkind == TPT_MAT_DIELECTRIC) { // src/material.cc:19-70
+    float ref_idx = m1.z;
+    V3 d = ps.ray.d;
+    V3 reflected = reflect(d, h.n);
+    V3 outward;
+    float ni_over_nt, cosine;
+    float ddn = dot(d, h.n);
+    if (ddn > 0) {
+      outward = -h.n;
+      ni_over_nt = ref_idx;
+      cosine = ddn / length(d);
+      cosine = sqrtf(1 - ref_idx * ref_idx * (1 - cosine * cosine));
+    } else {
+      outward = h.n;
+      ni_over_nt = PAR ? (float)(1.0 / (double)ref_idx) : 1.0f / ref_idx;
+      cosine = -ddn / length(d);
+    }
+    V3 refracted;
+    float reflect_prob;
+    if (refract<PAR>(d, outward, ni_over_nt, refracted))
+      reflect_prob = schlick<PAR>(cosine, ref_idx);
+    else
+      reflect_prob = 1.0f;
+    float xi = g.next();
+    ps.ray.o = h.p;
+    ps.ray.d = (xi < reflect_prob) ? reflected : refracted; // attenuation (1,1,1)
+  } else {
+    // lambertian: src/material.cc:3-17 + mixture sampling src/utils.cc:73-81
+    V3 atten = texture_value<PAR>(S, mtex, h.u, h.v, h.p);
+    Onb uvw = onb_from_w<PAR>(h.n);
+    V3 dir;
+    if (g.next() < 0.5f) {
+      dir = light_random<PAR>(S, h.p, g);
+    } else {
+      V3 l = random_on_hemisphere<PAR>(g);
+      dir = onb_local(uvw, l.x, l.y, l.z);
+    }
+    V3 udir = unit<PAR>(dir);
+    float lpdf = light_pdf<PAR>(S, h.p, dir);
+    float c1 = dot(udir, uvw.w);
+    float cpdf = c1 > 0 ? c1 : 0.0f; // cosine_pdf::value returns cos, not cos/pi
+    float pdf_value = PAR ? (float)(0.5 * (double)lpdf + 0.5 * (double)cpdf) : 0.5f * lpdf + 0.5f * cpdf;
+    float c2 = dot(h.n, udir);
+    float spdf;
+    if (c2 < 0)
+      spdf = 0;
+    else
+      spdf = PAR ? (float)((double)c2 / TPT_PI_D) : c2 * 0.3183098861837907f;
+    V3 w = (atten * spdf) / pdf_value;
+    ps.T = ps.T * w;
+    ps.ray.o = h.p;
+    ps.ray.d = dir;
+  }
+  ps.depth++;
+  if (dead_channel(ps.T.x) && dead_channel(ps.T.y) && dead_channel(ps.T.z)) {
+    radiance = mk(0, 0, 0);
+    return false;
+  }
+  return true;
+}
+
+} // namespace tptd

@@ -1,0 +1,50 @@
+// csrc/tpt_launch.h -- kernel argument blocks and the launcher entry points exported by the two
+// kernel translation units (parity / fast) to the C-ABI layer (tpt_api.cu).
+#pragma once
+#include "tpt_device.cuh"
+
+#define TPT_MEGA_THREADS 256
+
+namespace tptd {
+
+struct IntersectArgs {
+  SceneLayout scene;
+  const float *rays; // n x 7
+  size_t n;
+  float tmin, tmax;
+  tpt_hit *out;
+};
+
+struct RenderArgs {
+  SceneLayout scene;
+  CamView cam;
+  int nx, ny, ns, max_depth;
+  float t_min;
+  uint32_t seed_lo, seed_hi;
+  int n_ranges;                          // sample ranges per pixel (slices x sub-ranges)
+  int range_bounds[TPT_MAX_RANGES + 1];  // range r covers samples [bounds[r], bounds[r+1])
+  int tiles_x, tiles_y, part_index, part_count;
+  unsigned long long n_bins;             // local tiles x TILE^2 x n_ranges
+  float *acc;                            // [n_ranges][ny*nx][3] per-range radiance sums
+  unsigned long long *counters;          // [0] next bin, [1] rays, [2] NaN samples, [3] paths
+};
+
+struct TextureProbeArgs {
+  SceneLayout scene;
+  int texture;
+  const float *uvp; // n x 5
+  size_t n;
+  float *out; // n x 3
+};
+
+cudaError_t launch_intersect_parity(const IntersectArgs &A, bool smem, cudaStream_t st);
+cudaError_t launch_intersect_fast(const IntersectArgs &A, bool smem, cudaStream_t st);
+cudaError_t mega_occupancy_parity(bool smem, size_t smem_bytes, int *blocks_per_sm);
+cudaError_t mega_occupancy_fast(bool smem, size_t smem_bytes, int *blocks_per_sm);
+cudaError_t launch_mega_parity(const RenderArgs &A, bool smem, int blocks, cudaStream_t st);
+cudaError_t launch_mega_fast(const RenderArgs &A, bool smem, int blocks, cudaStream_t st);
+cudaError_t launch_texture_probe_parity(const TextureProbeArgs &A, cudaStream_t st);
+cudaError_t launch_texture_probe_fast(const TextureProbeArgs &A, cudaStream_t st);
+cudaError_t launch_philox_probe(const uint32_t ctr[4], const uint32_t key[2], uint32_t *d_out, cudaStream_t st);
+
+} // namespace tptd

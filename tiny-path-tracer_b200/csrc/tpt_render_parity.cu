@@ -1,0 +1,24 @@
+// csrc/tpt_render_parity.cu -- PARITY instantiation. Compiled with
+//   -fmad=false -prec-div=true -prec-sqrt=true -ftz=false
+// so every fp32/fp64 +,-,*,/,sqrt is a single correctly-rounded IEEE operation in source order,
+// like the reference's x86-64 -O3 build (no -march => no FMA contraction).
+#define TPT_PAR true
+#define TPT_SUFFIX parity
+#include "tpt_kernels.cuh"
+
+namespace tptd {
+__global__ void philox_probe_kernel(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                    uint32_t k1, uint32_t *out) {
+  uint32_t o[4];
+  philox4x32_10(c0, c1, c2, c3, k0, k1, o);
+  out[0] = o[0];
+  out[1] = o[1];
+  out[2] = o[2];
+  out[3] = o[3];
+}
+
+cudaError_t launch_philox_probe(const uint32_t ctr[4], const uint32_t key[2], uint32_t *d_out, cudaStream_t st) {
+  philox_probe_kernel<<<1, 1, 0, st>>>(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1], d_out);
+  return cudaGetLastError();
+}
+} // namespace tptd

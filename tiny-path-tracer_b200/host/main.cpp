@@ -1,0 +1,184 @@
+// host/main.cpp -- the driver, same flow as the reference's main.cpp:24-247:
+//   read ./config.ini (same keys, same defaults) -> echo it -> build the scene with the host
+//   classes -> camera -> light-sampling list -> [flatten + libtpt.so render on the GPU(s)]
+//   -> img.ppm (+ img_k.ppm bonus pictures) -> "time: X s" -> convert ... +append img.jpg
+// Only the bracketed step differs: it replaces the row-per-thread sample loop
+// (main.cpp:109-175) with the sm_100a core behind include/tpt.h.
+//
+// Additional, optional keys (absent => reference behaviour):
+//   [SCENE] name = cornell_box | sphere_cornell_box | random_scene | random_scene_list |
+//                  two_perlin_spheres | two_checker_spheres | light_spheres | earth
+//           background = black | sky        image = earthmap.ppm
+//   [GPU]   mode = fast | parity    kernel = mega | wavefront   seed = <u64>   gpus = <n>
+#include "tpt.h"
+#include "tpt_flatten.h"
+#include "tpt_image_io.h"
+#include "tpt_ini.h"
+#include "tpt_scene.h"
+
+#include <chrono>
+#include <fstream>
+#include <iostream>
+#include <thread>
+#include <vector>
+
+int main(int, char **) {
+  std::vector<std::string> filenames;
+  filenames.push_back("img.ppm");
+
+  std::ifstream config("config.ini");
+  // defaults of main.cpp:31-40
+  int nx = 400, ny = 200, ns = 10;
+  float aperture = 0.2f, time0 = 0.0f, time1 = 1.0f;
+  int sample_max_recurse_depth = 50;
+  float fov = 90.0f;
+  int allow_bonus_pic = 0, bonus_pic = 10;
+  std::string scene_name = "cornell_box", background = "black", image_file = "earthmap.jpg";
+  std::string mode = "fast", kernel = "mega";
+  unsigned long long seed = 0x5EEDULL;
+  int gpus = 1;
+
+  inipp::Ini<char> ini;
+  ini.parse(config);
+  inipp::extract(ini.sections["DEFAULT"]["width"], nx);
+  inipp::extract(ini.sections["DEFAULT"]["height"], ny);
+  inipp::extract(ini.sections["DEFAULT"]["sample"], ns);
+  inipp::extract(ini.sections["DEFAULT"]["recur_depth"], sample_max_recurse_depth);
+  inipp::extract(ini.sections["DEFAULT"]["fov"], fov);
+  inipp::extract(ini.sections["DEFAULT"]["bonus_pic"], bonus_pic);
+  inipp::extract(ini.sections["DEFAULT"]["allow_bonus_pic"], allow_bonus_pic);
+  inipp::extract(ini.sections["BLUR"]["aperture"], aperture);
+  inipp::extract(ini.sections["CAM_MOTION"]["start_time"], time0);
+  inipp::extract(ini.sections["CAM_MOTION"]["end_time"], time1);
+  if (ini.sections.count("SCENE")) {
+    inipp::extract(ini.sections["SCENE"]["name"], scene_name);
+    inipp::extract(ini.sections["SCENE"]["background"], background);
+    inipp::extract(ini.sections["SCENE"]["image"], image_file);
+  }
+  if (ini.sections.count("GPU")) {
+    inipp::extract(ini.sections["GPU"]["mode"], mode);
+    inipp::extract(ini.sections["GPU"]["kernel"], kernel);
+    inipp::extract(ini.sections["GPU"]["seed"], seed);
+    inipp::extract(ini.sections["GPU"]["gpus"], gpus);
+  }
+  ini.generate(std::cout);
+
+  std::cout << "<===========>" << std::endl;
+#ifdef DEBUG_MODE
+  std::cout << "IN DEBUG MODE" << std::endl;
+#else
+  std::cout << "IN RELEASE MODE" << std::endl;
+#endif
+  std::cout << "Threads num: " << std::thread::hardware_concurrency() << std::endl;
+  std::cout << "GPUs: " << tpt_device_count() << " (using " << gpus << ", " << mode << "/" << kernel
+            << ")" << std::endl;
+  std::cout << "<===========>" << std::endl;
+
+  if (allow_bonus_pic && (bonus_pic <= 0 || ns / bonus_pic <= 0)) {
+    // the reference divides by zero here (main.cpp:113,127): refuse instead
+    std::cerr << "sample must be >= bonus_pic when allow_bonus_pic is set" << std::endl;
+    return 2;
+  }
+
+  // ---- scene, camera, light list: host classes, as main.cpp:71-106 ----
+  hitable *world = nullptr;
+  vec3 lookfrom(0, 0, 800), lookat(0, 0, 0);
+  float dist_to_focus = 10.0f;
+  if (scene_name == "cornell_box") {
+    world = cornell_box();
+  } else {
+    // the alternatives the reference keeps commented out (main.cpp:71-84)
+    if (scene_name == "sphere_cornell_box") world = sphere_cornell_box();
+    else if (scene_name == "random_scene") world = random_scene();
+    else if (scene_name == "two_perlin_spheres") world = two_perlin_spheres();
+    else if (scene_name == "two_checker_spheres") world = two_checker_spheres();
+    else if (scene_name == "light_spheres") world = light_spheres();
+    else if (scene_name == "earth") {
+      int w, h, ch;
+      unsigned char *data = load_image_texture(image_file, w, h, ch);
+      if (!data) {
+        std::cerr << "cannot load " << image_file << std::endl;
+        return 2;
+      }
+      world = new sphere({0, 0, 0}, 3, new lambertian(new image_texture(data, w, h)));
+    } else {
+      std::cerr << "unknown scene " << scene_name << std::endl;
+      return 2;
+    }
+    if (scene_name != "sphere_cornell_box") {
+      lookfrom = vec3(13, 2, 3);
+      dist_to_focus = (lookfrom - lookat).length();
+    }
+  }
+  camera cam(lookfrom, lookat, vec3(0, 1, 0), fov, float(nx) / (float)ny, aperture, dist_to_focus,
+             time0, time1);
+
+  xz_rect light_shape(-100, 100, -150, -50, 298, nullptr);
+  sphere sphere_shape(vec3(120, -50, 40), 120, nullptr);
+  hitable *a[2] = {&light_shape, &sphere_shape};
+  hitable_list hlist(a, 2);
+
+  auto start = std::chrono::high_resolution_clock::now();
+
+  // ---- the replaced block: main.cpp:109-175 ----
+  tpt::FlatScene flat;
+  std::string err;
+  if (!tpt::flatten_scene(world, &hlist, background == "sky" ? TPT_BG_SKY : TPT_BG_BLACK, flat, err)) {
+    std::cerr << "flatten: " << err << std::endl;
+    return 3;
+  }
+  tpt_scene_desc desc = flat.desc();
+  tpt_scene *scene = nullptr;
+  if (tpt_scene_create(&desc, 0, &scene) != TPT_OK) {
+    std::cerr << "tpt_scene_create: " << tpt_last_error() << std::endl;
+    return 3;
+  }
+  tpt_camera cam_desc = tpt::make_camera_desc(cam);
+  tpt_render_params rp{};
+  rp.nx = nx;
+  rp.ny = ny;
+  rp.ns = ns;
+  rp.max_depth = sample_max_recurse_depth;
+  rp.slices = allow_bonus_pic ? bonus_pic : 1;
+  rp.mode = mode == "parity" ? TPT_MODE_PARITY : TPT_MODE_FAST;
+  rp.kernel = kernel == "wavefront" ? TPT_KERNEL_WAVEFRONT : TPT_KERNEL_MEGA;
+  rp.seed_lo = (uint32_t)seed;
+  rp.seed_hi = (uint32_t)(seed >> 32);
+  rp.t_min = 0.001f;
+  rp.part_index = 0;
+  rp.part_count = 1;
+  rp.device = 0;
+  rp.reserved[0] = gpus; // >1: in-process multi-GPU (static tile split + stealing)
+  std::vector<uint8_t> rgb8((size_t)nx * ny * 3);
+  std::vector<uint8_t> rgb8_slices(allow_bonus_pic ? (size_t)rp.slices * nx * ny * 3 : 0);
+  tpt_image img{};
+  img.rgb8 = rgb8.data();
+  img.rgb8_slices = allow_bonus_pic ? rgb8_slices.data() : nullptr;
+  if (tpt_render(scene, &cam_desc, &rp, &img) != TPT_OK) {
+    std::cerr << "tpt_render: " << tpt_last_error() << std::endl;
+    return 4;
+  }
+  tpt_stats st{};
+  tpt_get_stats(scene, &st);
+  std::cout << "gpu render: " << st.render_ms / 1000.0 << " s, " << st.paths / (st.render_ms * 1e3)
+            << " Mpaths/s, " << st.rays / (st.render_ms * 1e3) << " Mrays/s" << std::endl;
+
+  // ---- output, as main.cpp:176-245 ----
+  tpt::write_ppm_main(filenames[0], rgb8.data(), nx, ny);
+  if (allow_bonus_pic) {
+    for (int k = 0; k < bonus_pic; k++) {
+      std::string file = "img_" + std::to_string(k) + ".ppm";
+      filenames.push_back(file);
+      tpt::write_ppm_bonus(file, rgb8_slices.data() + (size_t)k * nx * ny * 3, nx, ny);
+    }
+  }
+  auto end = std::chrono::high_resolution_clock::now();
+  std::cout << "time: "
+            << std::chrono::duration_cast<std::chrono::milliseconds>(end - start).count() / 1000.0f
+            << " s" << std::endl;
+  tpt_scene_destroy(scene);
+#ifdef __linux__
+  tpt::merge_with_convert(filenames);
+#endif
+  return 0;
+}

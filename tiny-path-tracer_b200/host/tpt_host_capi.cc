@@ -1,0 +1,127 @@
+// host/tpt_host_capi.cc -- extern "C" access to the C++ front end for the Python tests and
+// bench.py (ctypes): build a named scene with the host classes, flatten it, hand out the
+// tpt_scene_desc; build a camera. No rendering here -- that is libtpt.so.
+#include "tpt_flatten.h"
+#include "tpt_scene.h"
+
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+namespace {
+thread_local std::string g_error;
+
+struct host_scene {
+  tpt::FlatScene flat;
+  tpt_scene_desc desc;
+};
+
+// leaves of a bvh in left-to-right order, each once
+void collect_leaves(hitable *h, std::vector<hitable *> &out) {
+  if (auto *b = dynamic_cast<bvh_node *>(h)) {
+    collect_leaves(b->left_, out);
+    if (b->right_ != b->left_) collect_leaves(b->right_, out);
+  } else {
+    out.push_back(h);
+  }
+}
+
+hitable *build_named(const std::string &name, const unsigned char *img, int iw, int ih) {
+  if (name == "cornell_box") return cornell_box();
+  if (name == "sphere_cornell_box") return sphere_cornell_box();
+  if (name == "random_scene") return random_scene();
+  if (name == "random_scene_list") {
+    // BASELINE config 1 ("no BVH"): the same leaves in a flat hitable_list (the commented
+    // alternative src/utils.cc:139), enumerated left-to-right from the built tree
+    std::vector<hitable *> leaves;
+    collect_leaves(random_scene(), leaves);
+    hitable **arr = new hitable *[leaves.size()];
+    for (size_t i = 0; i < leaves.size(); i++) arr[i] = leaves[i];
+    return new hitable_list(arr, (int)leaves.size());
+  }
+  if (name == "two_perlin_spheres") return two_perlin_spheres();
+  if (name == "two_checker_spheres") return two_checker_spheres();
+  if (name == "light_spheres") return light_spheres();
+  if (name == "cornell_box_smoke") return cornell_box_smoke();
+  if (name == "earth") { // main.cpp:78-81
+    if (!img) return nullptr;
+    unsigned char *copy = new unsigned char[(size_t)iw * ih * 3];
+    std::memcpy(copy, img, (size_t)iw * ih * 3);
+    return new sphere(vec3(0, 0, 0), 3, new lambertian(new image_texture(copy, iw, ih)));
+  }
+  return nullptr;
+}
+} // namespace
+
+extern "C" {
+
+const char *tpt_host_last_error(void) { return g_error.c_str(); }
+
+// lights == NULL -> the reference's hard-coded list (main.cpp:99-106)
+void *tpt_host_build_scene(const char *name, const unsigned char *img, int iw, int ih,
+                           const tpt_perlin_tables *force_perlin, const tpt_light *lights,
+                           int n_lights, int background) {
+  host_scene *hs = new host_scene();
+  std::string err;
+  bool ok = false;
+  std::string nm(name ? name : "");
+  // fresh thread => fresh default-seeded thread_local mt19937, i.e. the stream the reference's
+  // main thread sees when it builds the scene first thing (main.cpp:74)
+  std::thread builder([&] {
+    hitable *world = build_named(nm, img, iw, ih);
+    if (!world) {
+      err = "unknown scene '" + nm + "' (or missing image)";
+      return;
+    }
+    if (force_perlin) {
+      for (int i = 0; i < 256; i++) {
+        perlin_noise::random_vec3_[i] = vec3(force_perlin->ranvec[i][0], force_perlin->ranvec[i][1],
+                                             force_perlin->ranvec[i][2]);
+        perlin_noise::permute_x_[i] = force_perlin->perm_x[i];
+        perlin_noise::permute_y_[i] = force_perlin->perm_y[i];
+        perlin_noise::permute_z_[i] = force_perlin->perm_z[i];
+      }
+    }
+    hitable *shapes[16];
+    int n = 0;
+    if (!lights) {
+      shapes[n++] = new xz_rect(-100, 100, -150, -50, 298, nullptr);
+      shapes[n++] = new sphere(vec3(120, -50, 40), 120, nullptr);
+    } else {
+      for (int i = 0; i < n_lights && i < 16; i++) {
+        const tpt_light &L = lights[i];
+        if (L.kind == TPT_LIGHT_XZ_RECT)
+          shapes[n++] = new xz_rect(L.p[0], L.p[1], L.p[2], L.p[3], L.p[4], nullptr);
+        else if (L.kind == TPT_LIGHT_SPHERE)
+          shapes[n++] = new sphere(vec3(L.p[0], L.p[1], L.p[2]), L.p[3], nullptr);
+        else
+          shapes[n++] = new xy_rect(0, 0, 0, 0, 0, nullptr); // no pdf_value/random override
+      }
+    }
+    hitable_list hlist(shapes, n);
+    ok = tpt::flatten_scene(world, &hlist, background, hs->flat, err);
+  });
+  builder.join();
+  if (!ok) {
+    g_error = err;
+    delete hs;
+    return nullptr;
+  }
+  hs->desc = hs->flat.desc();
+  return hs;
+}
+
+const tpt_scene_desc *tpt_host_scene_desc(void *h) { return &static_cast<host_scene *>(h)->desc; }
+int tpt_host_scene_max_depth(void *h) { return static_cast<host_scene *>(h)->flat.max_depth; }
+void tpt_host_scene_free(void *h) { delete static_cast<host_scene *>(h); }
+
+void tpt_host_make_camera(const float *lookfrom, const float *lookat, const float *vup, float vfov,
+                          float aspect, float aperture, float focus_dist, float t0, float t1,
+                          tpt_camera *out) {
+  camera cam(vec3(lookfrom[0], lookfrom[1], lookfrom[2]), vec3(lookat[0], lookat[1], lookat[2]),
+             vec3(vup[0], vup[1], vup[2]), vfov, aspect, aperture, focus_dist, t0, t1);
+  *out = tpt::make_camera_desc(cam);
+}
+
+} // extern "C"

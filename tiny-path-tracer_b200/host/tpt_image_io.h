@@ -1,0 +1,19 @@
+// host/tpt_image_io.h -- picture output in the reference's formats + texture input.
+#ifndef TPT_HOST_IMAGE_IO_H_
+#define TPT_HOST_IMAGE_IO_H_
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace tpt {
+// Main picture: "P3\n<nx> <ny>\n255\n" then ONE PIXEL PER LINE "r g b \n", rows top to bottom
+// (main.cpp:69,183-189). rgb8 is [ny][nx][3] with row 0 = bottom row.
+bool write_ppm_main(const std::string &path, const uint8_t *rgb8, int nx, int ny);
+// Bonus pictures: same header, all pixels on one long line "r g b " (main.cpp:197-211).
+bool write_ppm_bonus(const std::string &path, const uint8_t *rgb8, int nx, int ny);
+// `convert a.ppm b.ppm ... +append img.jpg` (main.cpp:224-245); returns the system() status.
+int merge_with_convert(const std::vector<std::string> &files);
+// PPM (P6/P3) reader used by tests and as a texture source
+bool read_ppm(const std::string &path, std::vector<uint8_t> &rgb, int &w, int &h);
+} // namespace tpt
+#endif
