@@ -192,6 +192,23 @@ hitable *build_named(const std::string &name, ref_scene *sc, const unsigned char
   }
   if (name == "two_perlin_spheres") return two_perlin_spheres(); // src/utils.cc:227
   if (name == "light_spheres") return light_spheres();           // src/utils.cc:242
+  if (name == "textured_lit") {
+    // TEST-ONLY scene (not in the reference): the reference's texture classes under real light,
+    // because at HEAD every textured reference scene is black (no emitter, sky commented out).
+    // image-textured sphere (main.cpp:78-81) on a checker ground (src/utils.cc:99-103) lit by a
+    // diffuse_light sphere and a down-facing lamp rect; perlin marble sphere (src/utils.cc:228).
+    unsigned char *copy = new unsigned char[(size_t)iw * ih * 3];
+    std::memcpy(copy, img, (size_t)iw * ih * 3);
+    sc->image = copy;
+    hitable **l = new hitable *[6];
+    texture *checker = new checker_texture(new constant_texture({0.1, 0.1, 0.1}), new constant_texture({0.9, 0.9, 0.9}));
+    l[0] = new sphere(vec3(0, 0, 0), 3, new lambertian(new image_texture(copy, iw, ih)));
+    l[1] = new sphere(vec3(0, -1003, 0), 1000, new lambertian(checker));
+    l[2] = new sphere(vec3(-3, 6, 4), 2, new diffuse_light(new constant_texture(vec3(8, 8, 8))));
+    l[3] = new flip_normal(new xz_rect(-2, 2, -2, 2, 7, new diffuse_light(new constant_texture(vec3(4, 4, 4)))));
+    l[4] = new sphere(vec3(5, -1, -2), 2, new lambertian(new perlin_noise_texture(2.0f)));
+    return new hitable_list(l, 5);
+  }
   if (name == "earth") {
     // main.cpp:78-81 (commented alternative): sphere r=3 with image_texture(earthmap.jpg)
     unsigned char *copy = new unsigned char[(size_t)iw * ih * 3];
@@ -506,6 +523,76 @@ void ref_checker_value(const float *pts, int n, float *out_rgb) {
 // stbi_load through the reference's own wrapper (src/utils.cc:236-240). Returns malloc'ed RGB.
 unsigned char *ref_load_image(const char *path, int *w, int *h, int *ch) {
   return load_image_texture(path, *w, *h, *ch);
+}
+
+// Leaves of the reference tree in DFS order with their geometry and material parameters, read
+// from the public fields (headers/sphere.h:18-20,36-39, headers/rect_box.h:13-14,28-29,40-41,
+// headers/material.h:36,49-50,55,71). Lets the tests prove that the product's scene builders +
+// flattener describe exactly the scene the reference builds.
+struct ref_leaf_out {
+  int32_t kind;     // 0 sphere, 1 moving_sphere, 2 xy_rect, 3 xz_rect, 4 yz_rect
+  int32_t mat_kind; // 0 lambertian, 1 metal, 2 dielectric, 3 diffuse_light, 4 other
+  int32_t mat_id;
+  int32_t tex_kind; // 0 constant, 1 checker, 2 perlin, 3 image, -1 none
+  float p[12];
+  float mat[5];     // metal: albedo rgb, fuzz ; dielectric: ref_idx ; constant texture: rgb ; perlin: scale
+};
+
+int ref_dump_leaves(void *s, ref_leaf_out *out, int cap) {
+  ref_scene *sc = static_cast<ref_scene *>(s);
+  std::vector<tagged_leaf *> leaves;
+  std::map<hitable *, bool> seen;
+  struct walk {
+    static void go(hitable *h, std::vector<tagged_leaf *> &out, std::map<hitable *, bool> &seen) {
+      if (seen[h]) return;
+      seen[h] = true;
+      if (auto *t = dynamic_cast<tagged_leaf *>(h)) out.push_back(t);
+      else if (auto *b = dynamic_cast<bvh_node *>(h)) { go(b->left_, out, seen); go(b->right_, out, seen); }
+      else if (auto *l = dynamic_cast<hitable_list *>(h)) { for (int i = 0; i < l->list_size_; i++) go(l->list_[i], out, seen); }
+      else if (auto *bx = dynamic_cast<box *>(h)) go(bx->list_ptr_, out, seen);
+      else if (auto *t2 = dynamic_cast<translate *>(h)) go(t2->ptr_, out, seen);
+      else if (auto *r = dynamic_cast<rotate_y *>(h)) go(r->ptr_, out, seen);
+      else if (auto *f = dynamic_cast<flip_normal *>(h)) go(f->ptr_, out, seen);
+    }
+  };
+  walk::go(sc->world_tagged, leaves, seen);
+  int n = 0;
+  for (tagged_leaf *t : leaves) {
+    if (n >= cap) break;
+    ref_leaf_out &o = out[n++];
+    std::memset(&o, 0, sizeof(o));
+    hitable *h = t->inner_;
+    material *m = leaf_material(h);
+    if (auto *q = dynamic_cast<sphere *>(h)) {
+      o.kind = 0; o.p[0] = q->center_[0]; o.p[1] = q->center_[1]; o.p[2] = q->center_[2]; o.p[3] = q->radius_;
+    } else if (auto *q = dynamic_cast<moving_sphere *>(h)) {
+      o.kind = 1;
+      for (int c = 0; c < 3; c++) { o.p[c] = q->center0_[c]; o.p[4 + c] = q->center1_[c]; }
+      o.p[3] = q->radius_; o.p[7] = q->time0_; o.p[8] = q->time1_;
+    } else if (auto *q = dynamic_cast<xy_rect *>(h)) {
+      o.kind = 2; o.p[0] = q->x0_; o.p[1] = q->x1_; o.p[2] = q->y0_; o.p[3] = q->y1_; o.p[4] = q->k_;
+    } else if (auto *q = dynamic_cast<xz_rect *>(h)) {
+      o.kind = 3; o.p[0] = q->x0_; o.p[1] = q->x1_; o.p[2] = q->z0_; o.p[3] = q->z1_; o.p[4] = q->k_;
+    } else if (auto *q = dynamic_cast<yz_rect *>(h)) {
+      o.kind = 4; o.p[0] = q->y0_; o.p[1] = q->y1_; o.p[2] = q->z0_; o.p[3] = q->z1_; o.p[4] = q->k_;
+    }
+    o.mat_id = -1;
+    for (size_t i = 0; i < sc->mats.size(); i++) if (sc->mats[i] == m) o.mat_id = (int)i;
+    texture *tex = nullptr;
+    o.tex_kind = -1;
+    if (auto *q = dynamic_cast<lambertian *>(m)) { o.mat_kind = 0; tex = q->albedo_; }
+    else if (auto *q = dynamic_cast<metal *>(m)) { o.mat_kind = 1; o.mat[0] = q->albedo_[0]; o.mat[1] = q->albedo_[1]; o.mat[2] = q->albedo_[2]; o.mat[3] = q->fuzz_; }
+    else if (auto *q = dynamic_cast<dielectric *>(m)) { o.mat_kind = 2; o.mat[0] = q->ref_idx_; }
+    else if (auto *q = dynamic_cast<diffuse_light *>(m)) { o.mat_kind = 3; tex = q->emit_; }
+    else o.mat_kind = 4;
+    if (tex) {
+      if (auto *q = dynamic_cast<constant_texture *>(tex)) { o.tex_kind = 0; o.mat[0] = q->color_[0]; o.mat[1] = q->color_[1]; o.mat[2] = q->color_[2]; }
+      else if (dynamic_cast<checker_texture *>(tex)) o.tex_kind = 1;
+      else if (auto *q = dynamic_cast<perlin_noise_texture *>(tex)) { o.tex_kind = 2; o.mat[0] = q->scale_; }
+      else if (dynamic_cast<image_texture *>(tex)) o.tex_kind = 3;
+    }
+  }
+  return n;
 }
 
 int ref_hardware_concurrency(void) { return (int)std::thread::hardware_concurrency(); }

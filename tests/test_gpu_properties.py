@@ -1,0 +1,139 @@
+"""Size-independent properties of the CUDA sample loop, checked at and near BASELINE sizes:
+determinism, partition invariance (tiles / ranks), sample-range invariance, linearity in the
+emitted radiance, the quantiser, statistics, error behaviour."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import common
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cornell(T, gpu):
+    return T.Scene(common.host_scene(T, "cornell_box"))
+
+
+def test_deterministic_and_seeded(T, cornell):
+    cam = T.cornell_camera(200, 200)
+    a = cornell.render(cam, T.make_params(200, 200, 32, 15, seed=1))
+    b = cornell.render(cam, T.make_params(200, 200, 32, 15, seed=1))
+    c = cornell.render(cam, T.make_params(200, 200, 32, 15, seed=2))
+    assert np.array_equal(a.sum_rgb, b.sum_rgb) and np.array_equal(a.rgb8, b.rgb8)
+    assert not np.array_equal(a.sum_rgb, c.sum_rgb)
+    assert a.stats["rays"] == b.stats["rays"]
+
+
+@pytest.mark.parametrize("mode", ["parity", "fast"])
+def test_partition_invariance(T, cornell, mode):
+    """Philox is keyed on (pixel, sample): the union of the parts of a 3-way tile split is
+    bit-identical to the undivided render (what the multi-GPU gather relies on)."""
+    m = T.MODE_PARITY if mode == "parity" else T.MODE_FAST
+    nx, ny, ns = 150, 90, 16  # not multiples of the tile size
+    cam = T.cornell_camera(nx, ny)
+    whole = cornell.render(cam, T.make_params(nx, ny, ns, 15, mode=m, seed=5, subs=1))
+    acc = np.zeros_like(whole.sum_rgb)
+    owner = np.zeros((ny, nx), np.int32)
+    paths = 0
+    for part in range(3):
+        r = cornell.render(cam, T.make_params(nx, ny, ns, 15, mode=m, seed=5, part_index=part, part_count=3, subs=1))
+        owner += (np.abs(r.sum_rgb[0]).sum(axis=-1) > 0)
+        acc += r.sum_rgb
+        paths += r.stats["paths"]
+    assert paths == nx * ny * ns
+    assert owner.max() <= 1
+    assert np.array_equal(acc, whole.sum_rgb)
+
+
+def test_sub_range_invariance(T, cornell):
+    """cutting a pixel's samples into sub-ranges only changes the fp32 summation order."""
+    nx = ny = 128
+    cam = T.cornell_camera(nx, ny)
+    a = cornell.render(cam, T.make_params(nx, ny, 64, 15, seed=9, subs=1))
+    b = cornell.render(cam, T.make_params(nx, ny, 64, 15, seed=9, subs=4))
+    assert a.stats["rays"] == b.stats["rays"]
+    assert common.rel_err(b.sum_rgb, a.sum_rgb, 1e-3).max() < 1e-5
+
+
+def test_linearity_in_emission(T, gpu):
+    """radiance is linear in the lamp's emission; scaling it by 2 is exact in floating point."""
+    hs = common.host_scene(T, "cornell_box")
+    d = hs.desc.contents
+    lamp = [i for i in range(d.n_materials) if d.materials[i].kind == 3]
+    assert len(lamp) == 1
+    tex = d.materials[lamp[0]].texture
+    cam = T.cornell_camera(96, 96)
+    p = T.make_params(96, 96, 16, 15, seed=4)
+    base = T.Scene(hs).render(cam, p)
+    for c in range(3):
+        d.textures[tex].color[c] *= 2.0
+    twice = T.Scene(hs).render(cam, p)
+    assert base.sum_rgb.max() > 0
+    assert np.array_equal(twice.sum_rgb, 2.0 * base.sum_rgb)
+
+
+def test_quantiser_matches_reference_formula(T, cornell):
+    """main.cpp:135-139: col/=ns; sqrt; int(255.99f*c); clamp on write (:176-182)."""
+    cam = T.cornell_camera(256, 256, fov=61.93)
+    r = cornell.render(cam, T.make_params(256, 256, 8, 15, seed=3))
+    col = r.sum_rgb[0] / np.float32(8)
+    q = np.clip((np.float32(255.99) * np.sqrt(col)).astype(np.int32), 0, 255).astype(np.uint8)
+    assert np.array_equal(q, r.rgb8)
+    assert (r.rgb8 == 255).any() and (r.rgb8 == 0).any()  # the lamp saturates, shadows are black
+
+
+def test_statistics_headline_frame(T, cornell):
+    """full 1200x1200 frame (the headline resolution) at low spp: every (pixel, sample) is traced
+    exactly once; rays/path sits just below the reference's 2.41 (the GPU skips zombie bounces) and
+    about 1 % of the samples die as NaN (the reference counts 1.56 % because it also counts
+    zero-throughput paths that turn NaN later; both contribute 0 after de_nan)."""
+    nx = ny = 1200
+    cam = T.cornell_camera(nx, ny)
+    st = cornell.render_device(cam, T.make_params(nx, ny, 4, 15, seed=1))
+    assert st["paths"] == nx * ny * 4
+    assert 1.9 < st["rays"] / st["paths"] < 2.41
+    assert 0.005 < st["nan_samples"] / st["paths"] < 0.022
+    assert st["kernel_launches"] == 2
+
+
+def test_fast_and_parity_converge_to_the_same_image(T, cornell):
+    nx = ny = 64
+    cam = T.cornell_camera(nx, ny, fov=61.93)
+    a = cornell.render(cam, T.make_params(nx, ny, 512, 15, mode=T.MODE_PARITY, seed=11))
+    b = cornell.render(cam, T.make_params(nx, ny, 512, 15, mode=T.MODE_FAST, seed=12))
+    ia, ib = a.sum_rgb[0] / 512, b.sum_rgb[0] / 512
+    assert abs(ia.mean() - ib.mean()) < 0.01 * ia.mean()
+
+
+def test_error_behaviour(T, cornell):
+    cam = T.cornell_camera(32, 32)
+    with pytest.raises(T.TptError) as e:  # main.cpp:113,127 would SIGFPE (count % 0)
+        cornell.render(cam, T.make_params(32, 32, 4, 15, slices=8))
+    assert e.value.code == -1
+    with pytest.raises(T.TptError):
+        cornell.render(cam, T.make_params(32, 32, 4, 15, part_index=2, part_count=2))
+    with pytest.raises(T.TptError):
+        cornell.render(cam, T.make_params(0, 32, 4, 15))
+    with pytest.raises(T.TptError) as e:
+        cornell.render(cam, T.make_params(32, 32, 4, 15, kernel=7))
+    assert e.value.code == -4
+    hs = common.host_scene(T, "cornell_box")
+    hs.desc.contents.nodes[0].end_or_prim = 10 ** 6
+    with pytest.raises(T.TptError):
+        T.Scene(hs)
+    hs2 = common.host_scene(T, "cornell_box", lights=[])
+    with pytest.raises(T.TptError):
+        T.Scene(hs2).render(cam, T.make_params(32, 32, 4, 15))
+
+
+def test_depth_zero_and_one_sample(T, cornell):
+    """edge sizes: max_depth 0 (only directly visible emission), 1x1 image, ns=1."""
+    cam = T.cornell_camera(64, 64, fov=61.93)
+    r = cornell.render(cam, T.make_params(64, 64, 4, 0, seed=1))
+    assert r.stats["rays"] == r.stats["paths"]
+    lit = r.sum_rgb[0].sum(axis=-1) > 0
+    assert 0 < lit.mean() < 0.2  # only the lamp is visible
+    one = cornell.render(T.cornell_camera(1, 1), T.make_params(1, 1, 1, 15, seed=1))
+    assert one.stats["paths"] == 1

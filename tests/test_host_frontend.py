@@ -1,0 +1,171 @@
+"""Host C++ front end: scene builders + flattener describe exactly the reference's scenes,
+the camera ctor reproduces the reference's fields bit for bit, the ini reader and PPM writers
+behave like the reference's I/O."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+SCENES = ["cornell_box", "sphere_cornell_box", "random_scene", "random_scene_list", "two_perlin_spheres",
+          "light_spheres"]
+
+
+class RefLeaf(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("mat_kind", C.c_int32), ("mat_id", C.c_int32), ("tex_kind", C.c_int32),
+                ("p", C.c_float * 12), ("mat", C.c_float * 5)]
+
+
+def ref_leaves(O, name):
+    rs = O.RefScene(name)
+    arr = (RefLeaf * 4096)()
+    rs.lib.ref_dump_leaves.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    n = rs.lib.ref_dump_leaves(rs.h, arr, 4096)
+    return rs, [arr[i] for i in range(n)]
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_flattened_scene_equals_reference_scene(T, O, name):
+    """Same leaves, same order, same parameters (bitwise), same material assignment."""
+    hs = T.HostScene(name)
+    d = hs.desc.contents
+    rs, leaves = ref_leaves(O, name)
+    assert d.n_prims == len(leaves) == rs.n_leaves
+    assert d.n_materials == rs.n_materials
+    for i, rl in enumerate(leaves):
+        p = d.prims[i]
+        assert p.kind == rl.kind, (name, i)
+        assert p.material == rl.mat_id, (name, i)
+        n_par = {0: 4, 1: 9, 2: 5, 3: 5, 4: 5}[rl.kind]
+        got = np.array(p.p[:n_par], np.float32)
+        exp = np.array(rl.p[:n_par], np.float32)
+        assert got.tobytes() == exp.tobytes(), (name, i, got, exp)
+        m = d.materials[p.material]
+        assert m.kind == rl.mat_kind, (name, i)
+        if rl.mat_kind == 1:
+            assert np.array(list(m.albedo) + [m.fuzz], np.float32).tobytes() == np.array(rl.mat[:4], np.float32).tobytes()
+        if rl.mat_kind == 2:
+            assert np.float32(m.ref_idx) == np.float32(rl.mat[0])
+        if rl.mat_kind in (0, 3):
+            t = d.textures[m.texture]
+            assert t.kind == rl.tex_kind
+            if t.kind == 0:
+                assert np.array(t.color[:], np.float32).tobytes() == np.array(rl.mat[:3], np.float32).tobytes()
+            if t.kind == 2:
+                assert np.float32(t.scale) == np.float32(rl.mat[0])
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_preorder_structure(T, name):
+    hs = T.HostScene(name)
+    d = hs.desc.contents
+    ends = []
+    leaf_prims = []
+    skip_until = -1  # inside a duplicated sub-tree (second child of a one-element bvh_node)
+    for i in range(d.n_nodes):
+        while ends and ends[-1] == i:
+            ends.pop()
+        n = d.nodes[i]
+        k = n.kind & 0xFF
+        assert 0 <= (n.kind >> 16) < d.n_chains
+        if k == 2:
+            assert 0 <= n.end_or_prim < d.n_prims
+            if not (n.kind & 0x100) and i >= skip_until:
+                leaf_prims.append(n.end_or_prim)
+        else:
+            assert i < n.end_or_prim <= (ends[-1] if ends else d.n_nodes)
+            ends.append(n.end_or_prim)
+            if (n.kind & 0x100) and i >= skip_until:
+                skip_until = n.end_or_prim
+    # every primitive appears exactly once among the non-duplicate leaves, in DFS order
+    assert leaf_prims == list(range(d.n_prims))
+    assert d.chains[0].n_ops == 0
+    assert d.n_lights == 2  # main.cpp:99-106
+
+
+def test_cornell_box_layout(T):
+    hs = T.HostScene("cornell_box")
+    d = hs.desc.contents
+    assert (d.n_prims, d.n_chains, d.n_xform_ops, d.n_materials) == (19, 3, 4, 6)
+    # two boxes: translate(rotate_y(box)) -> chain = [TRANSLATE, ROTATE_Y]
+    for c in (1, 2):
+        ch = d.chains[c]
+        assert ch.n_ops == 2
+        assert d.xform_ops[ch.first_op].kind == 0 and d.xform_ops[ch.first_op + 1].kind == 1
+    flips = [d.prims[i].flags & 1 for i in range(d.n_prims)]
+    assert sum(flips) == 3 + 3 + 3  # right wall, ceiling, lamp + three faces per box
+
+
+def test_constant_medium_is_rejected_not_approximated(T):
+    with pytest.raises(RuntimeError, match="constant_medium"):
+        T.HostScene("cornell_box_smoke")
+
+
+@pytest.mark.parametrize("args", [
+    dict(lookfrom=(0, 0, 800), lookat=(0, 0, 0), vup=(0, 1, 0), vfov=90.0, aspect=1.0, aperture=0.1, focus=10.0, t0=0.0, t1=0.0),
+    dict(lookfrom=(13, 2, 3), lookat=(0, 0, 0), vup=(0, 1, 0), vfov=20.0, aspect=1.5, aperture=0.0, focus=13.49, t0=0.0, t1=1.0),
+    dict(lookfrom=(278, 278, -800), lookat=(278, 278, 0), vup=(0, 1, 0), vfov=61.93, aspect=2.0, aperture=0.2, focus=7.5, t0=0.25, t1=0.75),
+])
+def test_camera_fields_bit_exact(T, O, args):
+    cam = T.make_camera(args["lookfrom"], args["lookat"], args["vup"], args["vfov"], args["aspect"],
+                        args["aperture"], args["focus"], args["t0"], args["t1"])
+    ref = O.ref_camera(args["lookfrom"], args["lookat"], args["vup"], args["vfov"], args["aspect"],
+                       args["aperture"], args["focus"], args["t0"], args["t1"])
+    pairs = [("origin", "origin"), ("lower_left_corner", "lower_left"), ("vertical", "vertical"),
+             ("horizontal", "horizontal"), ("u", "u"), ("v", "v"), ("w", "w")]
+    for a, b in pairs:
+        assert bytes(getattr(cam, a)) == bytes(getattr(ref, b)), a
+    for f in ("lens_radius", "time0", "time1"):
+        assert np.float32(getattr(cam, f)) == np.float32(getattr(ref, f))
+
+
+def test_ppm_writers_match_reference_formats(T, tmp_path):
+    """main picture: one pixel per line 'r g b \\n' top row first; bonus: one long line."""
+    nx, ny = 3, 2
+    img = ((np.arange(nx * ny * 3).reshape(ny, nx, 3) * 13) % 256).astype(np.uint8)
+    H = T.host()
+    H.tpt_host_write_ppm.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
+    p1, p2 = str(tmp_path / "a.ppm"), str(tmp_path / "b.ppm")
+    assert H.tpt_host_write_ppm(p1.encode(), img.ctypes.data, nx, ny, 0) == 0
+    assert H.tpt_host_write_ppm(p2.encode(), img.ctypes.data, nx, ny, 1) == 0
+    rows_top_first = img[::-1]
+    exp1 = "P3\n3 2\n255\n" + "".join(f"{p[0]} {p[1]} {p[2]} \n" for r in rows_top_first for p in r)
+    exp2 = "P3\n3 2\n255\n" + "".join(f"{p[0]} {p[1]} {p[2]} " for r in rows_top_first for p in r)
+    assert open(p1).read() == exp1
+    assert open(p2).read() == exp2
+
+
+INI_PROBE = r'''
+#include "tpt_ini.h"
+#include <iostream>
+#include <sstream>
+int main() {
+  std::istringstream in("[DEFAULT]\nwidth = 400\n height=  400 \nsample = 50\nfov = 90.0\n; comment\nbad line\n"
+                        "width = 7\n[BLUR]\naperture = 0.1\n[CAM_MOTION]\nstart_time = 0.0\nend_time = x\n");
+  inipp::Ini<char> ini; ini.parse(in);
+  int nx = 1, ny = 2, ns = 3, depth = 50; float fov = 1, ap = 0.2f, t1 = 1.0f;
+  inipp::extract(ini.sections["DEFAULT"]["width"], nx);
+  inipp::extract(ini.sections["DEFAULT"]["height"], ny);
+  inipp::extract(ini.sections["DEFAULT"]["sample"], ns);
+  inipp::extract(ini.sections["DEFAULT"]["recur_depth"], depth);   // missing -> default kept
+  inipp::extract(ini.sections["DEFAULT"]["fov"], fov);
+  inipp::extract(ini.sections["BLUR"]["aperture"], ap);
+  inipp::extract(ini.sections["CAM_MOTION"]["end_time"], t1);      // unparsable -> default kept
+  std::cout << nx << " " << ny << " " << ns << " " << depth << " " << fov << " " << ap << " " << t1 << " "
+            << ini.errors.size() << "\n";
+  ini.generate(std::cout);
+}
+'''
+
+
+def test_ini_reader_semantics(T, tmp_path):
+    src = tmp_path / "probe.cc"
+    src.write_text(INI_PROBE)
+    exe = tmp_path / "probe"
+    subprocess.check_call(["g++", "-std=c++14", "-I", os.path.join(T.REPO_ROOT, "tiny-path-tracer_b200", "host"),
+                           str(src), "-o", str(exe)])
+    out = subprocess.check_output([str(exe)], text=True).splitlines()
+    assert out[0] == "400 400 50 50 90 0.1 1 2"  # two bad lines: 'bad line' and the duplicate width
+    assert out[1:] == ["[BLUR]", "aperture=0.1", "[CAM_MOTION]", "end_time=x", "start_time=0.0", "[DEFAULT]",
+                       "fov=90.0", "height=400", "recur_depth=", "sample=50", "width=400"]  # operator[] inserts, as std::map does for inipp

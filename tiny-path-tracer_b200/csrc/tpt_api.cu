@@ -337,7 +337,7 @@ int run_plan(tpt_scene *s, Plan &plan, bool want_sum, bool want_rgb8, bool want_
   st.sm_count = s->prop.multiProcessorCount;
   st.blocks = plan.blocks;
   st.threads_per_block = TPT_MEGA_THREADS;
-  st.h2d_bytes = sizeof(RenderArgs) + sizeof(ResolveArgs);
+  st.h2d_bytes = s->blob_bytes + sizeof(RenderArgs) + sizeof(ResolveArgs); // scene blob + launch arguments
   s->last_nx = A.nx;
   s->last_ny = A.ny;
   s->last_slices = R.slices;

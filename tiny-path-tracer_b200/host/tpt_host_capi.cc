@@ -2,6 +2,7 @@
 // bench.py (ctypes): build a named scene with the host classes, flatten it, hand out the
 // tpt_scene_desc; build a camera. No rendering here -- that is libtpt.so.
 #include "tpt_flatten.h"
+#include "tpt_image_io.h"
 #include "tpt_scene.h"
 
 #include <cstring>
@@ -44,6 +45,20 @@ hitable *build_named(const std::string &name, const unsigned char *img, int iw, 
   if (name == "two_checker_spheres") return two_checker_spheres();
   if (name == "light_spheres") return light_spheres();
   if (name == "cornell_box_smoke") return cornell_box_smoke();
+  if (name == "textured_lit") {
+    // test scene: every texture class under real light (HEAD's own textured scenes are black)
+    if (!img) return nullptr;
+    unsigned char *copy = new unsigned char[(size_t)iw * ih * 3];
+    std::memcpy(copy, img, (size_t)iw * ih * 3);
+    hitable **l = new hitable *[6];
+    texture *checker = new checker_texture(new constant_texture({0.1, 0.1, 0.1}), new constant_texture({0.9, 0.9, 0.9}));
+    l[0] = new sphere(vec3(0, 0, 0), 3, new lambertian(new image_texture(copy, iw, ih)));
+    l[1] = new sphere(vec3(0, -1003, 0), 1000, new lambertian(checker));
+    l[2] = new sphere(vec3(-3, 6, 4), 2, new diffuse_light(new constant_texture(vec3(8, 8, 8))));
+    l[3] = new flip_normal(new xz_rect(-2, 2, -2, 2, 7, new diffuse_light(new constant_texture(vec3(4, 4, 4)))));
+    l[4] = new sphere(vec3(5, -1, -2), 2, new lambertian(new perlin_noise_texture(2.0f)));
+    return new hitable_list(l, 5);
+  }
   if (name == "earth") { // main.cpp:78-81
     if (!img) return nullptr;
     unsigned char *copy = new unsigned char[(size_t)iw * ih * 3];
@@ -122,6 +137,12 @@ void tpt_host_make_camera(const float *lookfrom, const float *lookat, const floa
   camera cam(vec3(lookfrom[0], lookfrom[1], lookfrom[2]), vec3(lookat[0], lookat[1], lookat[2]),
              vec3(vup[0], vup[1], vup[2]), vfov, aspect, aperture, focus_dist, t0, t1);
   *out = tpt::make_camera_desc(cam);
+}
+
+// picture writers in the reference's formats (main.cpp:69,183-189 and :197-211)
+int tpt_host_write_ppm(const char *path, const unsigned char *rgb8, int nx, int ny, int bonus_format) {
+  bool ok = bonus_format ? tpt::write_ppm_bonus(path, rgb8, nx, ny) : tpt::write_ppm_main(path, rgb8, nx, ny);
+  return ok ? 0 : -1;
 }
 
 } // extern "C"
