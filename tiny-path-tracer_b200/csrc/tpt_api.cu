@@ -5,6 +5,7 @@
 #include "tpt.h"
 #include "tpt_launch.h"
 
+#include <algorithm>
 #include <chrono>
 #include <climits>
 #include <cstdio>
@@ -101,6 +102,7 @@ struct tpt_scene {
   float4 *d_blob = nullptr;
   size_t blob_bytes = 0;
   bool use_smem = false;
+  SmallScene small{}; // flat (chain, kind)-ordered geometry for the uniform brute-force closest hit
   std::vector<cudaArray_t> arrays;
   std::vector<cudaTextureObject_t> textures;
   bool has_lights = false;
@@ -189,6 +191,121 @@ int validate_desc(const tpt_scene_desc *d, int &depth_out) {
   return TPT_OK;
 }
 
+// Group the non-duplicate leaves by transform chain and primitive kind (xy, xz, yz rect, sphere).
+// Closest-hit does not depend on the order except on exact ties, which FAST mode does not
+// promise to resolve like the reference.
+void build_small_scene(const tpt_scene_desc *d, bool smem_ok, SmallScene &Q) {
+  std::memset(&Q, 0, sizeof(Q));
+  if (!smem_ok || d->n_prims > TPT_SMALL_MAX_PRIMS || d->n_chains > TPT_SMALL_MAX_GROUPS ||
+      d->n_xform_ops > TPT_SMALL_MAX_OPS)
+    return;
+  for (int i = 0; i < d->n_prims; i++)
+    if (d->prims[i].kind == TPT_PRIM_MOVING_SPHERE) return;
+  for (int i = 0; i < d->n_xform_ops; i++) {
+    const tpt_xform_op &op = d->xform_ops[i];
+    int32_t kind = op.kind;
+    float kf;
+    std::memcpy(&kf, &kind, 4);
+    Q.ops[i] = make_float4(kf, op.a, op.b, op.c);
+  }
+  // ---- recognise `box` lists: six non-duplicate leaf children of one LIST, same chain, that are
+  // exactly the faces of an axis-aligned block (src/rect_box.cc:93-115) ----
+  std::vector<int> in_box(d->n_prims, -1);
+  int nb = 0;
+  for (int i = 0; i < d->n_nodes && nb < TPT_SMALL_MAX_BOXES; i++) {
+    const tpt_node &g = d->nodes[i];
+    if ((g.kind & 0xff) != TPT_NODE_LIST || (g.kind & TPT_NODE_DUP) || g.end_or_prim - i - 1 != 6) continue;
+    int ids[6];
+    bool ok = true;
+    for (int c = 0; c < 6 && ok; c++) {
+      const tpt_node &l = d->nodes[i + 1 + c];
+      ok = (l.kind & 0xff) == TPT_NODE_LEAF && (l.kind >> 16) == (g.kind >> 16);
+      ids[c] = l.end_or_prim;
+      if (ok && in_box[ids[c]] >= 0) ok = false;
+    }
+    if (!ok) continue;
+    // candidate extents from the first xy_rect found
+    float lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+    int face[6] = {-1, -1, -1, -1, -1, -1};
+    float zs[2], ys[2], xs[2];
+    int nz = 0, ny = 0, nx = 0;
+    for (int c = 0; c < 6; c++) {
+      const tpt_prim &p = d->prims[ids[c]];
+      if (p.kind == TPT_PRIM_XY_RECT && nz < 2) zs[nz++] = p.p[4];
+      else if (p.kind == TPT_PRIM_XZ_RECT && ny < 2) ys[ny++] = p.p[4];
+      else if (p.kind == TPT_PRIM_YZ_RECT && nx < 2) xs[nx++] = p.p[4];
+      else ok = false;
+    }
+    if (!ok || nx != 2 || ny != 2 || nz != 2) continue;
+    lo[0] = std::min(xs[0], xs[1]); hi[0] = std::max(xs[0], xs[1]);
+    lo[1] = std::min(ys[0], ys[1]); hi[1] = std::max(ys[0], ys[1]);
+    lo[2] = std::min(zs[0], zs[1]); hi[2] = std::max(zs[0], zs[1]);
+    if (!(lo[0] < hi[0] && lo[1] < hi[1] && lo[2] < hi[2])) continue;
+    for (int c = 0; c < 6 && ok; c++) {
+      const tpt_prim &p = d->prims[ids[c]];
+      int axis, a, b; // plane axis and the two in-plane axes in the order of p.p[0..3]
+      if (p.kind == TPT_PRIM_XY_RECT) { axis = 2; a = 0; b = 1; }
+      else if (p.kind == TPT_PRIM_XZ_RECT) { axis = 1; a = 0; b = 2; }
+      else { axis = 0; a = 1; b = 2; }
+      ok = p.p[0] == lo[a] && p.p[1] == hi[a] && p.p[2] == lo[b] && p.p[3] == hi[b];
+      int side = p.p[4] == lo[axis] ? 0 : 1;
+      if (ok && face[2 * axis + side] >= 0) ok = false;
+      face[2 * axis + side] = ids[c];
+    }
+    if (!ok) continue;
+    SmallBox &B = Q.boxes[nb];
+    B.lo = make_float4(lo[0], lo[1], lo[2], 0.f);
+    B.hi = make_float4(hi[0], hi[1], hi[2], 0.f);
+    for (int f = 0; f < 6; f++) {
+      B.face[f] = face[f];
+      in_box[face[f]] = nb;
+    }
+    B.face[6] = g.kind >> 16; // chain, consumed below
+    nb++;
+  }
+  int n = 0, ng = 0, nbox_sorted = 0;
+  SmallBox sorted[TPT_SMALL_MAX_BOXES];
+  const int order[4] = {TPT_PRIM_XY_RECT, TPT_PRIM_XZ_RECT, TPT_PRIM_YZ_RECT, TPT_PRIM_SPHERE};
+  for (int c = 0; c < d->n_chains; c++) {
+    SmallGroup G{};
+    G.first_op = d->chains[c].first_op;
+    G.n_ops = d->chains[c].n_ops;
+    G.begin = n;
+    int ends[4];
+    for (int o = 0; o < 4; o++) {
+      for (int i = 0; i < d->n_prims; i++) {
+        const tpt_prim &p = d->prims[i];
+        if (p.chain != c || p.kind != order[o] || in_box[i] >= 0) continue;
+        int32_t id = i;
+        float idf;
+        std::memcpy(&idf, &id, 4);
+        if (p.kind == TPT_PRIM_SPHERE) {
+          Q.geo[n] = make_float4(p.p[0], p.p[1], p.p[2], p.p[3]);
+          Q.aux[n] = make_float2(p.p[3] * p.p[3], idf);
+        } else {
+          Q.geo[n] = make_float4(p.p[0], p.p[1], p.p[2], p.p[3]);
+          Q.aux[n] = make_float2(p.p[4], idf);
+        }
+        n++;
+      }
+      ends[o] = n;
+    }
+    G.box_begin = nbox_sorted;
+    for (int b = 0; b < nb; b++)
+      if (Q.boxes[b].face[6] == c) sorted[nbox_sorted++] = Q.boxes[b];
+    G.box_end = nbox_sorted;
+    if (n == G.begin && G.box_begin == G.box_end) continue; // nothing lives directly under this chain
+    G.xy_end = ends[0];
+    G.xz_end = ends[1];
+    G.yz_end = ends[2];
+    G.sph_end = ends[3];
+    Q.groups[ng++] = G;
+  }
+  for (int b = 0; b < nbox_sorted; b++) Q.boxes[b] = sorted[b];
+  Q.n_groups = ng;
+  Q.enabled = 1;
+}
+
 int ensure(void **p, size_t &have, size_t want) {
   if (have >= want && *p) return TPT_OK;
   if (*p) cudaFree(*p);
@@ -205,6 +322,7 @@ struct Plan {
   ResolveArgs res;
   int blocks = 0, blocks_per_sm = 0;
   bool parity = false;
+  bool wavefront = false;
   size_t npix = 0;
 };
 
@@ -216,13 +334,17 @@ int make_plan(tpt_scene *s, const tpt_camera *cam, const tpt_render_params *p, P
   int per_slice = p->ns / slices;
   if (per_slice <= 0) return fail(TPT_ERR_INVALID, "ns < slices (the reference would divide by zero, main.cpp:113,127)");
   if (p->mode != TPT_MODE_PARITY && p->mode != TPT_MODE_FAST) return fail(TPT_ERR_INVALID, "unknown mode");
-  if (p->kernel != TPT_KERNEL_MEGA) return fail(TPT_ERR_UNSUPPORTED, "kernel variant not built");
+  if (p->kernel != TPT_KERNEL_MEGA && p->kernel != TPT_KERNEL_WAVEFRONT) return fail(TPT_ERR_UNSUPPORTED, "unknown kernel variant");
+  if (p->kernel == TPT_KERNEL_WAVEFRONT && !s->use_smem)
+    return fail(TPT_ERR_UNSUPPORTED, "wavefront variant needs a shared-memory resident scene (<= 64 KB)");
+  plan.wavefront = p->kernel == TPT_KERNEL_WAVEFRONT;
   if (p->part_count <= 0 || p->part_index < 0 || p->part_index >= p->part_count) return fail(TPT_ERR_INVALID, "bad part_index/part_count");
   if (!s->has_lights) return fail(TPT_ERR_INVALID, "light-sampling list is empty (color() needs light_shape, main.cpp:99-106)");
   plan.parity = p->mode == TPT_MODE_PARITY;
   RenderArgs &A = plan.args;
   std::memset(&A, 0, sizeof(A));
   A.scene = s->layout;
+  A.small = s->small;
   auto v3 = [](const float *f) { return V3{f[0], f[1], f[2]}; };
   A.cam.origin = v3(cam->origin);
   A.cam.llc = v3(cam->lower_left_corner);
@@ -305,16 +427,24 @@ int run_plan(tpt_scene *s, Plan &plan, bool want_sum, bool want_rgb8, bool want_
 
   size_t smem = s->use_smem ? s->blob_bytes : 0;
   int bps = 0;
-  CK(plan.parity ? mega_occupancy_parity(s->use_smem, smem, &bps) : mega_occupancy_fast(s->use_smem, smem, &bps));
-  if (bps < 1) return fail(TPT_ERR_CUDA, "megakernel does not fit on an SM");
+  const bool small = s->small.enabled != 0;
+  if (plan.wavefront)
+    CK(plan.parity ? wave_occupancy_parity(A, small, &bps) : wave_occupancy_fast(A, small, &bps));
+  else
+    CK(plan.parity ? mega_occupancy_parity(s->use_smem, small, smem, &bps)
+                   : mega_occupancy_fast(s->use_smem, small, smem, &bps));
+  if (bps < 1) return fail(TPT_ERR_CUDA, "render kernel does not fit on an SM");
   plan.blocks_per_sm = bps;
   plan.blocks = bps * s->prop.multiProcessorCount;
 
   CK(cudaMemsetAsync(s->d_counters, 0, 8 * sizeof(unsigned long long), s->stream));
   CK(cudaMemsetAsync(s->d_acc, 0, acc_want, s->stream));
   CK(cudaEventRecord(s->ev[0], s->stream));
-  CK(plan.parity ? launch_mega_parity(A, s->use_smem, plan.blocks, s->stream)
-                 : launch_mega_fast(A, s->use_smem, plan.blocks, s->stream));
+  if (plan.wavefront)
+    CK(plan.parity ? launch_wave_parity(A, small, plan.blocks, s->stream) : launch_wave_fast(A, small, plan.blocks, s->stream));
+  else
+    CK(plan.parity ? launch_mega_parity(A, s->use_smem, small, plan.blocks, s->stream)
+                   : launch_mega_fast(A, s->use_smem, small, plan.blocks, s->stream));
   CK(cudaEventRecord(s->ev[1], s->stream));
   int rb = (int)((plan.npix + 255) / 256);
   resolve_kernel<<<rb, 256, 0, s->stream>>>(R);
@@ -336,7 +466,7 @@ int run_plan(tpt_scene *s, Plan &plan, bool want_sum, bool want_rgb8, bool want_
   st.kernel_launches = 2;
   st.sm_count = s->prop.multiProcessorCount;
   st.blocks = plan.blocks;
-  st.threads_per_block = TPT_MEGA_THREADS;
+  st.threads_per_block = plan.wavefront ? TPT_WAVE_THREADS : TPT_MEGA_THREADS;
   st.h2d_bytes = s->blob_bytes + sizeof(RenderArgs) + sizeof(ResolveArgs); // scene blob + launch arguments
   s->last_nx = A.nx;
   s->last_ny = A.ny;
@@ -457,6 +587,7 @@ int tpt_scene_create(const tpt_scene_desc *d, int device, tpt_scene **out) {
   CK(cudaMemcpy(s->d_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice));
   L.blob_global = s->d_blob;
   s->use_smem = blob.size() <= 64 * 1024;
+  build_small_scene(d, s->use_smem, s->small);
 
   // ---- image textures: RGB -> RGBA8 cudaArray, point sampling, clamp, unnormalised coords ----
   for (int i = 0; i < d->n_images; i++) {
@@ -523,13 +654,14 @@ int tpt_intersect_batch(const tpt_scene *cs, const tpt_ray *rays, size_t n, floa
   CK(cudaMemcpyAsync(d_rays, rays, n * sizeof(tpt_ray), cudaMemcpyHostToDevice, s->stream));
   IntersectArgs A;
   A.scene = s->layout;
+  A.small = s->small;
   A.rays = d_rays;
   A.n = n;
   A.tmin = tmin;
   A.tmax = tmax;
   A.out = d_out;
-  cudaError_t e = mode == TPT_MODE_PARITY ? launch_intersect_parity(A, s->use_smem, s->stream)
-                                          : launch_intersect_fast(A, s->use_smem, s->stream);
+  cudaError_t e = mode == TPT_MODE_PARITY ? launch_intersect_parity(A, s->use_smem, false, s->stream)
+                                          : launch_intersect_fast(A, s->use_smem, s->small.enabled != 0, s->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, n * sizeof(tpt_hit), cudaMemcpyDeviceToHost, s->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
   cudaFree(d_rays);

@@ -38,9 +38,41 @@ struct SceneLayout { // host-computed, lives in kernel parameter (constant) spac
   int image_w[TPT_MAX_IMAGES], image_h[TPT_MAX_IMAGES];
 };
 
+// Small scenes (<= TPT_SMALL_MAX_PRIMS primitives, no moving spheres): a second, flat copy of the
+// geometry ordered by (transform chain, primitive kind), passed BY VALUE in the kernel
+// parameters. Parameter space is the constant bank: the warp-uniform brute-force closest hit
+// below reads it through the uniform datapath (ULDC / constant operands), so a primitive test
+// costs no load instruction on the main pipes. FAST mode only.
+#define TPT_SMALL_MAX_PRIMS 48
+#define TPT_SMALL_MAX_GROUPS 8
+#define TPT_SMALL_MAX_OPS 16
+#define TPT_SMALL_MAX_BOXES 6
+struct SmallGroup {
+  int first_op, n_ops;            // transform chain of this group (outermost first)
+  int xy_end, xz_end, yz_end, sph_end; // the group's records are [begin, xy_end) xy_rects, ... spheres
+  int begin;
+  int box_begin, box_end;         // axis-aligned boxes (a `box` = list of its six faces) under this chain
+  int pad0, pad1, pad2;
+};
+// `box` (src/rect_box.cc:93-115) recognised at scene upload: six rect faces of one axis-aligned
+// block. One slab test finds the entry / exit face instead of six rectangle tests.
+struct SmallBox {
+  float4 lo, hi;  // pmin, pmax
+  int face[8];    // prim ids of the faces: [-x, +x, -y, +y, -z, +z]
+};
+struct SmallScene {
+  int n_groups, enabled, pad0, pad1;
+  SmallGroup groups[TPT_SMALL_MAX_GROUPS];
+  float4 ops[TPT_SMALL_MAX_OPS];     // tpt_xform_op
+  float4 geo[TPT_SMALL_MAX_PRIMS];   // rect: a0,a1,b0,b1 ; sphere: cx,cy,cz,r
+  float2 aux[TPT_SMALL_MAX_PRIMS];   // rect: k, prim id (int bits) ; sphere: r*r, prim id
+  SmallBox boxes[TPT_SMALL_MAX_BOXES];
+};
+
 struct SceneView {
-  const float4 *blob;   // shared-memory copy when it fits, else the global blob
-  const SceneLayout *L; // offsets / counts / texture objects (constant bank)
+  const float4 *blob;      // shared-memory copy when it fits, else the global blob
+  const SceneLayout *L;    // offsets / counts / texture objects (constant bank)
+  const SmallScene *small; // constant bank; valid when the kernel is instantiated with SMALL
 };
 
 struct V3 {
@@ -237,12 +269,16 @@ TPT_DEV V3 moving_center(float4 a, float4 b, float4 c, float time) {
 
 template <bool PAR>
 TPT_DEV bool sphere_test(V3 center, float radius, const XRay &x, float tmin, float tmax, float &t) {
-  // src/sphere.cc:15-41
+  // src/sphere.cc:15-41. The quadratic's coefficients and discriminant are evaluated with
+  // explicitly rounded fp32 operations in BOTH modes (never contracted into FMAs): the
+  // discriminant of a 1000- or 1e5-radius "wall" sphere is a catastrophic cancellation, and only
+  // the reference's own rounding sequence reproduces which of two such spheres wins.
   V3 oc = x.o - center;
-  float a = dot(x.d, x.d);
-  float b = 2.0f * dot(x.d, oc);
-  float c = dot(oc, oc) - radius * radius;
-  float disc = b * b - 4 * a * c;
+  float a = __fadd_rn(__fadd_rn(__fmul_rn(x.d.x, x.d.x), __fmul_rn(x.d.y, x.d.y)), __fmul_rn(x.d.z, x.d.z));
+  float b = 2.0f * __fadd_rn(__fadd_rn(__fmul_rn(x.d.x, oc.x), __fmul_rn(x.d.y, oc.y)), __fmul_rn(x.d.z, oc.z));
+  float c = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(oc.x, oc.x), __fmul_rn(oc.y, oc.y)), __fmul_rn(oc.z, oc.z)),
+                      -__fmul_rn(radius, radius));
+  float disc = __fadd_rn(__fmul_rn(b, b), -__fmul_rn(__fmul_rn(4.0f, a), c));
   if (disc > 0) {
     if (PAR) {
       // `sqrt` (unqualified) and the division are evaluated in double, rounded once to float
@@ -258,14 +294,14 @@ TPT_DEV bool sphere_test(V3 center, float radius, const XRay &x, float tmin, flo
         return true;
       }
     } else {
-      float sq = sqrtf(disc);
-      float inv2a = 0.5f / a;
-      float temp = (-b - sq) * inv2a;
+      float sq = __fsqrt_rn(disc);
+      float two_a = 2.0f * a;
+      float temp = __fdiv_rn(-b - sq, two_a);
       if (temp < tmax && temp > tmin) {
         t = temp;
         return true;
       }
-      temp = (-b + sq) * inv2a;
+      temp = __fdiv_rn(-b + sq, two_a);
       if (temp < tmax && temp > tmin) {
         t = temp;
         return true;
@@ -421,6 +457,96 @@ TPT_DEV bool closest_hit(const SceneView &S, const Ray &r, float tmin, float tma
     prim_out = best_prim;
     return best_prim >= 0;
   }
+}
+
+// ------------------------------------------------------------------------------------------
+// Small scenes (Cornell: 19 primitives under a BVH that prunes almost nothing -- the reference
+// itself tests 8.6 of its 9 boxes per ray): every lane tests every primitive in the same order.
+// Control flow and shared-memory addresses are warp-uniform (broadcast loads, no divergence);
+// only the "closer?" update is predicated. FAST mode only -- ties resolve to the first leaf.
+// ------------------------------------------------------------------------------------------
+// rect with compile-time axes: plane coordinate K, in-plane coordinates A and B (0=x,1=y,2=z)
+template <int K, int A, int B>
+TPT_DEV void small_rects(const SmallScene &Q, int begin, int end, const float (&o)[3], const float (&d)[3],
+                         const float (&inv)[3], float tmin, float &best, int &best_prim) {
+  for (int i = begin; i < end; i++) {
+    const float4 g = Q.geo[i];
+    const float2 w = Q.aux[i];
+    const float t = (w.x - o[K]) * inv[K];
+    const float a = fmaf(t, d[A], o[A]);
+    const float b = fmaf(t, d[B], o[B]);
+    // t_min <= t <= t_max and inside the rectangle, bounds inclusive (src/rect_box.cc:11-16)
+    const bool ok = (t >= tmin) & (t <= best) & (a >= g.x) & (a <= g.y) & (b >= g.z) & (b <= g.w);
+    best = ok ? t : best;
+    best_prim = ok ? __float_as_int(w.y) : best_prim;
+  }
+}
+
+TPT_DEV bool closest_hit_uniform(const SceneView &S, const Ray &r, float tmin, float tmax, float &t_out,
+                                 int &prim_out) {
+  const SmallScene &Q = *S.small;
+  float best = tmax;
+  int best_prim = -1;
+  for (int gi = 0; gi < Q.n_groups; gi++) {
+    const SmallGroup G = Q.groups[gi];
+    float o[3] = {r.o.x, r.o.y, r.o.z}, d[3] = {r.d.x, r.d.y, r.d.z};
+    for (int k = 0; k < G.n_ops; k++) { // headers/rect_box.h:89, src/rect_box.cc:175-179
+      const float4 op = Q.ops[G.first_op + k];
+      if (__float_as_int(op.x) == TPT_XF_TRANSLATE) {
+        o[0] -= op.y;
+        o[1] -= op.z;
+        o[2] -= op.w;
+      } else {
+        const float sn = op.y, co = op.z;
+        const float ox = co * o[0] - sn * o[2], oz = sn * o[0] + co * o[2];
+        const float dx = co * d[0] - sn * d[2], dz = sn * d[0] + co * d[2];
+        o[0] = ox;
+        o[2] = oz;
+        d[0] = dx;
+        d[2] = dz;
+      }
+    }
+    const float inv[3] = {1.0f / d[0], 1.0f / d[1], 1.0f / d[2]};
+    small_rects<2, 0, 1>(Q, G.begin, G.xy_end, o, d, inv, tmin, best, best_prim);  // xy_rect: z = k
+    small_rects<1, 0, 2>(Q, G.xy_end, G.xz_end, o, d, inv, tmin, best, best_prim); // xz_rect: y = k
+    small_rects<0, 1, 2>(Q, G.xz_end, G.yz_end, o, d, inv, tmin, best, best_prim); // yz_rect: x = k
+    for (int bi = G.box_begin; bi < G.box_end; bi++) {
+      const SmallBox &B = Q.boxes[bi];
+      const float x0 = (B.lo.x - o[0]) * inv[0], x1 = (B.hi.x - o[0]) * inv[0];
+      const float y0 = (B.lo.y - o[1]) * inv[1], y1 = (B.hi.y - o[1]) * inv[1];
+      const float z0 = (B.lo.z - o[2]) * inv[2], z1 = (B.hi.z - o[2]) * inv[2];
+      const float nx = fminf(x0, x1), fx = fmaxf(x0, x1);
+      const float ny = fminf(y0, y1), fy = fmaxf(y0, y1);
+      const float nz = fminf(z0, z1), fz = fmaxf(z0, z1);
+      const float tn = fmaxf(fmaxf(nx, ny), nz), tf = fminf(fminf(fx, fy), fz);
+      // the closest face hit with t >= t_min is the entry point, or the exit when the origin is inside
+      const bool entry = tn >= tmin;
+      const float t = entry ? tn : tf;
+      const bool ok = (tn <= tf) & (t >= tmin) & (t <= best);
+      if (ok) {
+        const int axis = entry ? (tn == nx ? 0 : (tn == ny ? 1 : 2)) : (tf == fx ? 0 : (tf == fy ? 1 : 2));
+        const float t_lo = axis == 0 ? x0 : (axis == 1 ? y0 : z0);
+        best = t;
+        best_prim = B.face[2 * axis + (t == t_lo ? 0 : 1)];
+      }
+    }
+    if (G.yz_end < G.sph_end) {
+      XRay x;
+      x.o = mk(o[0], o[1], o[2]);
+      x.d = mk(d[0], d[1], d[2]);
+      for (int i = G.yz_end; i < G.sph_end; i++) {
+        const float4 g = Q.geo[i];
+        float t;
+        if (sphere_test<false>(mk(g.x, g.y, g.z), g.w, x, tmin, best, t)) {
+          best = t;
+          best_prim = __float_as_int(Q.aux[i].y);
+        }
+      }
+    }
+  }
+  t_out = best;
+  prim_out = best_prim;
+  return best_prim >= 0;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -824,52 +950,57 @@ struct PathState {
 
 TPT_DEV bool dead_channel(float t) { return t == 0.0f || isnan(t); }
 
-template <bool PAR>
-TPT_DEV bool bounce(const SceneView &S, PathState &ps, Rng &g, int max_depth, float t_min, V3 &radiance) {
-  g.set_stage((uint32_t)ps.depth + 1u);
-  float t;
-  int prim;
-  if (!closest_hit<PAR>(S, ps.ray, t_min, FLT_MAX, t, prim)) {
+// extend(): world->hit plus every outcome that ends the path without a scatter() call
+// (src/utils.cc:61-66,82-86). Returns TPT_EXT_DONE with the sample's radiance, or the kind of the
+// scattering material (LAMBERTIAN / METAL / DIELECTRIC) with (prim, t) of the hit.
+#define TPT_EXT_DONE (-1)
+template <bool PAR, bool SMALL>
+TPT_DEV int extend(const SceneView &S, const PathState &ps, int max_depth, float t_min, float &t, int &prim,
+                   V3 &radiance) {
+  bool any_hit = (SMALL && !PAR) ? closest_hit_uniform(S, ps.ray, t_min, FLT_MAX, t, prim)
+                                 : closest_hit<PAR>(S, ps.ray, t_min, FLT_MAX, t, prim);
+  radiance = mk(0, 0, 0);
+  if (!any_hit) {
     if (S.L->background == TPT_BG_SKY) {
       // the commented gradient src/utils.cc:87-90
       V3 ud = unit<PAR>(ps.ray.d);
       float tt = PAR ? (float)(((double)ud.y + 1.0) * 0.5) : (ud.y + 1.0f) * 0.5f;
       V3 sky = 0.1f * ((1 - tt) * mk(1.0f, 1.0f, 1.0f) + tt * mk(0.5f, 0.7f, 1.0f));
       radiance = ps.T * sky;
-    } else {
-      radiance = mk(0, 0, 0);
     }
-    return false;
+    return TPT_EXT_DONE;
   }
   // tpt_material = {kind, texture, albedo[3], fuzz, ref_idx, pad}
+  const int mat = __float_as_int(S.blob[S.L->off_prims + 4 * prim].y);
+  const float4 m0 = S.blob[S.L->off_mats + 2 * mat];
+  const int mkind = __float_as_int(m0.x);
+  if (mkind == TPT_MAT_DIFFUSE_LIGHT) {
+    // src/material.cc:79-86: one-sided; base scatter() is false -> return emitted
+    const int mtex = __float_as_int(m0.y);
+    HitRec h;
+    fill_hit<PAR>(S, ps.ray, prim, t, texture_needs_uv(S, mtex), h);
+    if (dot(h.n, ps.ray.d) < 0) radiance = ps.T * texture_value<PAR>(S, mtex, h.u, h.v, h.p);
+    return TPT_EXT_DONE;
+  }
+  if (mkind == TPT_MAT_ABSORBER || ps.depth >= max_depth) return TPT_EXT_DONE; // emitted == 0
+  return mkind;
+}
+
+// shade(): material::scatter + the mixture-pdf step of color() for the hit (prim, t).
+// Returns true while the path continues (ps holds the next ray, throughput, depth).
+template <bool PAR> TPT_DEV bool shade(const SceneView &S, PathState &ps, Rng &g, int prim, float t) {
   const int mat = __float_as_int(S.blob[S.L->off_prims + 4 * prim].y);
   const float4 m0 = S.blob[S.L->off_mats + 2 * mat];
   const float4 m1 = S.blob[S.L->off_mats + 2 * mat + 1];
   const int mkind = __float_as_int(m0.x);
   const int mtex = __float_as_int(m0.y);
-  bool want_uv = (mkind == TPT_MAT_LAMBERTIAN || mkind == TPT_MAT_DIFFUSE_LIGHT) && texture_needs_uv(S, mtex);
+  bool want_uv = mkind == TPT_MAT_LAMBERTIAN && texture_needs_uv(S, mtex);
   HitRec h;
   fill_hit<PAR>(S, ps.ray, prim, t, want_uv, h);
-
-  if (mkind == TPT_MAT_DIFFUSE_LIGHT) {
-    // src/material.cc:79-86: one-sided; base scatter() is false -> return emitted
-    if (dot(h.n, ps.ray.d) < 0)
-      radiance = ps.T * texture_value<PAR>(S, mtex, h.u, h.v, h.p);
-    else
-      radiance = mk(0, 0, 0);
-    return false;
-  }
-  if (mkind == TPT_MAT_ABSORBER || ps.depth >= max_depth) {
-    radiance = mk(0, 0, 0); // emitted == 0 for every scattering material
-    return false;
-  }
   if (mkind == TPT_MAT_METAL) { // src/material.cc:88-98
     V3 reflected = reflect(unit<PAR>(ps.ray.d), h.n);
     V3 dir = reflected + m1.y * random_in_unit_sphere(g); // fuzz_
-    if (!(dot(dir, h.n) > 0)) {
-      radiance = mk(0, 0, 0);
-      return false;
-    }
+    if (!(dot(dir, h.n) > 0)) return false;
     ps.T = ps.T * mk(m0.z, m0.w, m1.x); // attenuation = albedo_, no emitted term (src/utils.cc:67-72)
     ps.ray.o = h.p;
     ps.ray.d = dir;
@@ -927,11 +1058,18 @@ TPT_DEV bool bounce(const SceneView &S, PathState &ps, Rng &g, int max_depth, fl
     ps.ray.d = dir;
   }
   ps.depth++;
-  if (dead_channel(ps.T.x) && dead_channel(ps.T.y) && dead_channel(ps.T.z)) {
-    radiance = mk(0, 0, 0);
-    return false;
-  }
-  return true;
+  return !(dead_channel(ps.T.x) && dead_channel(ps.T.y) && dead_channel(ps.T.z));
+}
+
+// one bounce = extend + shade (megakernel form)
+template <bool PAR, bool SMALL>
+TPT_DEV bool bounce(const SceneView &S, PathState &ps, Rng &g, int max_depth, float t_min, V3 &radiance) {
+  g.set_stage((uint32_t)ps.depth + 1u);
+  float t;
+  int prim;
+  int cls = extend<PAR, SMALL>(S, ps, max_depth, t_min, t, prim, radiance);
+  if (cls == TPT_EXT_DONE) return false;
+  return shade<PAR>(S, ps, g, prim, t);
 }
 
 } // namespace tptd

@@ -22,12 +22,13 @@ TPT_DEV const float4 *stage_scene(const SceneLayout &L, float4 *sblob) {
 // ------------------------------------------------------------------------------------------
 // Gate-1 kernel: world->hit(r, tmin, tmax, rec) for a batch of rays
 // ------------------------------------------------------------------------------------------
-template <bool PAR, bool SMEM>
+template <bool PAR, bool SMEM, bool SMALL>
 __global__ void __launch_bounds__(128) intersect_kernel(const __grid_constant__ IntersectArgs A) {
   extern __shared__ float4 sblob[];
   SceneView S;
   S.blob = stage_scene<SMEM>(A.scene, sblob);
   S.L = &A.scene;
+  S.small = &A.small;
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= A.n) return;
   const float *q = A.rays + 7 * idx;
@@ -44,7 +45,9 @@ __global__ void __launch_bounds__(128) intersect_kernel(const __grid_constant__ 
   out.n[0] = out.n[1] = out.n[2] = 0.f;
   float t;
   int prim;
-  if (closest_hit<PAR>(S, r, A.tmin, A.tmax, t, prim)) {
+  bool any_hit = (SMALL && !PAR) ? closest_hit_uniform(S, r, A.tmin, A.tmax, t, prim)
+                                 : closest_hit<PAR>(S, r, A.tmin, A.tmax, t, prim);
+  if (any_hit) {
     HitRec h;
     fill_hit<PAR>(S, r, prim, t, true, h);
     out.hit = 1;
@@ -75,12 +78,13 @@ __global__ void __launch_bounds__(128) intersect_kernel(const __grid_constant__ 
 // Bins are ordered tile-major with the pixel index fastest: the 32 lanes of a warp work on 32
 // neighbouring pixels of one tile.
 // ------------------------------------------------------------------------------------------
-template <bool PAR, bool SMEM>
+template <bool PAR, bool SMEM, bool SMALL>
 __global__ void __launch_bounds__(TPT_MEGA_THREADS) render_mega_kernel(const __grid_constant__ RenderArgs A) {
   extern __shared__ float4 sblob[];
   SceneView S;
   S.blob = stage_scene<SMEM>(A.scene, sblob);
   S.L = &A.scene;
+  S.small = &A.small;
   const unsigned FULL = 0xffffffffu;
   const unsigned lane = threadIdx.x & 31u;
 
@@ -144,7 +148,7 @@ __global__ void __launch_bounds__(TPT_MEGA_THREADS) render_mega_kernel(const __g
     if (active) {
       V3 rad;
       n_rays++;
-      if (!bounce<PAR>(S, ps, rng, A.max_depth, A.t_min, rad)) {
+      if (!bounce<PAR, SMALL>(S, ps, rng, A.max_depth, A.t_min, rad)) {
         // col += de_nan(tmp): main.cpp:126, headers/utils.h:100-109
         bool nan_any = isnan(rad.x) || isnan(rad.y) || isnan(rad.z) || isnan(ps.T.x) ||
                        isnan(ps.T.y) || isnan(ps.T.z);
@@ -172,12 +176,261 @@ __global__ void __launch_bounds__(TPT_MEGA_THREADS) render_mega_kernel(const __g
 }
 
 // ------------------------------------------------------------------------------------------
+// Persistent WAVEFRONT kernel: generate / extend / shade queues in shared memory.
+//
+// A CTA owns TPT_WAVE_SLOTS path slots whose state (ray, throughput, per-pixel accumulator,
+// sample bookkeeping) lives in shared memory as structure-of-arrays. Every iteration runs three
+// phases separated by __syncthreads():
+//   extend      thread i intersects slot i (warp-uniform brute force on small scenes); paths that
+//               end here (miss, lamp, absorber, depth limit) add their radiance to the slot's
+//               accumulator and go to the GENERATE queue, the others to the queue of their
+//               material, compacted with __ballot_sync/__popc + one shared-memory atomic per warp
+//   shade       warps pull 32-item chunks from the material queues: a warp shades 32 lambertian
+//               (or 32 dielectric, or 32 metal) hits together instead of diverging over the
+//               material switch; paths that die in scatter() join the GENERATE queue
+//   generate    the GENERATE queue finishes the sample (k++, store the bin when its range is
+//               complete, grab the next bin from the global work counter) and shoots the next
+//               camera ray, so every slot enters the next extend phase with a live ray
+// Same device functions, same Philox stream and same per-pixel summation order as the
+// megakernel: the two variants are bit-identical in their output and differ only in scheduling.
+// ------------------------------------------------------------------------------------------
+#define TPT_WAVE_NQ 4 // queues: 0 lambertian, 1 metal, 2 dielectric (= TPT_MAT_*), 3 generate
+enum { TPT_SLOT_IDLE = 0, TPT_SLOT_ACTIVE = 1 };
+
+template <bool PAR, bool SMALL>
+__global__ void __launch_bounds__(TPT_WAVE_THREADS) render_wave_kernel(const __grid_constant__ RenderArgs A) {
+  extern __shared__ float4 sblob[];
+  SceneView S;
+  S.blob = stage_scene<true>(A.scene, sblob);
+  S.L = &A.scene;
+  S.small = &A.small;
+  constexpr int NSLOT = TPT_WAVE_SLOTS;
+  constexpr int NWARP = TPT_WAVE_THREADS / 32;
+  float *sf = reinterpret_cast<float *>(sblob + A.scene.blob_words);
+  int *si = reinterpret_cast<int *>(sf);
+  // structure-of-arrays slot state: field f of slot s at sf[f * NSLOT + s]
+  enum { F_OX, F_OY, F_OZ, F_DX, F_DY, F_DZ, F_TIME, F_TX, F_TY, F_TZ, F_AX, F_AY, F_AZ,
+         F_PIXEL, F_K, F_KEND, F_ACCIDX, F_DEPTH, F_HPRIM, F_HT, F_STATE, F_COUNT };
+  unsigned short *queue = reinterpret_cast<unsigned short *>(sf + F_COUNT * NSLOT); // [NQ][NSLOT]
+  __shared__ int q_count[TPT_WAVE_NQ];
+  __shared__ int n_idle;
+#define SF(f, s) sf[(f) * NSLOT + (s)]
+#define SI(f, s) si[(f) * NSLOT + (s)]
+
+  const unsigned FULL = 0xffffffffu;
+  const int tid = threadIdx.x;
+  const unsigned lane = tid & 31u;
+  const int warp = tid >> 5;
+  const unsigned bins_per_tile = (unsigned)(TPT_TILE * TPT_TILE) * (unsigned)A.n_ranges;
+  unsigned long long n_rays = 0, n_nan = 0, n_paths = 0;
+
+  for (int s = tid; s < NSLOT; s += TPT_WAVE_THREADS) {
+    SI(F_STATE, s) = TPT_SLOT_IDLE;
+    SI(F_K, s) = 0;
+    SI(F_KEND, s) = -1; // no bin yet
+    queue[3 * NSLOT + s] = (unsigned short)s;
+  }
+  if (tid < TPT_WAVE_NQ) q_count[tid] = (tid == 3) ? NSLOT : 0;
+  if (tid == 0) n_idle = 0;
+  __syncthreads();
+
+  // warp-aggregated push of `slot` into queue q (all 32 lanes call; `want` selects)
+  auto push = [&](bool want, int q, int slot) {
+    unsigned m = __ballot_sync(FULL, want);
+    if (!m) return;
+    int leader = __ffs(m) - 1;
+    int base = 0;
+    if ((int)lane == leader) base = atomicAdd(&q_count[q], __popc(m));
+    base = __shfl_sync(FULL, base, leader);
+    if (want) queue[q * NSLOT + base + __popc(m & ((1u << lane) - 1u))] = (unsigned short)slot;
+  };
+
+  for (;;) {
+    // ------------------------------------------------------------------ extend
+    for (int s0 = warp * 32; s0 < NSLOT; s0 += TPT_WAVE_THREADS) {
+      const int s = s0 + (int)lane;
+      int cls = -2; // -2: nothing to do
+      if (SI(F_STATE, s) == TPT_SLOT_ACTIVE) {
+        PathState ps;
+        ps.ray.o = mk(SF(F_OX, s), SF(F_OY, s), SF(F_OZ, s));
+        ps.ray.d = mk(SF(F_DX, s), SF(F_DY, s), SF(F_DZ, s));
+        ps.ray.time = SF(F_TIME, s);
+        ps.T = mk(SF(F_TX, s), SF(F_TY, s), SF(F_TZ, s));
+        ps.depth = SI(F_DEPTH, s);
+        float t;
+        int prim;
+        V3 rad;
+        n_rays++;
+        cls = extend<PAR, SMALL>(S, ps, A.max_depth, A.t_min, t, prim, rad);
+        if (cls == TPT_EXT_DONE) {
+          // col += de_nan(tmp): main.cpp:126, headers/utils.h:100-109
+          if (isnan(rad.x) || isnan(rad.y) || isnan(rad.z)) n_nan++;
+          SF(F_AX, s) += isnan(rad.x) ? 0.f : rad.x;
+          SF(F_AY, s) += isnan(rad.y) ? 0.f : rad.y;
+          SF(F_AZ, s) += isnan(rad.z) ? 0.f : rad.z;
+        } else {
+          SI(F_HPRIM, s) = prim;
+          SF(F_HT, s) = t;
+        }
+      }
+      push(cls == TPT_MAT_LAMBERTIAN, 0, s);
+      push(cls == TPT_MAT_METAL, 1, s);
+      push(cls == TPT_MAT_DIELECTRIC, 2, s);
+      push(cls == TPT_EXT_DONE, 3, s);
+    }
+    __syncthreads();
+    // ------------------------------------------------------------------- shade
+    {
+      const int c0 = q_count[0], c1 = q_count[1], c2 = q_count[2];
+      const int t0 = (c0 + 31) >> 5, t1 = (c1 + 31) >> 5, t2 = (c2 + 31) >> 5;
+      for (int wt = warp; wt < t0 + t1 + t2; wt += NWARP) {
+        int q, chunk, cnt;
+        if (wt < t0) { q = 0; chunk = wt; cnt = c0; }
+        else if (wt < t0 + t1) { q = 1; chunk = wt - t0; cnt = c1; }
+        else { q = 2; chunk = wt - t0 - t1; cnt = c2; }
+        const int idx = chunk * 32 + (int)lane;
+        bool died = false;
+        int s = 0;
+        if (idx < cnt) {
+          s = queue[q * NSLOT + idx];
+          PathState ps;
+          ps.ray.o = mk(SF(F_OX, s), SF(F_OY, s), SF(F_OZ, s));
+          ps.ray.d = mk(SF(F_DX, s), SF(F_DY, s), SF(F_DZ, s));
+          ps.ray.time = SF(F_TIME, s);
+          ps.T = mk(SF(F_TX, s), SF(F_TY, s), SF(F_TZ, s));
+          ps.depth = SI(F_DEPTH, s);
+          Rng rng;
+          rng.begin(A.seed_lo, A.seed_hi, (uint32_t)SI(F_PIXEL, s), (uint32_t)SI(F_K, s));
+          rng.set_stage((uint32_t)ps.depth + 1u);
+          bool alive = shade<PAR>(S, ps, rng, SI(F_HPRIM, s), SF(F_HT, s));
+          if (alive) {
+            SF(F_OX, s) = ps.ray.o.x; SF(F_OY, s) = ps.ray.o.y; SF(F_OZ, s) = ps.ray.o.z;
+            SF(F_DX, s) = ps.ray.d.x; SF(F_DY, s) = ps.ray.d.y; SF(F_DZ, s) = ps.ray.d.z;
+            SF(F_TX, s) = ps.T.x; SF(F_TY, s) = ps.T.y; SF(F_TZ, s) = ps.T.z;
+            SI(F_DEPTH, s) = ps.depth;
+          } else {
+            died = true; // contributes 0 (metal absorbed, or throughput 0 / NaN in every channel)
+            if (isnan(ps.T.x) || isnan(ps.T.y) || isnan(ps.T.z)) n_nan++;
+          }
+        }
+        push(died, 3, s);
+      }
+    }
+    __syncthreads();
+    // ---------------------------------------------------------------- generate
+    {
+      const int cg = q_count[3];
+      for (int wt = warp; wt < ((cg + 31) >> 5); wt += NWARP) {
+        const int idx = wt * 32 + (int)lane;
+        const bool mine = idx < cg;
+        const int s = mine ? queue[3 * NSLOT + idx] : 0;
+        int k = 0, k_end = -1, pixel = 0;
+        bool have_bin = false;
+        if (mine) {
+          k_end = SI(F_KEND, s);
+          have_bin = k_end >= 0;
+          k = SI(F_K, s) + (have_bin ? 1 : 0); // the sample that just ended
+          pixel = SI(F_PIXEL, s);
+          if (have_bin && k >= k_end) { // bin finished: one store per (pixel, sample range)
+            float *o = A.acc + (size_t)(unsigned)SI(F_ACCIDX, s) * 3;
+            o[0] = SF(F_AX, s);
+            o[1] = SF(F_AY, s);
+            o[2] = SF(F_AZ, s);
+            have_bin = false;
+          }
+        }
+        bool need = mine && !have_bin;
+        bool exhausted = false;
+        for (;;) { // grab bins until every lane that needs one has a valid pixel or the counter is dry
+          unsigned m = __ballot_sync(FULL, need);
+          if (!m) break;
+          int leader = __ffs(m) - 1;
+          unsigned long long base = 0;
+          if ((int)lane == leader) base = atomicAdd(A.counters + 0, (unsigned long long)__popc(m));
+          base = __shfl_sync(FULL, base, leader);
+          if (need) {
+            unsigned long long b = base + __popc(m & ((1u << lane) - 1u));
+            if (b >= A.n_bins) {
+              exhausted = true;
+              need = false;
+            } else {
+              unsigned bb = (unsigned)b;
+              unsigned tile_local = bb / bins_per_tile;
+              unsigned rem = bb - tile_local * bins_per_tile;
+              unsigned range = rem / (unsigned)(TPT_TILE * TPT_TILE);
+              unsigned pit = rem - range * (unsigned)(TPT_TILE * TPT_TILE);
+              unsigned tile = (unsigned)A.part_index + tile_local * (unsigned)A.part_count;
+              unsigned ty = tile / (unsigned)A.tiles_x, tx = tile - ty * (unsigned)A.tiles_x;
+              int px = (int)(tx * TPT_TILE + (pit & (TPT_TILE - 1)));
+              int py = (int)(ty * TPT_TILE + (pit / TPT_TILE));
+              if (px < A.nx && py < A.ny) {
+                need = false;
+                have_bin = true;
+                pixel = py * A.nx + px;
+                k = A.range_bounds[range];
+                k_end = A.range_bounds[range + 1];
+                SI(F_PIXEL, s) = pixel;
+                SI(F_KEND, s) = k_end;
+                SI(F_ACCIDX, s) = (int)(range * (unsigned)(A.nx * A.ny) + (unsigned)pixel);
+                SF(F_AX, s) = 0.f;
+                SF(F_AY, s) = 0.f;
+                SF(F_AZ, s) = 0.f;
+              }
+            }
+          }
+        }
+        if (mine) {
+          if (have_bin) {
+            Rng rng;
+            rng.begin(A.seed_lo, A.seed_hi, (uint32_t)pixel, (uint32_t)k);
+            const int py = pixel / A.nx, px = pixel - py * A.nx;
+            Ray r = camera_sample<PAR>(A.cam, px, py, A.nx, A.ny, rng);
+            SF(F_OX, s) = r.o.x; SF(F_OY, s) = r.o.y; SF(F_OZ, s) = r.o.z;
+            SF(F_DX, s) = r.d.x; SF(F_DY, s) = r.d.y; SF(F_DZ, s) = r.d.z;
+            SF(F_TIME, s) = r.time;
+            SF(F_TX, s) = 1.f; SF(F_TY, s) = 1.f; SF(F_TZ, s) = 1.f;
+            SI(F_DEPTH, s) = 0;
+            SI(F_K, s) = k;
+            SI(F_STATE, s) = TPT_SLOT_ACTIVE;
+            n_paths++;
+          } else if (exhausted) {
+            SI(F_STATE, s) = TPT_SLOT_IDLE;
+            SI(F_KEND, s) = -1;
+            atomicAdd(&n_idle, 1);
+          }
+        }
+      }
+    }
+    __syncthreads();
+    const bool done = n_idle >= NSLOT;
+    __syncthreads();
+    if (tid < TPT_WAVE_NQ) q_count[tid] = 0;
+    if (done) break;
+    __syncthreads();
+  }
+#undef SF
+#undef SI
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    n_rays += __shfl_xor_sync(FULL, n_rays, o);
+    n_nan += __shfl_xor_sync(FULL, n_nan, o);
+    n_paths += __shfl_xor_sync(FULL, n_paths, o);
+  }
+  if (lane == 0) {
+    atomicAdd(A.counters + 1, n_rays);
+    atomicAdd(A.counters + 2, n_nan);
+    atomicAdd(A.counters + 3, n_paths);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // Known-answer probes
 // ------------------------------------------------------------------------------------------
 template <bool PAR> __global__ void texture_probe_kernel(const __grid_constant__ TextureProbeArgs A) {
   SceneView S;
   S.blob = A.scene.blob_global;
   S.L = &A.scene;
+  S.small = nullptr;
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= A.n) return;
   const float *q = A.uvp + 5 * idx;
@@ -199,37 +452,57 @@ template <typename K> static cudaError_t allow_smem(K kernel, size_t bytes) {
   return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
-cudaError_t TPT_FN(launch_intersect_)(const IntersectArgs &A, bool smem, cudaStream_t st) {
+cudaError_t TPT_FN(launch_intersect_)(const IntersectArgs &A, bool smem, bool small, cudaStream_t st) {
   size_t bytes = smem ? (size_t)A.scene.blob_words * 16 : 0;
   int blocks = (int)((A.n + 127) / 128);
   if (blocks == 0) return cudaSuccess;
+  typedef void (*fn)(IntersectArgs);
+  fn k = smem ? (small ? (fn)intersect_kernel<TPT_PAR, true, true> : (fn)intersect_kernel<TPT_PAR, true, false>)
+              : (fn)intersect_kernel<TPT_PAR, false, false>;
   cudaError_t e;
-  if (smem) {
-    if ((e = allow_smem(intersect_kernel<TPT_PAR, true>, bytes)) != cudaSuccess) return e;
-    intersect_kernel<TPT_PAR, true><<<blocks, 128, bytes, st>>>(A);
-  } else {
-    intersect_kernel<TPT_PAR, false><<<blocks, 128, 0, st>>>(A);
-  }
+  if (smem && (e = allow_smem(k, bytes)) != cudaSuccess) return e;
+  k<<<blocks, 128, bytes, st>>>(A);
   return cudaGetLastError();
 }
 
-cudaError_t TPT_FN(mega_occupancy_)(bool smem, size_t smem_bytes, int *blocks_per_sm) {
-  cudaError_t e;
-  if (smem) {
-    if ((e = allow_smem(render_mega_kernel<TPT_PAR, true>, smem_bytes)) != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, render_mega_kernel<TPT_PAR, true>,
-                                                         TPT_MEGA_THREADS, smem_bytes);
-  }
-  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, render_mega_kernel<TPT_PAR, false>,
-                                                       TPT_MEGA_THREADS, 0);
+// kernel variant table: [smem][small]
+typedef void (*mega_fn)(RenderArgs);
+static mega_fn mega_variant(bool smem, bool small) {
+  if (smem) return small ? render_mega_kernel<TPT_PAR, true, true> : render_mega_kernel<TPT_PAR, true, false>;
+  return small ? render_mega_kernel<TPT_PAR, false, true> : render_mega_kernel<TPT_PAR, false, false>;
 }
 
-cudaError_t TPT_FN(launch_mega_)(const RenderArgs &A, bool smem, int blocks, cudaStream_t st) {
+cudaError_t TPT_FN(mega_occupancy_)(bool smem, bool small, size_t smem_bytes, int *blocks_per_sm) {
+  mega_fn k = mega_variant(smem, small);
+  cudaError_t e;
+  if (smem && (e = allow_smem(k, smem_bytes)) != cudaSuccess) return e;
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k, TPT_MEGA_THREADS, smem ? smem_bytes : 0);
+}
+
+cudaError_t TPT_FN(launch_mega_)(const RenderArgs &A, bool smem, bool small, int blocks, cudaStream_t st) {
   size_t bytes = smem ? (size_t)A.scene.blob_words * 16 : 0;
-  if (smem)
-    render_mega_kernel<TPT_PAR, true><<<blocks, TPT_MEGA_THREADS, bytes, st>>>(A);
-  else
-    render_mega_kernel<TPT_PAR, false><<<blocks, TPT_MEGA_THREADS, 0, st>>>(A);
+  mega_variant(smem, small)<<<blocks, TPT_MEGA_THREADS, bytes, st>>>(A);
+  return cudaGetLastError();
+}
+
+typedef void (*wave_fn)(RenderArgs);
+static wave_fn wave_variant(bool small) {
+  return small ? render_wave_kernel<TPT_PAR, true> : render_wave_kernel<TPT_PAR, false>;
+}
+static size_t wave_smem_bytes(const RenderArgs &A) {
+  return (size_t)A.scene.blob_words * 16 + (size_t)TPT_WAVE_SLOTS * (21 * 4 + TPT_WAVE_NQ * 2);
+}
+
+cudaError_t TPT_FN(wave_occupancy_)(const RenderArgs &A, bool small, int *blocks_per_sm) {
+  wave_fn k = wave_variant(small);
+  size_t bytes = wave_smem_bytes(A);
+  cudaError_t e = allow_smem(k, bytes);
+  if (e != cudaSuccess) return e;
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k, TPT_WAVE_THREADS, bytes);
+}
+
+cudaError_t TPT_FN(launch_wave_)(const RenderArgs &A, bool small, int blocks, cudaStream_t st) {
+  wave_variant(small)<<<blocks, TPT_WAVE_THREADS, wave_smem_bytes(A), st>>>(A);
   return cudaGetLastError();
 }
 

@@ -4,11 +4,14 @@
 #include "tpt_device.cuh"
 
 #define TPT_MEGA_THREADS 256
+#define TPT_WAVE_THREADS 256
+#define TPT_WAVE_SLOTS 256
 
 namespace tptd {
 
 struct IntersectArgs {
   SceneLayout scene;
+  SmallScene small;
   const float *rays; // n x 7
   size_t n;
   float tmin, tmax;
@@ -17,6 +20,7 @@ struct IntersectArgs {
 
 struct RenderArgs {
   SceneLayout scene;
+  SmallScene small;
   CamView cam;
   int nx, ny, ns, max_depth;
   float t_min;
@@ -37,12 +41,18 @@ struct TextureProbeArgs {
   float *out; // n x 3
 };
 
-cudaError_t launch_intersect_parity(const IntersectArgs &A, bool smem, cudaStream_t st);
-cudaError_t launch_intersect_fast(const IntersectArgs &A, bool smem, cudaStream_t st);
-cudaError_t mega_occupancy_parity(bool smem, size_t smem_bytes, int *blocks_per_sm);
-cudaError_t mega_occupancy_fast(bool smem, size_t smem_bytes, int *blocks_per_sm);
-cudaError_t launch_mega_parity(const RenderArgs &A, bool smem, int blocks, cudaStream_t st);
-cudaError_t launch_mega_fast(const RenderArgs &A, bool smem, int blocks, cudaStream_t st);
+cudaError_t launch_intersect_parity(const IntersectArgs &A, bool smem, bool small, cudaStream_t st);
+cudaError_t launch_intersect_fast(const IntersectArgs &A, bool smem, bool small, cudaStream_t st);
+// `small`: scene has few enough primitives for the warp-uniform brute-force closest hit
+cudaError_t mega_occupancy_parity(bool smem, bool small, size_t smem_bytes, int *blocks_per_sm);
+cudaError_t mega_occupancy_fast(bool smem, bool small, size_t smem_bytes, int *blocks_per_sm);
+cudaError_t launch_mega_parity(const RenderArgs &A, bool smem, bool small, int blocks, cudaStream_t st);
+cudaError_t launch_mega_fast(const RenderArgs &A, bool smem, bool small, int blocks, cudaStream_t st);
+// persistent wavefront variant (scene must be shared-memory resident)
+cudaError_t wave_occupancy_parity(const RenderArgs &A, bool small, int *blocks_per_sm);
+cudaError_t wave_occupancy_fast(const RenderArgs &A, bool small, int *blocks_per_sm);
+cudaError_t launch_wave_parity(const RenderArgs &A, bool small, int blocks, cudaStream_t st);
+cudaError_t launch_wave_fast(const RenderArgs &A, bool small, int blocks, cudaStream_t st);
 cudaError_t launch_texture_probe_parity(const TextureProbeArgs &A, cudaStream_t st);
 cudaError_t launch_texture_probe_fast(const TextureProbeArgs &A, cudaStream_t st);
 cudaError_t launch_philox_probe(const uint32_t ctr[4], const uint32_t key[2], uint32_t *d_out, cudaStream_t st);
