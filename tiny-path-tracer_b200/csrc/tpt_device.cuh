@@ -129,6 +129,15 @@ TPT_DEV void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, u
   out[3] = c3;
 }
 
+// out-of-line block function for the rare refills (keeps the Rng state in registers: nothing
+// takes its address)
+static __device__ __noinline__ uint4 philox_block_slow(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                                uint32_t k1) {
+  uint32_t o[4];
+  philox4x32_10(c0, c1, c2, c3, k0, k1, o);
+  return make_uint4(o[0], o[1], o[2], o[3]);
+}
+
 struct Rng {
   uint32_t k0, k1, pixel, sample, stage, ndraw;
   uint32_t b0, b1, b2, b3;
@@ -140,21 +149,32 @@ struct Rng {
     stage = 0;
     ndraw = 0;
   }
+  // Start a stage and generate its first block right away: camera (u, v, lens y, lens x),
+  // lambertian (mixture pick, light index, 2 coordinates), dielectric (1) and the first round of
+  // metal's rejection loop (3) all fit in four draws, so the block function is expanded at ONE
+  // place per stage instead of at every draw (instruction-cache footprint) and next() is three
+  // selects. Draws beyond four (rejection-loop retries, shutter time) take the out-of-line refill.
   TPT_DEV void set_stage(uint32_t s) {
     stage = s;
     ndraw = 0;
+    uint32_t o[4];
+    philox4x32_10(pixel, sample, stage, 0u, k0, k1, o);
+    b0 = o[0];
+    b1 = o[1];
+    b2 = o[2];
+    b3 = o[3];
+  }
+  TPT_DEV void refill() {
+    uint4 o = philox_block_slow(pixel, sample, stage, ndraw >> 2, k0, k1);
+    b0 = o.x;
+    b1 = o.y;
+    b2 = o.z;
+    b3 = o.w;
   }
   // next uniform in [0,1): (x >> 8) * 2^-24, exactly representable in fp32
   TPT_DEV float next() {
     uint32_t lane = ndraw & 3u;
-    if (lane == 0) {
-      uint32_t o[4];
-      philox4x32_10(pixel, sample, stage, ndraw >> 2, k0, k1, o);
-      b0 = o[0];
-      b1 = o[1];
-      b2 = o[2];
-      b3 = o[3];
-    }
+    if (lane == 0 && ndraw != 0) refill();
     uint32_t x = lane == 0 ? b0 : (lane == 1 ? b1 : (lane == 2 ? b2 : b3));
     ndraw++;
     return (float)(x >> 8) * 5.9604644775390625e-8f;
@@ -900,6 +920,7 @@ struct CamView {
 
 template <bool PAR>
 TPT_DEV Ray camera_sample(const CamView &C, int i, int j, int nx, int ny, Rng &g) {
+  g.set_stage(0u);
   float r_u = g.next();
   float r_v = g.next();
   float s, t;
@@ -989,6 +1010,7 @@ TPT_DEV int extend(const SceneView &S, const PathState &ps, int max_depth, float
 // shade(): material::scatter + the mixture-pdf step of color() for the hit (prim, t).
 // Returns true while the path continues (ps holds the next ray, throughput, depth).
 template <bool PAR> TPT_DEV bool shade(const SceneView &S, PathState &ps, Rng &g, int prim, float t) {
+  g.set_stage((uint32_t)ps.depth + 1u); // stage d+1 = the draws color() makes at depth d
   const int mat = __float_as_int(S.blob[S.L->off_prims + 4 * prim].y);
   const float4 m0 = S.blob[S.L->off_mats + 2 * mat];
   const float4 m1 = S.blob[S.L->off_mats + 2 * mat + 1];
@@ -1064,7 +1086,6 @@ template <bool PAR> TPT_DEV bool shade(const SceneView &S, PathState &ps, Rng &g
 // one bounce = extend + shade (megakernel form)
 template <bool PAR, bool SMALL>
 TPT_DEV bool bounce(const SceneView &S, PathState &ps, Rng &g, int max_depth, float t_min, V3 &radiance) {
-  g.set_stage((uint32_t)ps.depth + 1u);
   float t;
   int prim;
   int cls = extend<PAR, SMALL>(S, ps, max_depth, t_min, t, prim, radiance);

@@ -301,7 +301,6 @@ __global__ void __launch_bounds__(TPT_WAVE_THREADS) render_wave_kernel(const __g
           ps.depth = SI(F_DEPTH, s);
           Rng rng;
           rng.begin(A.seed_lo, A.seed_hi, (uint32_t)SI(F_PIXEL, s), (uint32_t)SI(F_K, s));
-          rng.set_stage((uint32_t)ps.depth + 1u);
           bool alive = shade<PAR>(S, ps, rng, SI(F_HPRIM, s), SF(F_HT, s));
           if (alive) {
             SF(F_OX, s) = ps.ray.o.x; SF(F_OY, s) = ps.ray.o.y; SF(F_OZ, s) = ps.ray.o.z;
