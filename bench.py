@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="fast", choices=["fast", "parity"])
     ap.add_argument("--variant", default="A", choices=["A", "B"])
+    ap.add_argument("--kernel", default="wavefront", choices=["wavefront", "mega"])
     ap.add_argument("--spp", type=int, default=NS, help="override samples per pixel (default: the headline 2048)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the bounded baseline sample")
@@ -201,8 +202,9 @@ def run_ours(args, rank, local_rank, world):
     hs = T.HostScene("cornell_box")
     scene = T.Scene(hs, device=local_rank)
     cam = T.cornell_camera(NX, NY, fov=v["fov"])
+    kernel = T.KERNEL_WAVEFRONT if args.kernel == "wavefront" else T.KERNEL_MEGA
     params = T.make_params(NX, NY, args.spp, v["depth"], mode=mode, seed=0x5EED, part_index=rank, part_count=world,
-                           device=local_rank)
+                           device=local_rank, kernel=kernel)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     for _ in range(max(args.warmup, 0)):
@@ -281,13 +283,13 @@ def run_ours(args, rank, local_rank, world):
     traffic = None
     try:
         prof = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json")))
-        traffic = prof.get("render_mega_kernel", {}).get("dram_bytes_per_launch")
+        traffic = prof.get("render_wave_kernel" if args.kernel == "wavefront" else "render_mega_kernel", {}).get("dram_bytes_per_launch")
     except Exception:
         pass
     acc_bytes = npix / world * 12 * max(1, min(8, (args.spp // 256) or 1))
     roofline = {
         "bound": "fp32", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops,
-        "traffic": traffic, "kernel": "render_mega_kernel",
+        "traffic": traffic, "kernel": "render_wave_kernel" if args.kernel == "wavefront" else "render_mega_kernel",
         "peak_source": f"{sm_count} SMs x {SM_FP32_LANES} FP32 lanes x 2 FLOP x {sm_max:.0f} MHz (clocks.max.sm); no tensor/HBM "
                        "bound applies (SURVEY 8d): MEASURED_PEAKS.json has no FP32-issue figure, so this is the nominal one",
         "flop_per_path": F_PATH[args.variant],
@@ -309,7 +311,7 @@ def run_ours(args, rank, local_rank, world):
         "scaling": "strong", "vs_baseline": value / PUBLISHED_MPATHS, "dtype": "f32" if args.mode == "fast" else "f32+f64",
         "data": "synthetic",
         "config": {"workload": f"Cornell box metal+glass 1200x1200 @ {args.spp} spp, variant {args.variant} "
-                               f"(fov {v['fov']}, depth {v['depth']}, aperture 0.1), {args.mode} mode megakernel",
+                               f"(fov {v['fov']}, depth {v['depth']}, aperture 0.1), {args.mode} mode, {args.kernel} kernel",
                    "paths_per_step": total_paths / args.steps, "partition": f"static interleaved 16x16 tiles over {world} rank(s)",
                    "l2": "256 MiB memset between steps (flush); scene working set is shared-memory resident",
                    "published_baseline": "README.md:22: 941 s on Xeon E5-2630 v4 = 3.13 Mpaths/s (fov/depth unstated)"},

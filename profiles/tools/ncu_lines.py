@@ -34,6 +34,33 @@ tot_i = sum(l[0] for l in lines)
 tot_t = sum(l[1] for l in lines)
 tot_s = sum(l[2] for l in lines)
 print(f"total warp-inst {tot_i:.4g}  thread-inst {tot_t:.4g}  avg active {tot_t / max(tot_i, 1):.2f}  samples {tot_s}")
+# ---- per function (nearest preceding definition line in the same file) ----
+import bisect, collections, os, re
+here = os.path.dirname(os.path.abspath(__file__))
+src_dir = os.path.join(here, "..", "..", "tiny-path-tracer_b200", "csrc")
+defs = {}
+for fn in os.listdir(src_dir):
+    if fn.endswith((".cuh", ".cu", ".h")):
+        L = open(os.path.join(src_dir, fn)).read().split("\n")
+        marks = []
+        for i, l in enumerate(L):
+            m = re.match(r"(?:template\s*<[^>]*>\s*)?(?:static\s+)?(?:TPT_DEV|__global__|__device__)[^(]*?([A-Za-z_0-9]+)\s*\(", l)
+            if m and not l.startswith("TPT_DEV V3 operator") and not l.startswith("TPT_DEV float dot") and "{ return" not in l:
+                marks.append((i + 1, m.group(1)))
+        defs[fn] = marks
+agg = collections.defaultdict(lambda: [0, 0, 0])
+for inst, tinst, samples, f, ln, src in lines:
+    name = f
+    if f in defs and defs[f]:
+        idx = bisect.bisect_right([m[0] for m in defs[f]], int(ln)) - 1
+        if idx >= 0:
+            name = defs[f][idx][1]
+    a = agg[name]
+    a[0] += inst; a[1] += tinst; a[2] += samples
+print(f"{'warp-inst%':>10} {'samples%':>9} {'active':>6}  function")
+for name, (inst, tinst, samples) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:25]:
+    print(f"{100 * inst / tot_i:10.2f} {100 * samples / max(tot_s, 1):9.2f} {tinst / max(inst, 1):6.1f}  {name}")
+print()
 print(f"{'warp-inst%':>10} {'samples%':>9} {'active':>6}  file:line  source")
 for inst, tinst, samples, f, ln, src in sorted(lines, reverse=True)[:top]:
     print(f"{100 * inst / tot_i:10.2f} {100 * samples / max(tot_s, 1):9.2f} {tinst / max(inst, 1):6.1f}  {f}:{ln}  {src}")

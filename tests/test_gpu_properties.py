@@ -47,6 +47,53 @@ def test_partition_invariance(T, cornell, mode):
     assert np.array_equal(acc, whole.sum_rgb)
 
 
+@pytest.mark.parametrize("mode", ["parity", "fast"])
+def test_wavefront_equals_megakernel(T, cornell, mode):
+    """the two scheduling variants run the same device functions on the same Philox stream with
+    the same per-pixel summation order: bit-identical sums, identical ray / NaN statistics."""
+    m = T.MODE_PARITY if mode == "parity" else T.MODE_FAST
+    nx, ny, ns = 200, 136, 24
+    for fov, depth in ((90.0, 15), (61.93, 50)):
+        cam = T.cornell_camera(nx, ny, fov=fov)
+        a = cornell.render(cam, T.make_params(nx, ny, ns, depth, mode=m, seed=21, kernel=T.KERNEL_MEGA, slices=3), want_slices=True)
+        b = cornell.render(cam, T.make_params(nx, ny, ns, depth, mode=m, seed=21, kernel=T.KERNEL_WAVEFRONT, slices=3), want_slices=True)
+        if mode == "parity":  # no FMA contraction: every operation is the same in both kernels
+            assert np.array_equal(a.sum_rgb, b.sum_rgb)
+            assert np.array_equal(a.rgb8, b.rgb8) and np.array_equal(a.rgb8_slices, b.rgb8_slices)
+            for k in ("paths", "rays", "nan_samples"):
+                assert a.stats[k] == b.stats[k], k
+        else:  # fast: the compiler contracts different mul/add pairs in the two kernels (ulp-level)
+            rel = common.rel_err(b.sum_rgb, a.sum_rgb, 1e-3 * ns)
+            assert (rel > 1e-4).any(axis=-1).mean() < 0.02
+            assert a.stats["paths"] == b.stats["paths"]
+            assert abs(a.stats["rays"] - b.stats["rays"]) <= 2e-3 * a.stats["rays"]
+
+
+def test_wavefront_partition_and_tail(T, cornell):
+    """wavefront variant: 3-way tile split reproduces the whole frame; tiny frames (fewer bins than
+    slots) and a frame whose size is not a multiple of the tile work."""
+    nx, ny, ns = 150, 90, 8
+    cam = T.cornell_camera(nx, ny)
+    whole = cornell.render(cam, T.make_params(nx, ny, ns, 15, seed=5, kernel=T.KERNEL_WAVEFRONT, subs=1))
+    acc = np.zeros_like(whole.sum_rgb)
+    for part in range(3):
+        acc += cornell.render(cam, T.make_params(nx, ny, ns, 15, seed=5, kernel=T.KERNEL_WAVEFRONT, part_index=part,
+                                                 part_count=3, subs=1)).sum_rgb
+    assert np.array_equal(acc, whole.sum_rgb)
+    tiny = cornell.render(T.cornell_camera(3, 2), T.make_params(3, 2, 5, 15, seed=5, kernel=T.KERNEL_WAVEFRONT))
+    ref = cornell.render(T.cornell_camera(3, 2), T.make_params(3, 2, 5, 15, seed=5, kernel=T.KERNEL_MEGA))
+    assert np.array_equal(tiny.sum_rgb, ref.sum_rgb) and tiny.stats["paths"] == 30
+
+
+def test_wavefront_needs_resident_scene(T, gpu):
+    """random_scene (92 KB of tables) does not fit the shared-memory budget of the wavefront
+    variant: the call is refused, not silently rerouted."""
+    sc = T.Scene(common.host_scene(T, "random_scene"))
+    with pytest.raises(T.TptError) as e:
+        sc.render(T.book_camera(32, 32), T.make_params(32, 32, 2, 5, kernel=T.KERNEL_WAVEFRONT))
+    assert e.value.code == -4
+
+
 def test_sub_range_invariance(T, cornell):
     """cutting a pixel's samples into sub-ranges only changes the fp32 summation order."""
     nx = ny = 128

@@ -24,7 +24,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 REPO_ROOT = os.path.dirname(_HERE)
 LIB_DIR = os.path.join(_HERE, "lib")
-LIBTPT = os.path.join(LIB_DIR, "libtpt.so")
+LIBTPT = os.environ.get("TPT_LIBTPT", os.path.join(LIB_DIR, "libtpt.so"))  # override: tuning builds only
 LIBHOST = os.path.join(LIB_DIR, "libtpt_host.so")
 
 TPT_API_VERSION = 1

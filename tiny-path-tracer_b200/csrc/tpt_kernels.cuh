@@ -178,24 +178,29 @@ __global__ void __launch_bounds__(TPT_MEGA_THREADS) render_mega_kernel(const __g
 // ------------------------------------------------------------------------------------------
 // Persistent WAVEFRONT kernel: generate / extend / shade queues in shared memory.
 //
-// A CTA owns TPT_WAVE_SLOTS path slots whose state (ray, throughput, per-pixel accumulator,
-// sample bookkeeping) lives in shared memory as structure-of-arrays. Every iteration runs three
-// phases separated by __syncthreads():
-//   extend      thread i intersects slot i (warp-uniform brute force on small scenes); paths that
-//               end here (miss, lamp, absorber, depth limit) add their radiance to the slot's
-//               accumulator and go to the GENERATE queue, the others to the queue of their
-//               material, compacted with __ballot_sync/__popc + one shared-memory atomic per warp
-//   shade       warps pull 32-item chunks from the material queues: a warp shades 32 lambertian
-//               (or 32 dielectric, or 32 metal) hits together instead of diverging over the
-//               material switch; paths that die in scatter() join the GENERATE queue
-//   generate    the GENERATE queue finishes the sample (k++, store the bin when its range is
-//               complete, grab the next bin from the global work counter) and shoots the next
-//               camera ray, so every slot enters the next extend phase with a live ray
+// A CTA owns TPT_WAVE_SLOTS path slots (two per thread) whose state -- ray, throughput, per-pixel
+// accumulator, sample bookkeeping, pending hit -- lives in shared memory as structure-of-arrays.
+// Every iteration has two phases separated by __syncthreads():
+//   extend          each thread intersects its slots (warp-uniform brute force on small scenes).
+//                   Paths that end here (miss, lamp, absorber, depth limit) add their radiance to
+//                   the slot's accumulator and go to the GENERATE queue, the others to the queue of
+//                   their material. Queues are compacted with __ballot_sync/__popc and ONE packed
+//                   64-bit shared-memory atomic per warp.
+//   shade+generate  warps pull 32-item chunks from the queues: a warp shades 32 lambertian (or 32
+//                   dielectric, or 32 metal) hits together instead of diverging over the material
+//                   switch, or finishes 32 samples together (k++, store the bin when its range is
+//                   complete, grab the next bin from the global work counter, shoot the next camera
+//                   ray). Paths that die inside scatter() are queued for the next iteration's
+//                   generate step (queue counters are double-buffered by iteration parity).
 // Same device functions, same Philox stream and same per-pixel summation order as the
-// megakernel: the two variants are bit-identical in their output and differ only in scheduling.
+// megakernel: the two variants produce bit-identical images and differ only in scheduling.
+//
+// Evaluated alternative (profiles/r01_wave_warp_autonomous_rejected_metrics.csv): one autonomous
+// queue scheduler per WARP, no block barriers. Its warps drift into different stages, the SM's
+// instruction working set becomes the whole kernel (~80 KB) and the "no instruction" stall grows
+// from 1.6 to 7.2 cycles per issued instruction; it ran 35 % slower than this lock-step form.
 // ------------------------------------------------------------------------------------------
 #define TPT_WAVE_NQ 4 // queues: 0 lambertian, 1 metal, 2 dielectric (= TPT_MAT_*), 3 generate
-enum { TPT_SLOT_IDLE = 0, TPT_SLOT_ACTIVE = 1 };
 
 template <bool PAR, bool SMALL>
 __global__ void __launch_bounds__(TPT_WAVE_THREADS) render_wave_kernel(const __grid_constant__ RenderArgs A) {
@@ -210,47 +215,43 @@ __global__ void __launch_bounds__(TPT_WAVE_THREADS) render_wave_kernel(const __g
   int *si = reinterpret_cast<int *>(sf);
   // structure-of-arrays slot state: field f of slot s at sf[f * NSLOT + s]
   enum { F_OX, F_OY, F_OZ, F_DX, F_DY, F_DZ, F_TIME, F_TX, F_TY, F_TZ, F_AX, F_AY, F_AZ,
-         F_PIXEL, F_K, F_KEND, F_ACCIDX, F_DEPTH, F_HPRIM, F_HT, F_STATE, F_COUNT };
-  unsigned short *queue = reinterpret_cast<unsigned short *>(sf + F_COUNT * NSLOT); // [NQ][NSLOT]
-  __shared__ int q_count[TPT_WAVE_NQ];
+         F_PIXEL, F_K, F_KEND, F_ACCIDX, F_DEPTH, F_HPRIM, F_HT, F_ACTIVE, F_COUNT };
+  // queue[parity][q][NSLOT] slot ids; counters packed 4 x 16 bit in one 64-bit word per parity
+  unsigned short *queue = reinterpret_cast<unsigned short *>(sf + F_COUNT * NSLOT);
+  __shared__ unsigned long long q_packed[2];
   __shared__ int n_idle;
 #define SF(f, s) sf[(f) * NSLOT + (s)]
 #define SI(f, s) si[(f) * NSLOT + (s)]
+#define QUEUE(par, q) (queue + ((par) * TPT_WAVE_NQ + (q)) * NSLOT)
 
   const unsigned FULL = 0xffffffffu;
   const int tid = threadIdx.x;
   const unsigned lane = tid & 31u;
+  const unsigned lt_mask = (1u << lane) - 1u;
   const int warp = tid >> 5;
   const unsigned bins_per_tile = (unsigned)(TPT_TILE * TPT_TILE) * (unsigned)A.n_ranges;
   unsigned long long n_rays = 0, n_nan = 0, n_paths = 0;
 
   for (int s = tid; s < NSLOT; s += TPT_WAVE_THREADS) {
-    SI(F_STATE, s) = TPT_SLOT_IDLE;
+    SI(F_ACTIVE, s) = 0;
     SI(F_K, s) = 0;
     SI(F_KEND, s) = -1; // no bin yet
-    queue[3 * NSLOT + s] = (unsigned short)s;
+    QUEUE(0, 3)[s] = (unsigned short)s;
   }
-  if (tid < TPT_WAVE_NQ) q_count[tid] = (tid == 3) ? NSLOT : 0;
-  if (tid == 0) n_idle = 0;
+  if (tid == 0) {
+    q_packed[0] = (unsigned long long)NSLOT << 48; // everything starts in GENERATE
+    q_packed[1] = 0;
+    n_idle = 0;
+  }
   __syncthreads();
 
-  // warp-aggregated push of `slot` into queue q (all 32 lanes call; `want` selects)
-  auto push = [&](bool want, int q, int slot) {
-    unsigned m = __ballot_sync(FULL, want);
-    if (!m) return;
-    int leader = __ffs(m) - 1;
-    int base = 0;
-    if ((int)lane == leader) base = atomicAdd(&q_count[q], __popc(m));
-    base = __shfl_sync(FULL, base, leader);
-    if (want) queue[q * NSLOT + base + __popc(m & ((1u << lane) - 1u))] = (unsigned short)slot;
-  };
-
-  for (;;) {
+  for (int par = 0;; par ^= 1) {
     // ------------------------------------------------------------------ extend
+    if (tid == 0) q_packed[par ^ 1] = 0; // next iteration's counters (nobody touches them before the barrier)
     for (int s0 = warp * 32; s0 < NSLOT; s0 += TPT_WAVE_THREADS) {
       const int s = s0 + (int)lane;
       int cls = -2; // -2: nothing to do
-      if (SI(F_STATE, s) == TPT_SLOT_ACTIVE) {
+      if (SI(F_ACTIVE, s)) {
         PathState ps;
         ps.ray.o = mk(SF(F_OX, s), SF(F_OY, s), SF(F_OZ, s));
         ps.ray.d = mk(SF(F_DX, s), SF(F_DY, s), SF(F_DZ, s));
@@ -268,147 +269,173 @@ __global__ void __launch_bounds__(TPT_WAVE_THREADS) render_wave_kernel(const __g
           SF(F_AX, s) += isnan(rad.x) ? 0.f : rad.x;
           SF(F_AY, s) += isnan(rad.y) ? 0.f : rad.y;
           SF(F_AZ, s) += isnan(rad.z) ? 0.f : rad.z;
+          SI(F_ACTIVE, s) = 0;
         } else {
           SI(F_HPRIM, s) = prim;
           SF(F_HT, s) = t;
         }
       }
-      push(cls == TPT_MAT_LAMBERTIAN, 0, s);
-      push(cls == TPT_MAT_METAL, 1, s);
-      push(cls == TPT_MAT_DIELECTRIC, 2, s);
-      push(cls == TPT_EXT_DONE, 3, s);
-    }
-    __syncthreads();
-    // ------------------------------------------------------------------- shade
-    {
-      const int c0 = q_count[0], c1 = q_count[1], c2 = q_count[2];
-      const int t0 = (c0 + 31) >> 5, t1 = (c1 + 31) >> 5, t2 = (c2 + 31) >> 5;
-      for (int wt = warp; wt < t0 + t1 + t2; wt += NWARP) {
-        int q, chunk, cnt;
-        if (wt < t0) { q = 0; chunk = wt; cnt = c0; }
-        else if (wt < t0 + t1) { q = 1; chunk = wt - t0; cnt = c1; }
-        else { q = 2; chunk = wt - t0 - t1; cnt = c2; }
-        const int idx = chunk * 32 + (int)lane;
-        bool died = false;
-        int s = 0;
-        if (idx < cnt) {
-          s = queue[q * NSLOT + idx];
-          PathState ps;
-          ps.ray.o = mk(SF(F_OX, s), SF(F_OY, s), SF(F_OZ, s));
-          ps.ray.d = mk(SF(F_DX, s), SF(F_DY, s), SF(F_DZ, s));
-          ps.ray.time = SF(F_TIME, s);
-          ps.T = mk(SF(F_TX, s), SF(F_TY, s), SF(F_TZ, s));
-          ps.depth = SI(F_DEPTH, s);
-          Rng rng;
-          rng.begin(A.seed_lo, A.seed_hi, (uint32_t)SI(F_PIXEL, s), (uint32_t)SI(F_K, s));
-          bool alive = shade<PAR>(S, ps, rng, SI(F_HPRIM, s), SF(F_HT, s));
-          if (alive) {
-            SF(F_OX, s) = ps.ray.o.x; SF(F_OY, s) = ps.ray.o.y; SF(F_OZ, s) = ps.ray.o.z;
-            SF(F_DX, s) = ps.ray.d.x; SF(F_DY, s) = ps.ray.d.y; SF(F_DZ, s) = ps.ray.d.z;
-            SF(F_TX, s) = ps.T.x; SF(F_TY, s) = ps.T.y; SF(F_TZ, s) = ps.T.z;
-            SI(F_DEPTH, s) = ps.depth;
-          } else {
-            died = true; // contributes 0 (metal absorbed, or throughput 0 / NaN in every channel)
-            if (isnan(ps.T.x) || isnan(ps.T.y) || isnan(ps.T.z)) n_nan++;
-          }
+      // queue of this slot: TPT_MAT_LAMBERTIAN=0, METAL=1, DIELECTRIC=2, done -> 3 (generate)
+      const int q = cls == TPT_EXT_DONE ? 3 : cls;
+      const unsigned m0 = __ballot_sync(FULL, q == 0), m1 = __ballot_sync(FULL, q == 1);
+      const unsigned m2 = __ballot_sync(FULL, q == 2), m3 = __ballot_sync(FULL, q == 3);
+      if (m0 | m1 | m2 | m3) {
+        unsigned long long add = (unsigned long long)__popc(m0) | ((unsigned long long)__popc(m1) << 16) |
+                                 ((unsigned long long)__popc(m2) << 32) | ((unsigned long long)__popc(m3) << 48);
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(&q_packed[par], add);
+        base = __shfl_sync(FULL, base, 0);
+        if (q >= 0) {
+          const unsigned mine = q == 0 ? m0 : q == 1 ? m1 : q == 2 ? m2 : m3;
+          const int at = (int)((base >> (16 * q)) & 0xffffu) + __popc(mine & lt_mask);
+          QUEUE(par, q)[at] = (unsigned short)s;
         }
-        push(died, 3, s);
       }
     }
     __syncthreads();
-    // ---------------------------------------------------------------- generate
+    // -------------------------------------------------------- shade + generate
     {
-      const int cg = q_count[3];
-      for (int wt = warp; wt < ((cg + 31) >> 5); wt += NWARP) {
-        const int idx = wt * 32 + (int)lane;
-        const bool mine = idx < cg;
-        const int s = mine ? queue[3 * NSLOT + idx] : 0;
-        int k = 0, k_end = -1, pixel = 0;
-        bool have_bin = false;
-        if (mine) {
-          k_end = SI(F_KEND, s);
-          have_bin = k_end >= 0;
-          k = SI(F_K, s) + (have_bin ? 1 : 0); // the sample that just ended
-          pixel = SI(F_PIXEL, s);
-          if (have_bin && k >= k_end) { // bin finished: one store per (pixel, sample range)
-            float *o = A.acc + (size_t)(unsigned)SI(F_ACCIDX, s) * 3;
-            o[0] = SF(F_AX, s);
-            o[1] = SF(F_AY, s);
-            o[2] = SF(F_AZ, s);
-            have_bin = false;
-          }
-        }
-        bool need = mine && !have_bin;
-        bool exhausted = false;
-        for (;;) { // grab bins until every lane that needs one has a valid pixel or the counter is dry
-          unsigned m = __ballot_sync(FULL, need);
-          if (!m) break;
-          int leader = __ffs(m) - 1;
-          unsigned long long base = 0;
-          if ((int)lane == leader) base = atomicAdd(A.counters + 0, (unsigned long long)__popc(m));
-          base = __shfl_sync(FULL, base, leader);
-          if (need) {
-            unsigned long long b = base + __popc(m & ((1u << lane) - 1u));
-            if (b >= A.n_bins) {
-              exhausted = true;
-              need = false;
+      const unsigned long long packed = q_packed[par];
+      const int c0 = (int)(packed & 0xffffu), c1 = (int)((packed >> 16) & 0xffffu);
+      const int c2 = (int)((packed >> 32) & 0xffffu), c3 = (int)((packed >> 48) & 0xffffu);
+      const int t0 = (c0 + 31) >> 5, t1 = (c1 + 31) >> 5, t2 = (c2 + 31) >> 5, t3 = (c3 + 31) >> 5;
+      // GENERATE chunks first (they are the most numerous and the most uniform), then the materials
+#if TPT_WAVE_SPLIT_GEN
+      for (int pass = 0; pass < 2; pass++) {
+      if (pass == 1) __syncthreads();
+      const int lo_t = pass == 0 ? t3 : 0, hi_t = pass == 0 ? t0 + t1 + t2 + t3 : t3;
+      for (int wt = lo_t + warp; wt < hi_t; wt += NWARP) {
+#else
+      for (int wt = warp; wt < t0 + t1 + t2 + t3; wt += NWARP) {
+#endif
+        int q, chunk, cnt;
+        if (wt < t3) { q = 3; chunk = wt; cnt = c3; }
+        else if (wt < t3 + t0) { q = 0; chunk = wt - t3; cnt = c0; }
+        else if (wt < t3 + t0 + t2) { q = 2; chunk = wt - t3 - t0; cnt = c2; }
+        else { q = 1; chunk = wt - t3 - t0 - t2; cnt = c1; }
+        const int idx = chunk * 32 + (int)lane;
+        const bool mine = idx < cnt;
+        const int s = mine ? QUEUE(par, q)[idx] : 0;
+        if (q != 3) {
+          // ------------------------------------------------------------- shade
+          bool died = false;
+          if (mine) {
+            PathState ps;
+            ps.ray.o = mk(SF(F_OX, s), SF(F_OY, s), SF(F_OZ, s));
+            ps.ray.d = mk(SF(F_DX, s), SF(F_DY, s), SF(F_DZ, s));
+            ps.ray.time = SF(F_TIME, s);
+            ps.T = mk(SF(F_TX, s), SF(F_TY, s), SF(F_TZ, s));
+            ps.depth = SI(F_DEPTH, s);
+            Rng rng;
+            rng.begin(A.seed_lo, A.seed_hi, (uint32_t)SI(F_PIXEL, s), (uint32_t)SI(F_K, s));
+            bool alive = shade<PAR>(S, ps, rng, SI(F_HPRIM, s), SF(F_HT, s));
+            if (alive) {
+              SF(F_OX, s) = ps.ray.o.x; SF(F_OY, s) = ps.ray.o.y; SF(F_OZ, s) = ps.ray.o.z;
+              SF(F_DX, s) = ps.ray.d.x; SF(F_DY, s) = ps.ray.d.y; SF(F_DZ, s) = ps.ray.d.z;
+              SF(F_TX, s) = ps.T.x; SF(F_TY, s) = ps.T.y; SF(F_TZ, s) = ps.T.z;
+              SI(F_DEPTH, s) = ps.depth;
             } else {
-              unsigned bb = (unsigned)b;
-              unsigned tile_local = bb / bins_per_tile;
-              unsigned rem = bb - tile_local * bins_per_tile;
-              unsigned range = rem / (unsigned)(TPT_TILE * TPT_TILE);
-              unsigned pit = rem - range * (unsigned)(TPT_TILE * TPT_TILE);
-              unsigned tile = (unsigned)A.part_index + tile_local * (unsigned)A.part_count;
-              unsigned ty = tile / (unsigned)A.tiles_x, tx = tile - ty * (unsigned)A.tiles_x;
-              int px = (int)(tx * TPT_TILE + (pit & (TPT_TILE - 1)));
-              int py = (int)(ty * TPT_TILE + (pit / TPT_TILE));
-              if (px < A.nx && py < A.ny) {
+              died = true; // contributes 0 (metal absorbed, or throughput 0 / NaN in every channel)
+              SI(F_ACTIVE, s) = 0;
+              if (isnan(ps.T.x) || isnan(ps.T.y) || isnan(ps.T.z)) n_nan++;
+            }
+          }
+          // dead paths regenerate in the NEXT iteration: push into the other parity's GENERATE queue
+          const unsigned md = __ballot_sync(FULL, died);
+          if (md) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(&q_packed[par ^ 1], (unsigned long long)__popc(md) << 48);
+            base = __shfl_sync(FULL, base, 0);
+            if (died) QUEUE(par ^ 1, 3)[(int)(base >> 48) + __popc(md & lt_mask)] = (unsigned short)s;
+          }
+        } else {
+          // ---------------------------------------------------------- generate
+          int k = 0, k_end = -1, pixel = 0;
+          bool have_bin = false;
+          if (mine) {
+            k_end = SI(F_KEND, s);
+            have_bin = k_end >= 0;
+            k = SI(F_K, s) + (have_bin ? 1 : 0); // the sample that just ended
+            pixel = SI(F_PIXEL, s);
+            if (have_bin && k >= k_end) { // bin finished: one store per (pixel, sample range)
+              float *o = A.acc + (size_t)(unsigned)SI(F_ACCIDX, s) * 3;
+              o[0] = SF(F_AX, s);
+              o[1] = SF(F_AY, s);
+              o[2] = SF(F_AZ, s);
+              have_bin = false;
+            }
+          }
+          bool need = mine && !have_bin;
+          bool exhausted = false;
+          for (;;) { // grab bins until every lane that needs one has a valid pixel or the counter is dry
+            unsigned m = __ballot_sync(FULL, need);
+            if (!m) break;
+            int leader = __ffs(m) - 1;
+            unsigned long long b0 = 0;
+            if ((int)lane == leader) b0 = atomicAdd(A.counters + 0, (unsigned long long)__popc(m));
+            b0 = __shfl_sync(FULL, b0, leader);
+            if (need) {
+              unsigned long long b = b0 + __popc(m & lt_mask);
+              if (b >= A.n_bins) {
+                exhausted = true;
                 need = false;
-                have_bin = true;
-                pixel = py * A.nx + px;
-                k = A.range_bounds[range];
-                k_end = A.range_bounds[range + 1];
-                SI(F_PIXEL, s) = pixel;
-                SI(F_KEND, s) = k_end;
-                SI(F_ACCIDX, s) = (int)(range * (unsigned)(A.nx * A.ny) + (unsigned)pixel);
-                SF(F_AX, s) = 0.f;
-                SF(F_AY, s) = 0.f;
-                SF(F_AZ, s) = 0.f;
+              } else {
+                unsigned bb = (unsigned)b;
+                unsigned tile_local = bb / bins_per_tile;
+                unsigned rem = bb - tile_local * bins_per_tile;
+                unsigned range = rem / (unsigned)(TPT_TILE * TPT_TILE);
+                unsigned pit = rem - range * (unsigned)(TPT_TILE * TPT_TILE);
+                unsigned tile = (unsigned)A.part_index + tile_local * (unsigned)A.part_count;
+                unsigned ty = tile / (unsigned)A.tiles_x, tx = tile - ty * (unsigned)A.tiles_x;
+                int px = (int)(tx * TPT_TILE + (pit & (TPT_TILE - 1)));
+                int py = (int)(ty * TPT_TILE + (pit / TPT_TILE));
+                if (px < A.nx && py < A.ny) {
+                  need = false;
+                  have_bin = true;
+                  pixel = py * A.nx + px;
+                  k = A.range_bounds[range];
+                  k_end = A.range_bounds[range + 1];
+                  SI(F_PIXEL, s) = pixel;
+                  SI(F_KEND, s) = k_end;
+                  SI(F_ACCIDX, s) = (int)(range * (unsigned)(A.nx * A.ny) + (unsigned)pixel);
+                  SF(F_AX, s) = 0.f;
+                  SF(F_AY, s) = 0.f;
+                  SF(F_AZ, s) = 0.f;
+                }
               }
             }
           }
-        }
-        if (mine) {
-          if (have_bin) {
-            Rng rng;
-            rng.begin(A.seed_lo, A.seed_hi, (uint32_t)pixel, (uint32_t)k);
-            const int py = pixel / A.nx, px = pixel - py * A.nx;
-            Ray r = camera_sample<PAR>(A.cam, px, py, A.nx, A.ny, rng);
-            SF(F_OX, s) = r.o.x; SF(F_OY, s) = r.o.y; SF(F_OZ, s) = r.o.z;
-            SF(F_DX, s) = r.d.x; SF(F_DY, s) = r.d.y; SF(F_DZ, s) = r.d.z;
-            SF(F_TIME, s) = r.time;
-            SF(F_TX, s) = 1.f; SF(F_TY, s) = 1.f; SF(F_TZ, s) = 1.f;
-            SI(F_DEPTH, s) = 0;
-            SI(F_K, s) = k;
-            SI(F_STATE, s) = TPT_SLOT_ACTIVE;
-            n_paths++;
-          } else if (exhausted) {
-            SI(F_STATE, s) = TPT_SLOT_IDLE;
-            SI(F_KEND, s) = -1;
-            atomicAdd(&n_idle, 1);
+          if (mine) {
+            if (have_bin) {
+              Rng rng;
+              rng.begin(A.seed_lo, A.seed_hi, (uint32_t)pixel, (uint32_t)k);
+              const int py = pixel / A.nx, px = pixel - py * A.nx;
+              Ray r = camera_sample<PAR>(A.cam, px, py, A.nx, A.ny, rng);
+              SF(F_OX, s) = r.o.x; SF(F_OY, s) = r.o.y; SF(F_OZ, s) = r.o.z;
+              SF(F_DX, s) = r.d.x; SF(F_DY, s) = r.d.y; SF(F_DZ, s) = r.d.z;
+              SF(F_TIME, s) = r.time;
+              SF(F_TX, s) = 1.f; SF(F_TY, s) = 1.f; SF(F_TZ, s) = 1.f;
+              SI(F_DEPTH, s) = 0;
+              SI(F_K, s) = k;
+              SI(F_ACTIVE, s) = 1;
+              n_paths++;
+            } else if (exhausted) {
+              SI(F_KEND, s) = -1;
+              atomicAdd(&n_idle, 1);
+            }
           }
         }
       }
+#if TPT_WAVE_SPLIT_GEN
+      }
+#endif
     }
     __syncthreads();
-    const bool done = n_idle >= NSLOT;
-    __syncthreads();
-    if (tid < TPT_WAVE_NQ) q_count[tid] = 0;
-    if (done) break;
-    __syncthreads();
+    if (n_idle >= NSLOT) break; // every slot idle: the work counter is dry and all paths ended
   }
 #undef SF
 #undef SI
+#undef QUEUE
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     n_rays += __shfl_xor_sync(FULL, n_rays, o);
@@ -489,7 +516,7 @@ static wave_fn wave_variant(bool small) {
   return small ? render_wave_kernel<TPT_PAR, true> : render_wave_kernel<TPT_PAR, false>;
 }
 static size_t wave_smem_bytes(const RenderArgs &A) {
-  return (size_t)A.scene.blob_words * 16 + (size_t)TPT_WAVE_SLOTS * (21 * 4 + TPT_WAVE_NQ * 2);
+  return (size_t)A.scene.blob_words * 16 + (size_t)TPT_WAVE_SLOTS * (21 * 4 + 2 * TPT_WAVE_NQ * 2);
 }
 
 cudaError_t TPT_FN(wave_occupancy_)(const RenderArgs &A, bool small, int *blocks_per_sm) {

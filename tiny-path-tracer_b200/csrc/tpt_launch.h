@@ -4,8 +4,15 @@
 #include "tpt_device.cuh"
 
 #define TPT_MEGA_THREADS 256
+#ifndef TPT_WAVE_SPLIT_GEN
+#define TPT_WAVE_SPLIT_GEN 1 // 1: generate runs as its own phase after shade (one more barrier, +8 % measured)
+#endif
+#ifndef TPT_WAVE_THREADS
 #define TPT_WAVE_THREADS 256
-#define TPT_WAVE_SLOTS 256
+#endif
+#ifndef TPT_WAVE_SLOTS
+#define TPT_WAVE_SLOTS 512 // path slots per CTA (two per thread)
+#endif
 
 namespace tptd {
 
