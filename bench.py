@@ -169,12 +169,12 @@ def run_ours(args, rank, local_rank, world):
     import tpt_b200 as T
 
     dist = None
-    gloo = None
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: ONE JSON line
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        gloo = dist.new_group(backend="gloo")  # host-side gather of the image tiles
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
 
@@ -245,23 +245,38 @@ def run_ours(args, rank, local_rank, world):
     img.rgb8 = C.cast(rgb_host.data_ptr(), C.POINTER(C.c_uint8))
     e2e_s = []
     h2d = d2h = 0
+    class _DevBuf:  # zero-copy view of a library-owned device buffer for torch (NCCL gather)
+        def __init__(self, ptr, nbytes, typestr):
+            itemsize = int(typestr[-1])
+            self.__cuda_array_interface__ = {"shape": (nbytes // itemsize,), "typestr": typestr, "data": (ptr, False),
+                                             "version": 2}
+
     for i in range(1 + args.steps):  # first iteration untimed (allocations)
         barrier()
         t0 = time.perf_counter()
         s = T.Scene(hs, device=local_rank)  # flattened scene -> HBM
-        T._check(T.lib().tpt_render(s._s, C.byref(cam), C.byref(params), C.byref(img)))
+        if dist is None:
+            T._check(T.lib().tpt_render(s._s, C.byref(cam), C.byref(params), C.byref(img)))
+        else:
+            # every rank renders its tiles; the disjoint per-GPU products are combined over NVLink
+            # (tiles a rank does not own are zero, so SUM is an exact gather), then ONE download on rank 0
+            T._check(T.lib().tpt_render_device(s._s, C.byref(cam), C.byref(params)))
+            sp, sb, rp, rb = s.device_buffers()
+            d_sum = torch.as_tensor(_DevBuf(sp, sb, "<f4"), device=dev)
+            d_rgb = torch.as_tensor(_DevBuf(rp, rb, "|u1"), device=dev)
+            dist.reduce(d_sum, dst=0, op=dist.ReduceOp.SUM)
+            dist.reduce(d_rgb, dst=0, op=dist.ReduceOp.SUM)
+            torch.cuda.synchronize()
+            if rank == 0:
+                T._check(T.lib().tpt_render_fetch(s._s, C.byref(img)))
         st2 = s.stats()
-        if dist is not None:  # host gather: tiles are disjoint, the other ranks hold zeros there
-            dist.reduce(sum_host, dst=0, op=dist.ReduceOp.SUM, group=gloo)
-            rgb32 = rgb_host.to(torch.int32)
-            dist.reduce(rgb32, dst=0, op=dist.ReduceOp.SUM, group=gloo)
         loss = float(sum_host[0, NY // 2, NX // 2, 1])  # the step's result is read on the host
         s.close()
         barrier()
         if i > 0:
             e2e_s.append(time.perf_counter() - t0)
         h2d = int(st2["h2d_bytes"])  # flattened scene blob + camera/params launch arguments
-        d2h = int(st2["d2h_bytes"])
+        d2h = int(st2["d2h_bytes"]) if rank == 0 else 0
     e2e_step = max_over_ranks(statistics.mean(e2e_s))
     e2e_value = (total_paths / args.steps) / e2e_step / 1e6
 

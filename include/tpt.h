@@ -255,6 +255,20 @@ int tpt_render(tpt_scene *scene, const tpt_camera *cam, const tpt_render_params 
 int tpt_render_device(tpt_scene *scene, const tpt_camera *cam, const tpt_render_params *params);
 int tpt_render_fetch(tpt_scene *scene, tpt_image *out);
 
+/* In-process multi-GPU: `scenes[g]` is the same scene created on GPU g (tpt_scene_create with
+ * device = g). The frame is cut into 8 x n batches of interleaved 16x16 tiles; every GPU renders a
+ * static share and then steals the remaining batches from a shared counter (one host thread per
+ * GPU inside the call); GPU 0 gathers the disjoint partial frames over NVLink and the image is
+ * downloaded once. The result is bit-identical to a single-GPU tpt_render (Philox is keyed on
+ * pixel and sample). params->part_index/part_count must be 0/1. Statistics are read from
+ * scenes[0]. */
+int tpt_render_multi(tpt_scene *const *scenes, int n_scenes, const tpt_camera *cam, const tpt_render_params *params,
+                     tpt_image *out);
+
+/* device addresses of the last render's products (valid until the next render / destroy): lets a
+ * multi-GPU caller combine the disjoint per-GPU tiles over NVLink before one download */
+int tpt_device_buffers(const tpt_scene *scene, void **sum_rgb, size_t *sum_bytes, void **rgb8, size_t *rgb8_bytes);
+
 int tpt_get_stats(const tpt_scene *scene, tpt_stats *out);
 
 /* known-answer probes used by the unit tests (each is one tiny kernel launch) */

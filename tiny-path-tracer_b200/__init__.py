@@ -40,6 +40,7 @@ STATUS = {0: "TPT_OK", -1: "TPT_ERR_INVALID", -2: "TPT_ERR_CUDA", -3: "TPT_ERR_N
 C_ABI_SYMBOLS = [
     "tpt_api_version", "tpt_device_count", "tpt_last_error", "tpt_scene_create", "tpt_scene_destroy",
     "tpt_intersect_batch", "tpt_render", "tpt_render_device", "tpt_render_fetch", "tpt_get_stats",
+    "tpt_device_buffers", "tpt_render_multi",
     "tpt_debug_philox", "tpt_debug_texture",
 ]
 
@@ -167,6 +168,10 @@ def lib() -> C.CDLL:
         L.tpt_render_device.argtypes = [C.c_void_p, C.POINTER(Camera), C.POINTER(RenderParams)]
         L.tpt_render_fetch.argtypes = [C.c_void_p, C.POINTER(Image)]
         L.tpt_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
+        L.tpt_render_multi.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.POINTER(Camera), C.POINTER(RenderParams),
+                                       C.POINTER(Image)]
+        L.tpt_device_buffers.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t),
+                                         C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
         L.tpt_debug_philox.argtypes = [C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
         L.tpt_debug_texture.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]
         _lib = L
@@ -316,6 +321,13 @@ class Scene:
         _check(lib().tpt_get_stats(self._s, C.byref(st)))
         return {k: getattr(st, k) for k, _ in Stats._fields_ if k != "reserved"}
 
+    def device_buffers(self):
+        """(sum_ptr, sum_bytes, rgb8_ptr, rgb8_bytes): device addresses of the last render's products."""
+        sp, rp = C.c_void_p(), C.c_void_p()
+        sb, rb = C.c_size_t(), C.c_size_t()
+        _check(lib().tpt_device_buffers(self._s, C.byref(sp), C.byref(sb), C.byref(rp), C.byref(rb)))
+        return sp.value, sb.value, rp.value, rb.value
+
     def render_device(self, cam: Camera, params: RenderParams) -> dict:
         _check(lib().tpt_render_device(self._s, C.byref(cam), C.byref(params)))
         return self.stats()
@@ -351,6 +363,15 @@ class Scene:
         out = np.zeros((uvp.shape[0], 3), np.float32)
         _check(lib().tpt_debug_texture(self._s, texture, uvp.ctypes.data, uvp.shape[0], mode, out.ctypes.data))
         return out
+
+
+def render_multi(scenes, cam: Camera, params: RenderParams, want_sum=True, want_rgb8=True,
+                 want_slices=False) -> RenderResult:
+    """tpt_render_multi: one Scene per GPU, static tile split + work stealing + NVLink gather."""
+    img, s, r, rs = scenes[0]._buffers(params, want_sum, want_rgb8, want_slices)
+    arr = (C.c_void_p * len(scenes))(*[sc._s for sc in scenes])
+    _check(lib().tpt_render_multi(arr, len(scenes), C.byref(cam), C.byref(params), C.byref(img)))
+    return RenderResult(s, r, rs, scenes[0].stats())
 
 
 def philox(ctr, key, device: int = 0):

@@ -8,9 +8,12 @@
 #include <algorithm>
 #include <chrono>
 #include <climits>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <atomic>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace tptd;
@@ -33,10 +36,14 @@ int cuda_fail(cudaError_t e, const char *what) {
     if (e_ != cudaSuccess) return cuda_fail(e_, #call);                                            \
   } while (0)
 
+#define TPT_MAX_BATCHES 256 // work-stealing batches of one multi-GPU render
+
 struct ResolveArgs {
   const float *acc; // [n_ranges][npix][3]
   int n_ranges, npix, ns, slices, per_slice;
   int slice_last_range[TPT_MAX_RANGES];
+  int nx, tiles_x, part_count;
+  unsigned owned[TPT_MAX_BATCHES / 32]; // bit b: this device rendered the tiles t with t % part_count == b
   float *sum_rgb;       // [slices][npix][3] or null
   uint8_t *rgb8;        // [npix][3] or null
   uint8_t *rgb8_slices; // [slices][npix][3] or null
@@ -56,9 +63,14 @@ __device__ __forceinline__ uint8_t quantise(float sum, float denom) {
 __global__ void resolve_kernel(const __grid_constant__ ResolveArgs R) {
   int pix = blockIdx.x * blockDim.x + threadIdx.x;
   if (pix >= R.npix) return;
+  // pixels of tiles another part renders: the accumulators were never written (and are never
+  // read); their outputs are zero so that parts can be gathered by addition
+  const int py = pix / R.nx, px = pix - py * R.nx;
+  const int batch = ((py / TPT_TILE) * R.tiles_x + (px / TPT_TILE)) % R.part_count;
+  const bool mine = (R.owned[batch >> 5] >> (batch & 31)) & 1u;
   float rx = 0.f, ry = 0.f, rz = 0.f;
   int slice = 0;
-  for (int r = 0; r < R.n_ranges; r++) {
+  for (int r = 0; r < (mine ? R.n_ranges : 0); r++) {
     const float *a = R.acc + ((size_t)r * R.npix + pix) * 3;
     rx += a[0];
     ry += a[1];
@@ -77,6 +89,13 @@ __global__ void resolve_kernel(const __grid_constant__ ResolveArgs R) {
         R.rgb8_slices[o + 2] = quantise(rz, den);
       }
       slice++;
+    }
+  }
+  if (!mine) {
+    for (int sl = 0; sl < R.slices; sl++) {
+      size_t o = ((size_t)sl * R.npix + pix) * 3;
+      if (R.sum_rgb) R.sum_rgb[o] = R.sum_rgb[o + 1] = R.sum_rgb[o + 2] = 0.f;
+      if (R.rgb8_slices) R.rgb8_slices[o] = R.rgb8_slices[o + 1] = R.rgb8_slices[o + 2] = 0;
     }
   }
   if (R.rgb8) {
@@ -339,6 +358,7 @@ int make_plan(tpt_scene *s, const tpt_camera *cam, const tpt_render_params *p, P
     return fail(TPT_ERR_UNSUPPORTED, "wavefront variant needs a shared-memory resident scene (<= 64 KB)");
   plan.wavefront = p->kernel == TPT_KERNEL_WAVEFRONT;
   if (p->part_count <= 0 || p->part_index < 0 || p->part_index >= p->part_count) return fail(TPT_ERR_INVALID, "bad part_index/part_count");
+  if (p->part_count > TPT_MAX_BATCHES) return fail(TPT_ERR_UNSUPPORTED, "part_count above TPT_MAX_BATCHES");
   if (!s->has_lights) return fail(TPT_ERR_INVALID, "light-sampling list is empty (color() needs light_shape, main.cpp:99-106)");
   plan.parity = p->mode == TPT_MODE_PARITY;
   RenderArgs &A = plan.args;
@@ -365,9 +385,24 @@ int make_plan(tpt_scene *s, const tpt_camera *cam, const tpt_render_params *p, P
   A.seed_hi = p->seed_hi;
   // sample ranges: each slice is cut into `subs` sub-ranges (finer bins => shorter kernel tail);
   // samples beyond slices*per_slice (ns not divisible) form one tail range.
+  // Automatic choice (fast mode): enough bins that every resident path slot works through >= 32 of
+  // them -- a slot runs a bin's samples sequentially, so the launch's tail is about one bin long.
+  // Matters when a launch covers a fraction of the frame (1/N of the tiles per GPU, 1/(8N) per
+  // stolen batch): at 8 GPUs a 256-sample bin would be a fifth of the whole launch.
   int subs = p->reserved[1];
-  if (subs <= 0) subs = plan.parity ? 1 : std::max(1, std::min(8, per_slice / 256));
   int tail = p->ns - slices * per_slice;
+  if (subs <= 0) {
+    subs = 1;
+    if (!plan.parity) {
+      const double slots = (double)s->prop.multiProcessorCount * 1536.0;
+      const double local_pixels = (double)p->nx * p->ny / p->part_count;
+      long long want = (long long)std::ceil(32.0 * slots / std::max(local_pixels, 1.0) / slices);
+      long long by_samples = std::max(1, per_slice / 8);                       // >= 8 samples per bin
+      long long by_table = std::max(1, (TPT_MAX_RANGES - (tail ? 1 : 0)) / slices);
+      long long by_memory = std::max<long long>(1, (long long)((2.0 * (1 << 30)) / (12.0 * p->nx * p->ny * slices)));
+      subs = (int)std::max<long long>(1, std::min(std::min(want, by_samples), std::min(by_table, by_memory)));
+    }
+  }
   while (subs > 1 && slices * subs + (tail ? 1 : 0) > TPT_MAX_RANGES) subs--;
   if (slices * subs + (tail ? 1 : 0) > TPT_MAX_RANGES) return fail(TPT_ERR_UNSUPPORTED, "too many slices");
   if (subs > per_slice) subs = per_slice;
@@ -398,6 +433,10 @@ int make_plan(tpt_scene *s, const tpt_camera *cam, const tpt_render_params *p, P
   if (A.n_bins >= (1ULL << 32)) return fail(TPT_ERR_UNSUPPORTED, "too many bins for one launch");
   plan.npix = (size_t)p->nx * p->ny;
   R.n_ranges = A.n_ranges;
+  R.nx = p->nx;
+  R.tiles_x = A.tiles_x;
+  R.part_count = p->part_count;
+  R.owned[p->part_index >> 5] |= 1u << (p->part_index & 31);
   R.npix = (int)plan.npix;
   R.ns = p->ns;
   R.slices = slices;
@@ -438,7 +477,6 @@ int run_plan(tpt_scene *s, Plan &plan, bool want_sum, bool want_rgb8, bool want_
   plan.blocks = bps * s->prop.multiProcessorCount;
 
   CK(cudaMemsetAsync(s->d_counters, 0, 8 * sizeof(unsigned long long), s->stream));
-  CK(cudaMemsetAsync(s->d_acc, 0, acc_want, s->stream));
   CK(cudaEventRecord(s->ev[0], s->stream));
   if (plan.wavefront)
     CK(plan.parity ? launch_wave_parity(A, small, plan.blocks, s->stream) : launch_wave_fast(A, small, plan.blocks, s->stream));
@@ -498,6 +536,233 @@ int fetch(tpt_scene *s, tpt_image *out) {
   s->stats.d2h_ms = now_ms() - t0;
   s->stats.d2h_bytes = bytes;
   return TPT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// In-process multi-GPU render: static split + work stealing + gather.
+// The frame is cut into NB = 8 x n_gpus batches; batch b = the tiles t with t % NB == b (every
+// batch is a uniform sample of the frame, so batches cost about the same). One host thread per
+// GPU first renders its static share (3/4 of the batches, b % n_gpus == g) and then steals the
+// remaining batches from a shared atomic counter, so a slower or busier GPU simply takes fewer.
+// Every batch is one launch of the persistent kernel into that GPU's own accumulators (bins are
+// disjoint); each GPU then resolves its partial frame, GPU 0 pulls the others over NVLink
+// (cudaMemcpyPeerAsync) and adds them -- tiles a GPU did not render are zero, so the sum is an
+// exact gather -- and one download serves the caller. No NCCL: nothing else is exchanged.
+// ---------------------------------------------------------------------------------------------
+__global__ void add_f32_kernel(float *dst, const float *src, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] += src[i];
+}
+__global__ void add_u8_kernel(uint8_t *dst, const uint8_t *src, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = (uint8_t)(dst[i] + src[i]);
+}
+
+struct MultiWorker {
+  tpt_scene *s = nullptr;
+  int rc = TPT_OK;
+  std::string err;
+  int batches = 0;
+  double busy_ms = 0;
+  unsigned owned[TPT_MAX_BATCHES / 32] = {};
+};
+
+int prepare_buffers(tpt_scene *s, Plan &plan, bool want_slices) {
+  CK(cudaSetDevice(s->device));
+  RenderArgs &A = plan.args;
+  ResolveArgs &R = plan.res;
+  int rc;
+  size_t acc_want = (size_t)A.n_ranges * plan.npix * 3 * sizeof(float);
+  if ((rc = ensure((void **)&s->d_acc, s->acc_bytes, acc_want)) != TPT_OK) return rc;
+  if ((rc = ensure((void **)&s->d_sum, s->sum_bytes, (size_t)R.slices * plan.npix * 3 * sizeof(float))) != TPT_OK) return rc;
+  if ((rc = ensure((void **)&s->d_rgb8, s->rgb8_bytes, plan.npix * 3)) != TPT_OK) return rc;
+  if ((rc = ensure((void **)&s->d_rgb8_slices, s->rgb8_slices_bytes, (size_t)R.slices * plan.npix * 3)) != TPT_OK) return rc;
+  R.acc = s->d_acc;
+  R.sum_rgb = s->d_sum;
+  R.rgb8 = s->d_rgb8;
+  R.rgb8_slices = want_slices ? s->d_rgb8_slices : nullptr;
+  CK(cudaMemsetAsync(s->d_counters, 0, TPT_MAX_BATCHES * 8 * sizeof(unsigned long long), s->stream));
+  return TPT_OK;
+}
+
+int launch_batch(tpt_scene *s, const tpt_camera *cam, const tpt_render_params *p, int batch, int n_batches) {
+  tpt_render_params bp = *p;
+  bp.part_index = batch;
+  bp.part_count = n_batches;
+  Plan plan;
+  int rc = make_plan(s, cam, &bp, plan);
+  if (rc != TPT_OK) return rc;
+  RenderArgs &A = plan.args;
+  A.acc = s->d_acc;
+  A.counters = s->d_counters + (size_t)batch * 8;
+  size_t smem = s->use_smem ? s->blob_bytes : 0;
+  int bps = 0;
+  const bool small = s->small.enabled != 0;
+  if (plan.wavefront)
+    CK(plan.parity ? wave_occupancy_parity(A, small, &bps) : wave_occupancy_fast(A, small, &bps));
+  else
+    CK(plan.parity ? mega_occupancy_parity(s->use_smem, small, smem, &bps)
+                   : mega_occupancy_fast(s->use_smem, small, smem, &bps));
+  if (bps < 1) return fail(TPT_ERR_CUDA, "render kernel does not fit on an SM");
+  int blocks = bps * s->prop.multiProcessorCount;
+  if (plan.wavefront)
+    CK(plan.parity ? launch_wave_parity(A, small, blocks, s->stream) : launch_wave_fast(A, small, blocks, s->stream));
+  else
+    CK(plan.parity ? launch_mega_parity(A, s->use_smem, small, blocks, s->stream)
+                   : launch_mega_fast(A, s->use_smem, small, blocks, s->stream));
+  s->stats.blocks = blocks;
+  return TPT_OK;
+}
+
+int render_multi(tpt_scene *const *scenes, int n, const tpt_camera *cam, const tpt_render_params *p, tpt_image *out) {
+  if (!scenes || n < 1 || !cam || !p) return fail(TPT_ERR_INVALID, "null argument");
+  for (int i = 0; i < n; i++) {
+    if (!scenes[i]) return fail(TPT_ERR_INVALID, "null scene");
+    for (int j = 0; j < i; j++)
+      if (scenes[j]->device == scenes[i]->device) return fail(TPT_ERR_INVALID, "two scenes on the same device");
+  }
+  if (p->part_count != 1 || p->part_index != 0) return fail(TPT_ERR_INVALID, "tpt_render_multi partitions the frame itself");
+  const double t_begin = now_ms();
+  const int n_batches = std::min(TPT_MAX_BATCHES, 8 * n);
+  const int n_static = (n_batches * 3 / 4) / n * n; // multiple of n: every GPU gets the same static share
+  Plan plan0;
+  int rc = make_plan(scenes[0], cam, p, plan0);
+  if (rc != TPT_OK) return rc;
+  const bool want_slices = out && out->rgb8_slices;
+  std::atomic<int> next(n_static);
+  std::vector<MultiWorker> W(n);
+  std::vector<std::thread> threads;
+  for (int g = 0; g < n; g++) {
+    W[g].s = scenes[g];
+    threads.emplace_back([&, g]() {
+      MultiWorker &w = W[g];
+      tpt_scene *s = w.s;
+      Plan plan; // sized like a batch launch (same sample ranges as launch_batch will use)
+      tpt_render_params pp = *p;
+      pp.part_index = 0;
+      pp.part_count = n_batches;
+      if ((w.rc = make_plan(s, cam, &pp, plan)) != TPT_OK || (w.rc = prepare_buffers(s, plan, want_slices)) != TPT_OK) {
+        w.err = g_error;
+        return;
+      }
+      cudaEventRecord(s->ev[0], s->stream);
+      for (int b = g; b < n_static && w.rc == TPT_OK; b += n) { // static share
+        w.rc = launch_batch(s, cam, p, b, n_batches);
+        w.batches++;
+        w.owned[b >> 5] |= 1u << (b & 31);
+      }
+      // steal: when this GPU has drained its static share it takes the next free batch, one at a time
+      while (w.rc == TPT_OK) {
+        if (cudaStreamSynchronize(s->stream) != cudaSuccess) {
+          w.rc = TPT_ERR_CUDA;
+          g_error = "stream synchronize failed while stealing";
+          break;
+        }
+        int b = next.fetch_add(1);
+        if (b >= n_batches) break;
+        w.rc = launch_batch(s, cam, p, b, n_batches);
+        w.batches++;
+        w.owned[b >> 5] |= 1u << (b & 31);
+      }
+      if (w.rc != TPT_OK) {
+        w.err = g_error;
+        return;
+      }
+      cudaEventRecord(s->ev[1], s->stream);
+      ResolveArgs R = plan.res;
+      R.part_count = n_batches;
+      std::memcpy(R.owned, w.owned, sizeof(R.owned));
+      int rb = (int)((plan.npix + 255) / 256);
+      resolve_kernel<<<rb, 256, 0, s->stream>>>(R);
+      cudaEventRecord(s->ev[2], s->stream);
+      cudaError_t e = cudaStreamSynchronize(s->stream);
+      if (e != cudaSuccess) {
+        w.rc = TPT_ERR_CUDA;
+        w.err = cudaGetErrorString(e);
+        return;
+      }
+      float ms = 0;
+      cudaEventElapsedTime(&ms, s->ev[0], s->ev[1]);
+      w.busy_ms = ms;
+      s->last_nx = p->nx;
+      s->last_ny = p->ny;
+      s->last_slices = plan.res.slices;
+    });
+  }
+  for (auto &t : threads) t.join();
+  for (int g = 0; g < n; g++)
+    if (W[g].rc != TPT_OK) return fail(W[g].rc, "GPU " + std::to_string(scenes[g]->device) + ": " + W[g].err);
+  // ---- gather on GPU 0 over NVLink ----
+  tpt_scene *s0 = scenes[0];
+  CK(cudaSetDevice(s0->device));
+  const size_t npix = plan0.npix;
+  const size_t sum_n = (size_t)plan0.res.slices * npix * 3, rgb_n = npix * 3;
+  double t_gather = now_ms();
+  if (n > 1) {
+    float *tmp_f = nullptr; // only when a peer is not directly addressable
+    uint8_t *tmp_b = nullptr;
+    for (int g = 1; g < n; g++) {
+      int can = 0;
+      cudaDeviceCanAccessPeer(&can, s0->device, scenes[g]->device);
+      if (can) {
+        cudaError_t e = cudaDeviceEnablePeerAccess(scenes[g]->device, 0);
+        if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+        else if (e != cudaSuccess) can = 0;
+      }
+      const float *src_f = scenes[g]->d_sum;
+      const uint8_t *src_b = scenes[g]->d_rgb8, *src_s = scenes[g]->d_rgb8_slices;
+      if (can) {
+        // GPU 0 reads the peer's buffers in place over NVLink: the add IS the transfer
+        add_f32_kernel<<<(unsigned)((sum_n + 255) / 256), 256, 0, s0->stream>>>(s0->d_sum, src_f, sum_n);
+        add_u8_kernel<<<(unsigned)((rgb_n + 255) / 256), 256, 0, s0->stream>>>(s0->d_rgb8, src_b, rgb_n);
+        if (want_slices)
+          add_u8_kernel<<<(unsigned)((sum_n + 255) / 256), 256, 0, s0->stream>>>(s0->d_rgb8_slices, src_s, sum_n);
+      } else {
+        if (!tmp_f) {
+          CK(cudaMalloc((void **)&tmp_f, sum_n * sizeof(float)));
+          CK(cudaMalloc((void **)&tmp_b, std::max(rgb_n, sum_n)));
+        }
+        CK(cudaMemcpyPeerAsync(tmp_f, s0->device, src_f, scenes[g]->device, sum_n * sizeof(float), s0->stream));
+        add_f32_kernel<<<(unsigned)((sum_n + 255) / 256), 256, 0, s0->stream>>>(s0->d_sum, tmp_f, sum_n);
+        CK(cudaMemcpyPeerAsync(tmp_b, s0->device, src_b, scenes[g]->device, rgb_n, s0->stream));
+        add_u8_kernel<<<(unsigned)((rgb_n + 255) / 256), 256, 0, s0->stream>>>(s0->d_rgb8, tmp_b, rgb_n);
+        if (want_slices) {
+          CK(cudaMemcpyPeerAsync(tmp_b, s0->device, src_s, scenes[g]->device, sum_n, s0->stream));
+          add_u8_kernel<<<(unsigned)((sum_n + 255) / 256), 256, 0, s0->stream>>>(s0->d_rgb8_slices, tmp_b, sum_n);
+        }
+      }
+    }
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(s0->stream));
+    if (tmp_f) cudaFree(tmp_f);
+    if (tmp_b) cudaFree(tmp_b);
+  }
+  t_gather = now_ms() - t_gather;
+  // ---- statistics: sums over GPUs and batches, time = slowest GPU ----
+  tpt_stats st;
+  std::memset(&st, 0, sizeof(st));
+  for (int g = 0; g < n; g++) {
+    CK(cudaSetDevice(scenes[g]->device));
+    std::vector<unsigned long long> c((size_t)n_batches * 8);
+    CK(cudaMemcpy(c.data(), scenes[g]->d_counters, c.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    for (int b = 0; b < n_batches; b++) {
+      st.paths += c[(size_t)b * 8 + 3];
+      st.rays += c[(size_t)b * 8 + 1];
+      st.nan_samples += c[(size_t)b * 8 + 2];
+    }
+    st.render_ms = std::max(st.render_ms, W[g].busy_ms);
+    st.kernel_launches += W[g].batches + 1;
+    st.reserved[g < 4 ? g : 3] = W[g].batches; // batches taken by the first GPUs (load-balance evidence)
+  }
+  st.resolve_ms = t_gather;
+  st.sm_count = s0->prop.multiProcessorCount;
+  st.blocks = s0->stats.blocks;
+  st.threads_per_block = plan0.wavefront ? TPT_WAVE_THREADS : TPT_MEGA_THREADS;
+  st.h2d_bytes = (s0->blob_bytes + sizeof(RenderArgs) + sizeof(ResolveArgs)) * n;
+  s0->stats = st;
+  rc = fetch(s0, out);
+  s0->stats.wall_ms = now_ms() - t_begin;
+  return rc;
 }
 
 } // namespace
@@ -616,7 +881,7 @@ int tpt_scene_create(const tpt_scene_desc *d, int device, tpt_scene **out) {
     L.image_w[i] = im.width;
     L.image_h[i] = im.height;
   }
-  CK(cudaMalloc((void **)&s->d_counters, 8 * sizeof(unsigned long long)));
+  CK(cudaMalloc((void **)&s->d_counters, TPT_MAX_BATCHES * 8 * sizeof(unsigned long long)));
   s->stats.h2d_bytes = blob.size();
   *out = s;
   return TPT_OK;
@@ -695,6 +960,22 @@ int tpt_render(tpt_scene *s, const tpt_camera *cam, const tpt_render_params *p, 
   rc = fetch(s, out);
   s->stats.wall_ms = now_ms() - t0;
   return rc;
+}
+
+int tpt_render_multi(tpt_scene *const *scenes, int n_scenes, const tpt_camera *cam, const tpt_render_params *params,
+                     tpt_image *out) {
+  return render_multi(scenes, n_scenes, cam, params, out);
+}
+
+int tpt_device_buffers(const tpt_scene *s, void **sum_rgb, size_t *sum_bytes, void **rgb8, size_t *rgb8_bytes) {
+  if (!s) return fail(TPT_ERR_INVALID, "null scene");
+  size_t npix = (size_t)s->last_nx * s->last_ny;
+  if (npix == 0) return fail(TPT_ERR_INVALID, "nothing rendered yet");
+  if (sum_rgb) *sum_rgb = s->d_sum;
+  if (sum_bytes) *sum_bytes = (size_t)s->last_slices * npix * 3 * sizeof(float);
+  if (rgb8) *rgb8 = s->d_rgb8;
+  if (rgb8_bytes) *rgb8_bytes = npix * 3;
+  return TPT_OK;
 }
 
 int tpt_get_stats(const tpt_scene *s, tpt_stats *out) {

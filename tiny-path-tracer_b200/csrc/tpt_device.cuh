@@ -23,7 +23,7 @@ namespace tptd {
 #define TPT_DEV __device__ __forceinline__
 #define TPT_MAX_FRAMES 32
 #define TPT_MAX_IMAGES 8
-#define TPT_MAX_RANGES 64
+#define TPT_MAX_RANGES 256
 
 // ------------------------------------------------------------------------------------------
 // Scene view: one contiguous blob of 16-byte words (shared memory when it fits, else global),
