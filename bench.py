@@ -54,19 +54,23 @@ def parse():
 
 # ------------------------------------------------------------------------------------ clocks
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """nvidia-smi clocks + throttle reasons (B200_PROFILING.md). Started before the warm-up (the
+    tool needs ~0.5 s to come up, longer than an 8-GPU timed region); rows are time-stamped and
+    only those inside the timed window are used, falling back to warm-up + timed when the window
+    holds fewer than three samples (said in the result)."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index = index
         self.rows = []
         self.proc = None
+        self.t_begin = self.t_end = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -75,31 +79,46 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def mark_begin(self):
+        self.t_begin = time.time()
+
+    def mark_end(self):
+        self.t_end = time.time()
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, pw, reasons = [], [], [], set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[0]))
-                mx.append(float(r[1]))
-                pw.append(float(r[2]))
-            except (ValueError, IndexError):
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        # "under load": samples at or above the median power draw
-        load = [s for s, p in zip(sm, pw) if p >= statistics.median(pw)] if pw else sm
+
+        def parse(rows):
+            sm, mx, pw, reasons = [], [], [], set()
+            for _, r in rows:
+                try:
+                    sm.append(float(r[1]))
+                    mx.append(float(r[2]))
+                    pw.append(float(r[3]))
+                except (ValueError, IndexError):
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            return sm, mx, pw, reasons
+
+        inside = [x for x in self.rows if self.t_begin is not None and self.t_begin <= x[0] <= (self.t_end or 1e30)]
+        window = "timed"
+        if len(inside) < 3:
+            inside, window = self.rows, "warmup+timed"
+        sm, mx, pw, reasons = parse(inside)
+        load = [s for s, p in zip(sm, pw) if p >= statistics.median(pw)] if pw else sm  # samples under load
         return {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "window": window, "reasons": sorted(reasons)}
 
 
 # ---------------------------------------------------------------------------- CPU reference
@@ -207,12 +226,13 @@ def run_ours(args, rank, local_rank, world):
                            device=local_rank, kernel=kernel)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(max(args.warmup, 0)):
         scene.render_device(cam, params)
 
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
+    sampler.mark_begin()
     t0 = time.perf_counter()
     dev_ms, render_ms, paths, rays, launches = 0.0, 0.0, 0, 0, 0
     for _ in range(args.steps):
@@ -226,6 +246,7 @@ def run_ours(args, rank, local_rank, world):
         launches += st["kernel_launches"]
     barrier()
     wall_ms = 1e3 * (time.perf_counter() - t0)
+    sampler.mark_end()
     clocks = sampler.stop()
 
     dev_ms_max = max_over_ranks(dev_ms)

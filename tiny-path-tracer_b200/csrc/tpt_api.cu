@@ -290,6 +290,31 @@ void build_small_scene(const tpt_scene_desc *d, bool smem_ok, SmallScene &Q) {
     G.first_op = d->chains[c].first_op;
     G.n_ops = d->chains[c].n_ops;
     G.begin = n;
+    {
+      // compose the wrappers (outermost first): translate: o -= t ; rotate_y: (x,z) -> (c x - s z, s x + c z)
+      double cs = 1.0, sn = 0.0, bx = 0.0, by = 0.0, bz = 0.0;
+      for (int k = 0; k < G.n_ops; k++) {
+        const tpt_xform_op &op = d->xform_ops[G.first_op + k];
+        if (op.kind == TPT_XF_TRANSLATE) {
+          bx -= op.a;
+          by -= op.b;
+          bz -= op.c;
+        } else {
+          double s2 = op.a, c2 = op.b;
+          double ncs = c2 * cs - s2 * sn, nsn = s2 * cs + c2 * sn;
+          double nbx = c2 * bx - s2 * bz, nbz = s2 * bx + c2 * bz;
+          cs = ncs;
+          sn = nsn;
+          bx = nbx;
+          bz = nbz;
+        }
+      }
+      G.cs = (float)cs;
+      G.sn = (float)sn;
+      G.bx = (float)bx;
+      G.by = (float)by;
+      G.bz = (float)bz;
+    }
     int ends[4];
     for (int o = 0; o < 4; o++) {
       for (int i = 0; i < d->n_prims; i++) {
@@ -300,7 +325,7 @@ void build_small_scene(const tpt_scene_desc *d, bool smem_ok, SmallScene &Q) {
         std::memcpy(&idf, &id, 4);
         if (p.kind == TPT_PRIM_SPHERE) {
           Q.geo[n] = make_float4(p.p[0], p.p[1], p.p[2], p.p[3]);
-          Q.aux[n] = make_float2(p.p[3] * p.p[3], idf);
+          Q.aux[n] = make_float2(p.p[3] >= 500.0f ? 1.0f : 0.0f, idf); // huge "wall" spheres: exact roots
         } else {
           Q.geo[n] = make_float4(p.p[0], p.p[1], p.p[2], p.p[3]);
           Q.aux[n] = make_float2(p.p[4], idf);

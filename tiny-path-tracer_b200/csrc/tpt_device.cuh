@@ -48,11 +48,13 @@ struct SceneLayout { // host-computed, lives in kernel parameter (constant) spac
 #define TPT_SMALL_MAX_OPS 16
 #define TPT_SMALL_MAX_BOXES 6
 struct SmallGroup {
-  int first_op, n_ops;            // transform chain of this group (outermost first)
+  // the chain's translate / rotate_y wrappers composed on the host: o' = Ry*o + b, d' = Ry*d
+  float cs, sn, bx, by, bz;
+  int first_op, n_ops;            // the chain itself (kept for reference; fill_hit replays it exactly)
   int xy_end, xz_end, yz_end, sph_end; // the group's records are [begin, xy_end) xy_rects, ... spheres
   int begin;
   int box_begin, box_end;         // axis-aligned boxes (a `box` = list of its six faces) under this chain
-  int pad0, pad1, pad2;
+  int pad0;
 };
 // `box` (src/rect_box.cc:93-115) recognised at scene upload: six rect faces of one axis-aligned
 // block. One slab test finds the entry / exit face instead of six rectangle tests.
@@ -287,7 +289,10 @@ TPT_DEV V3 moving_center(float4 a, float4 b, float4 c, float time) {
   return c0 + f * (c1 - c0);
 }
 
-template <bool PAR>
+// EXACT (fast mode only): IEEE fp32 sqrt / divide for the roots. Needed for the huge "wall"
+// spheres, where t decides which of two nearly coincident surfaces wins; ordinary spheres take the
+// approximate MUFU forms.
+template <bool PAR, bool EXACT = true>
 TPT_DEV bool sphere_test(V3 center, float radius, const XRay &x, float tmin, float tmax, float &t) {
   // src/sphere.cc:15-41. The quadratic's coefficients and discriminant are evaluated with
   // explicitly rounded fp32 operations in BOTH modes (never contracted into FMAs): the
@@ -313,7 +318,7 @@ TPT_DEV bool sphere_test(V3 center, float radius, const XRay &x, float tmin, flo
         t = temp;
         return true;
       }
-    } else {
+    } else if (EXACT) {
       float sq = __fsqrt_rn(disc);
       float two_a = 2.0f * a;
       float temp = __fdiv_rn(-b - sq, two_a);
@@ -322,6 +327,19 @@ TPT_DEV bool sphere_test(V3 center, float radius, const XRay &x, float tmin, flo
         return true;
       }
       temp = __fdiv_rn(-b + sq, two_a);
+      if (temp < tmax && temp > tmin) {
+        t = temp;
+        return true;
+      }
+    } else {
+      float sq = sqrtf(disc);
+      float inv = __frcp_rn(2.0f * a); // one reciprocal, two multiplies
+      float temp = (-b - sq) * inv;
+      if (temp < tmax && temp > tmin) {
+        t = temp;
+        return true;
+      }
+      temp = (-b + sq) * inv;
       if (temp < tmax && temp > tmin) {
         t = temp;
         return true;
@@ -508,24 +526,11 @@ TPT_DEV bool closest_hit_uniform(const SceneView &S, const Ray &r, float tmin, f
   float best = tmax;
   int best_prim = -1;
   for (int gi = 0; gi < Q.n_groups; gi++) {
-    const SmallGroup G = Q.groups[gi];
-    float o[3] = {r.o.x, r.o.y, r.o.z}, d[3] = {r.d.x, r.d.y, r.d.z};
-    for (int k = 0; k < G.n_ops; k++) { // headers/rect_box.h:89, src/rect_box.cc:175-179
-      const float4 op = Q.ops[G.first_op + k];
-      if (__float_as_int(op.x) == TPT_XF_TRANSLATE) {
-        o[0] -= op.y;
-        o[1] -= op.z;
-        o[2] -= op.w;
-      } else {
-        const float sn = op.y, co = op.z;
-        const float ox = co * o[0] - sn * o[2], oz = sn * o[0] + co * o[2];
-        const float dx = co * d[0] - sn * d[2], dz = sn * d[0] + co * d[2];
-        o[0] = ox;
-        o[2] = oz;
-        d[0] = dx;
-        d[2] = dz;
-      }
-    }
+    const SmallGroup &G = Q.groups[gi];
+    // ray into the group's space with the composed transform (headers/rect_box.h:89 and
+    // src/rect_box.cc:175-179 applied in chain order, folded into one y-rotation + offset)
+    const float o[3] = {G.cs * r.o.x - G.sn * r.o.z + G.bx, r.o.y + G.by, G.sn * r.o.x + G.cs * r.o.z + G.bz};
+    const float d[3] = {G.cs * r.d.x - G.sn * r.d.z, r.d.y, G.sn * r.d.x + G.cs * r.d.z};
     const float inv[3] = {1.0f / d[0], 1.0f / d[1], 1.0f / d[2]};
     small_rects<2, 0, 1>(Q, G.begin, G.xy_end, o, d, inv, tmin, best, best_prim);  // xy_rect: z = k
     small_rects<1, 0, 2>(Q, G.xy_end, G.xz_end, o, d, inv, tmin, best, best_prim); // xz_rect: y = k
@@ -556,10 +561,13 @@ TPT_DEV bool closest_hit_uniform(const SceneView &S, const Ray &r, float tmin, f
       x.d = mk(d[0], d[1], d[2]);
       for (int i = G.yz_end; i < G.sph_end; i++) {
         const float4 g = Q.geo[i];
+        const float2 w = Q.aux[i]; // w.x != 0: huge sphere, exact roots
         float t;
-        if (sphere_test<false>(mk(g.x, g.y, g.z), g.w, x, tmin, best, t)) {
+        const bool hit = (w.x != 0.0f) ? sphere_test<false, true>(mk(g.x, g.y, g.z), g.w, x, tmin, best, t)
+                                       : sphere_test<false, false>(mk(g.x, g.y, g.z), g.w, x, tmin, best, t);
+        if (hit) {
           best = t;
-          best_prim = __float_as_int(Q.aux[i].y);
+          best_prim = __float_as_int(w.y);
         }
       }
     }
@@ -872,7 +880,9 @@ template <bool PAR> TPT_DEV float light_pdf(const SceneView &S, V3 origin, V3 di
       float t;
       V3 c = mk(l0.y, l0.z, l0.w);
       float radius = l1.x;
-      if (sphere_test<PAR>(c, radius, x, 0.001f, FLT_MAX, t)) {
+      const bool sph_hit = (PAR || radius >= 500.0f) ? sphere_test<PAR, true>(c, radius, x, 0.001f, FLT_MAX, t)
+                                                     : sphere_test<PAR, false>(c, radius, x, 0.001f, FLT_MAX, t);
+      if (sph_hit) {
         float tmp = (radius * radius) / sqlen(c - origin);
         float cmax = sqrtf(1 - tmp);
         float solid = PAR ? (float)(2 * TPT_PI_D * (double)(1 - cmax)) : (2.f * TPT_PI_F) * (1 - cmax);

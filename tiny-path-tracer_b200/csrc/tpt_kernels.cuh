@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(TPT_MEGA_THREADS) render_mega_kernel(const __g
 #define TPT_WAVE_NQ 4 // queues: 0 lambertian, 1 metal, 2 dielectric (= TPT_MAT_*), 3 generate
 
 template <bool PAR, bool SMALL>
-__global__ void __launch_bounds__(TPT_WAVE_THREADS) render_wave_kernel(const __grid_constant__ RenderArgs A) {
+__global__ void __launch_bounds__(TPT_WAVE_THREADS, TPT_WAVE_MIN_BLOCKS) render_wave_kernel(const __grid_constant__ RenderArgs A) {
   extern __shared__ float4 sblob[];
   SceneView S;
   S.blob = stage_scene<true>(A.scene, sblob);

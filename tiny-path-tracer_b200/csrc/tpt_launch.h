@@ -7,6 +7,9 @@
 #ifndef TPT_WAVE_SPLIT_GEN
 #define TPT_WAVE_SPLIT_GEN 1 // 1: generate runs as its own phase after shade (one more barrier, +8 % measured)
 #endif
+#ifndef TPT_WAVE_MIN_BLOCKS
+#define TPT_WAVE_MIN_BLOCKS 3 // __launch_bounds__ min blocks per SM: 80 registers, 3 CTAs (measured best)
+#endif
 #ifndef TPT_WAVE_THREADS
 #define TPT_WAVE_THREADS 256
 #endif
