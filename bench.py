@@ -322,7 +322,7 @@ def run_ours(args, rank, local_rank, world):
         traffic = prof.get("render_wave_kernel" if args.kernel == "wavefront" else "render_mega_kernel", {}).get("dram_bytes_per_launch")
     except Exception:
         pass
-    acc_bytes = npix / world * 12 * max(1, min(8, (args.spp // 256) or 1))
+    acc_bytes = npix / world * 12 * max(1, st["reserved"][0])  # R accumulator planes x 12 B per owned pixel
     roofline = {
         "bound": "fp32", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops,
         "traffic": traffic, "kernel": "render_wave_kernel" if args.kernel == "wavefront" else "render_mega_kernel",

@@ -231,7 +231,8 @@ typedef struct tpt_stats {
   int32_t kernel_launches; /* kernels launched by the last call            */
   int32_t sm_count;
   int32_t blocks, threads_per_block;
-  int32_t reserved[4];
+  int32_t reserved[4];     /* [0] = sample ranges per pixel of the last single-device render
+                              (tpt_render_multi: batches taken by GPUs 0..3) */
 } tpt_stats;
 
 typedef struct tpt_scene tpt_scene; /* opaque: owns the device copies */

@@ -319,7 +319,9 @@ class Scene:
     def stats(self) -> dict:
         st = Stats()
         _check(lib().tpt_get_stats(self._s, C.byref(st)))
-        return {k: getattr(st, k) for k, _ in Stats._fields_ if k != "reserved"}
+        d = {k: getattr(st, k) for k, _ in Stats._fields_ if k != "reserved"}
+        d["reserved"] = [int(x) for x in st.reserved]
+        return d
 
     def device_buffers(self):
         """(sum_ptr, sum_bytes, rgb8_ptr, rgb8_bytes): device addresses of the last render's products."""

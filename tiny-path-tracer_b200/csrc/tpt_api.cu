@@ -350,13 +350,17 @@ void build_small_scene(const tpt_scene_desc *d, bool smem_ok, SmallScene &Q) {
   Q.enabled = 1;
 }
 
-int ensure(void **p, size_t &have, size_t want) {
+// Render products come from the device's stream-ordered memory pool (cudaMallocAsync): the pool
+// keeps freed blocks (release threshold = max, set in tpt_scene_create), so creating a scene,
+// rendering and destroying it again -- the end-to-end pattern of a short-lived caller -- does not
+// pay cudaMalloc / cudaFree device synchronisations and page (un)mapping every time.
+int ensure(cudaStream_t st, void **p, size_t &have, size_t want) {
   if (have >= want && *p) return TPT_OK;
-  if (*p) cudaFree(*p);
+  if (*p) cudaFreeAsync(*p, st);
   *p = nullptr;
   have = 0;
-  cudaError_t e = cudaMalloc(p, want);
-  if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+  cudaError_t e = cudaMallocAsync(p, want, st);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMallocAsync");
   have = want;
   return TPT_OK;
 }
@@ -475,11 +479,11 @@ int run_plan(tpt_scene *s, Plan &plan, bool want_sum, bool want_rgb8, bool want_
   ResolveArgs &R = plan.res;
   int rc;
   size_t acc_want = (size_t)A.n_ranges * plan.npix * 3 * sizeof(float);
-  if ((rc = ensure((void **)&s->d_acc, s->acc_bytes, acc_want)) != TPT_OK) return rc;
+  if ((rc = ensure(s->stream, (void **)&s->d_acc, s->acc_bytes, acc_want)) != TPT_OK) return rc;
   size_t sum_want = (size_t)R.slices * plan.npix * 3 * sizeof(float);
-  if ((rc = ensure((void **)&s->d_sum, s->sum_bytes, sum_want)) != TPT_OK) return rc;
-  if ((rc = ensure((void **)&s->d_rgb8, s->rgb8_bytes, plan.npix * 3)) != TPT_OK) return rc;
-  if ((rc = ensure((void **)&s->d_rgb8_slices, s->rgb8_slices_bytes, (size_t)R.slices * plan.npix * 3)) != TPT_OK) return rc;
+  if ((rc = ensure(s->stream, (void **)&s->d_sum, s->sum_bytes, sum_want)) != TPT_OK) return rc;
+  if ((rc = ensure(s->stream, (void **)&s->d_rgb8, s->rgb8_bytes, plan.npix * 3)) != TPT_OK) return rc;
+  if ((rc = ensure(s->stream, (void **)&s->d_rgb8_slices, s->rgb8_slices_bytes, (size_t)R.slices * plan.npix * 3)) != TPT_OK) return rc;
   A.acc = s->d_acc;
   A.counters = s->d_counters;
   R.acc = s->d_acc;
@@ -530,6 +534,7 @@ int run_plan(tpt_scene *s, Plan &plan, bool want_sum, bool want_rgb8, bool want_
   st.sm_count = s->prop.multiProcessorCount;
   st.blocks = plan.blocks;
   st.threads_per_block = plan.wavefront ? TPT_WAVE_THREADS : TPT_MEGA_THREADS;
+  st.reserved[0] = A.n_ranges; // sample ranges per pixel (accumulator planes written by the kernel)
   st.h2d_bytes = s->blob_bytes + sizeof(RenderArgs) + sizeof(ResolveArgs); // scene blob + launch arguments
   s->last_nx = A.nx;
   s->last_ny = A.ny;
@@ -598,10 +603,10 @@ int prepare_buffers(tpt_scene *s, Plan &plan, bool want_slices) {
   ResolveArgs &R = plan.res;
   int rc;
   size_t acc_want = (size_t)A.n_ranges * plan.npix * 3 * sizeof(float);
-  if ((rc = ensure((void **)&s->d_acc, s->acc_bytes, acc_want)) != TPT_OK) return rc;
-  if ((rc = ensure((void **)&s->d_sum, s->sum_bytes, (size_t)R.slices * plan.npix * 3 * sizeof(float))) != TPT_OK) return rc;
-  if ((rc = ensure((void **)&s->d_rgb8, s->rgb8_bytes, plan.npix * 3)) != TPT_OK) return rc;
-  if ((rc = ensure((void **)&s->d_rgb8_slices, s->rgb8_slices_bytes, (size_t)R.slices * plan.npix * 3)) != TPT_OK) return rc;
+  if ((rc = ensure(s->stream, (void **)&s->d_acc, s->acc_bytes, acc_want)) != TPT_OK) return rc;
+  if ((rc = ensure(s->stream, (void **)&s->d_sum, s->sum_bytes, (size_t)R.slices * plan.npix * 3 * sizeof(float))) != TPT_OK) return rc;
+  if ((rc = ensure(s->stream, (void **)&s->d_rgb8, s->rgb8_bytes, plan.npix * 3)) != TPT_OK) return rc;
+  if ((rc = ensure(s->stream, (void **)&s->d_rgb8_slices, s->rgb8_slices_bytes, (size_t)R.slices * plan.npix * 3)) != TPT_OK) return rc;
   R.acc = s->d_acc;
   R.sum_rgb = s->d_sum;
   R.rgb8 = s->d_rgb8;
@@ -829,6 +834,13 @@ int tpt_scene_create(const tpt_scene_desc *d, int device, tpt_scene **out) {
     return fail(TPT_ERR_NO_DEVICE, "device is not sm_100-class; kernels are built for sm_100a only");
   }
   CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+  {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      unsigned long long keep = ~0ULL;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+  }
   for (auto &ev : s->ev) CK(cudaEventCreate(&ev));
 
   // ---- blob: the C structs back to back, each table padded to 16 bytes ----
@@ -873,8 +885,9 @@ int tpt_scene_create(const tpt_scene_desc *d, int device, tpt_scene **out) {
   L.background = d->background;
   s->has_lights = d->n_lights > 0;
   s->blob_bytes = blob.size();
-  CK(cudaMalloc((void **)&s->d_blob, blob.size()));
-  CK(cudaMemcpy(s->d_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+  CK(cudaMallocAsync((void **)&s->d_blob, blob.size(), s->stream));
+  CK(cudaMemcpyAsync(s->d_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice, s->stream));
+  CK(cudaStreamSynchronize(s->stream));
   L.blob_global = s->d_blob;
   s->use_smem = blob.size() <= 64 * 1024;
   build_small_scene(d, s->use_smem, s->small);
@@ -906,7 +919,7 @@ int tpt_scene_create(const tpt_scene_desc *d, int device, tpt_scene **out) {
     L.image_w[i] = im.width;
     L.image_h[i] = im.height;
   }
-  CK(cudaMalloc((void **)&s->d_counters, TPT_MAX_BATCHES * 8 * sizeof(unsigned long long)));
+  CK(cudaMallocAsync((void **)&s->d_counters, TPT_MAX_BATCHES * 8 * sizeof(unsigned long long), s->stream));
   s->stats.h2d_bytes = blob.size();
   *out = s;
   return TPT_OK;
@@ -917,12 +930,15 @@ void tpt_scene_destroy(tpt_scene *s) {
   cudaSetDevice(s->device);
   for (auto t : s->textures) cudaDestroyTextureObject(t);
   for (auto a : s->arrays) cudaFreeArray(a);
-  cudaFree(s->d_blob);
-  cudaFree(s->d_acc);
-  cudaFree(s->d_counters);
-  cudaFree(s->d_sum);
-  cudaFree(s->d_rgb8);
-  cudaFree(s->d_rgb8_slices);
+  if (s->stream) {
+    if (s->d_acc) cudaFreeAsync(s->d_acc, s->stream);
+    if (s->d_sum) cudaFreeAsync(s->d_sum, s->stream);
+    if (s->d_rgb8) cudaFreeAsync(s->d_rgb8, s->stream);
+    if (s->d_rgb8_slices) cudaFreeAsync(s->d_rgb8_slices, s->stream);
+    if (s->d_blob) cudaFreeAsync(s->d_blob, s->stream);
+    if (s->d_counters) cudaFreeAsync(s->d_counters, s->stream);
+    cudaStreamSynchronize(s->stream);
+  }
   for (auto ev : s->ev)
     if (ev) cudaEventDestroy(ev);
   if (s->stream) cudaStreamDestroy(s->stream);
