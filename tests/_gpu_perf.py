@@ -31,7 +31,7 @@ for kern in kernels:
 for scene, camf in (("random_scene", T.book_camera), ("random_scene_list", T.book_camera), ("textured_lit", T.book_camera)):
     s2 = T.Scene(common.host_scene(T, scene, perlin=common.perlin_struct(T, common.golden("textures")), lights=common.TEXTURED_LIGHTS if scene == "textured_lit" else None))
     cam3 = camf(800, 800, fov=20.0 if "random" in scene else 50.0)
-    for mode in (T.MODE_FAST, T.MODE_PARITY):
-        p = T.make_params(800, 800, 16, 15, mode=mode, seed=1)
+    for mode, kern in ((T.MODE_FAST, 0), (T.MODE_FAST, 1), (T.MODE_PARITY, 0), (T.MODE_PARITY, 1)):
+        p = T.make_params(800, 800, 16, 15, mode=mode, seed=1, kernel=kern)
         st = s2.render_device(cam3, p); st = s2.render_device(cam3, p)
-        print(f"{scene} mode {mode}: {st['render_ms']:.2f} ms  {st['paths']/st['render_ms']/1e3:.0f} Mpaths/s  {st['rays']/st['render_ms']/1e3:.0f} Mrays/s rays/path {st['rays']/st['paths']:.3f}")
+        print(f"{scene} mode {mode} kernel {kern}: {st['render_ms']:.2f} ms  {st['paths']/st['render_ms']/1e3:.0f} Mpaths/s  {st['rays']/st['render_ms']/1e3:.0f} Mrays/s rays/path {st['rays']/st['paths']:.3f}")

@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cfloat>
 #include <climits>
 #include <cmath>
 #include <cstdio>
@@ -125,6 +126,8 @@ struct tpt_scene {
   std::vector<cudaArray_t> arrays;
   std::vector<cudaTextureObject_t> textures;
   bool has_lights = false;
+  bool fbvh_has_moving = false; // the fast BVH boxes moving spheres over [fbvh_t0, fbvh_t1] only
+  float fbvh_t0 = 0, fbvh_t1 = 0;
   // render products (device)
   float *d_acc = nullptr;
   size_t acc_bytes = 0;
@@ -208,6 +211,184 @@ int validate_desc(const tpt_scene_desc *d, int &depth_out) {
     if (!d->images[i].rgb || d->images[i].width <= 0 || d->images[i].height <= 0)
       return fail(TPT_ERR_INVALID, "image without pixels");
   return TPT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// FAST-mode acceleration structure for scenes above the brute-force size: binned-SAH BVH2 over
+// the world-space boxes of the non-duplicate leaves. Host side, once per scene upload.
+// ---------------------------------------------------------------------------------------------
+struct Box3 {
+  float lo[3], hi[3];
+  void reset() {
+    for (int c = 0; c < 3; c++) { lo[c] = FLT_MAX; hi[c] = -FLT_MAX; }
+  }
+  void grow(const Box3 &b) {
+    for (int c = 0; c < 3; c++) { lo[c] = std::min(lo[c], b.lo[c]); hi[c] = std::max(hi[c], b.hi[c]); }
+  }
+  float area() const {
+    float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+    return 2.f * (dx * dy + dy * dz + dz * dx);
+  }
+};
+
+struct FastBvh {
+  std::vector<float> nodes; // 16 floats per node
+  std::vector<int32_t> leaf_prims;
+  float moving_t0 = FLT_MAX, moving_t1 = -FLT_MAX; // ray times the moving-sphere boxes are valid for
+  bool has_moving = false;
+};
+
+// object-space box of a leaf -> world space through the inverse of its wrapper chain
+// (translate: +offset, rotate_y: x = c x' + s z', z = -s x' + c z'), innermost wrapper first
+Box3 world_box(const tpt_scene_desc *d, const tpt_node &leaf) {
+  const tpt_chain &ch = d->chains[leaf.kind >> 16];
+  Box3 out;
+  out.reset();
+  for (int corner = 0; corner < 8; corner++) {
+    double p[3] = {corner & 1 ? leaf.bmax[0] : leaf.bmin[0], corner & 2 ? leaf.bmax[1] : leaf.bmin[1],
+                   corner & 4 ? leaf.bmax[2] : leaf.bmin[2]};
+    for (int k = ch.n_ops - 1; k >= 0; k--) {
+      const tpt_xform_op &op = d->xform_ops[ch.first_op + k];
+      if (op.kind == TPT_XF_TRANSLATE) {
+        p[0] += op.a; p[1] += op.b; p[2] += op.c;
+      } else {
+        double x = op.b * p[0] + op.a * p[2], z = -op.a * p[0] + op.b * p[2];
+        p[0] = x; p[2] = z;
+      }
+    }
+    Box3 b;
+    for (int c = 0; c < 3; c++) b.lo[c] = b.hi[c] = (float)p[c];
+    out.grow(b);
+  }
+  for (int c = 0; c < 3; c++) { // conservative padding: fp32 slab test vs the primitive's own arithmetic
+    float pad = 1e-4f + 1e-5f * std::max(std::fabs(out.lo[c]), std::fabs(out.hi[c]));
+    out.lo[c] -= pad;
+    out.hi[c] += pad;
+  }
+  return out;
+}
+
+struct BuildItem { Box3 box; float cen[3]; int prim; };
+
+int32_t build_fbvh_rec(std::vector<BuildItem> &items, int begin, int end, FastBvh &out, Box3 &bounds_out);
+
+// returns the child reference: >= 0 inner node index, < 0 ~((first << 3) | (count - 1))
+int32_t make_child(std::vector<BuildItem> &items, int begin, int end, FastBvh &out, Box3 &box) {
+  int n = end - begin;
+  if (n <= 2) {
+    box.reset();
+    int first = (int)out.leaf_prims.size();
+    for (int i = begin; i < end; i++) {
+      out.leaf_prims.push_back(items[i].prim);
+      box.grow(items[i].box);
+    }
+    return ~((first << 3) | (n - 1));
+  }
+  return build_fbvh_rec(items, begin, end, out, box);
+}
+
+int32_t build_fbvh_rec(std::vector<BuildItem> &items, int begin, int end, FastBvh &out, Box3 &bounds_out) {
+  Box3 cb, bb;
+  cb.reset();
+  bb.reset();
+  for (int i = begin; i < end; i++) {
+    Box3 c;
+    for (int k = 0; k < 3; k++) c.lo[k] = c.hi[k] = items[i].cen[k];
+    cb.grow(c);
+    bb.grow(items[i].box);
+  }
+  bounds_out = bb;
+  // binned SAH over the axis / plane with the lowest cost
+  const int NB = 16;
+  int best_axis = -1, best_split = -1;
+  float best_cost = FLT_MAX;
+  for (int axis = 0; axis < 3; axis++) {
+    float ext = cb.hi[axis] - cb.lo[axis];
+    if (!(ext > 0)) continue;
+    Box3 bins[NB];
+    int cnt[NB] = {0};
+    for (auto &b : bins) b.reset();
+    for (int i = begin; i < end; i++) {
+      int k = std::min(NB - 1, (int)(NB * (items[i].cen[axis] - cb.lo[axis]) / ext));
+      bins[k].grow(items[i].box);
+      cnt[k]++;
+    }
+    float right_area[NB];
+    int right_cnt[NB];
+    Box3 acc;
+    acc.reset();
+    int c = 0;
+    for (int k = NB - 1; k > 0; k--) {
+      acc.grow(bins[k]);
+      c += cnt[k];
+      right_area[k] = c ? acc.area() : 0.f;
+      right_cnt[k] = c;
+    }
+    acc.reset();
+    c = 0;
+    for (int k = 0; k < NB - 1; k++) {
+      acc.grow(bins[k]);
+      c += cnt[k];
+      if (c == 0 || right_cnt[k + 1] == 0) continue;
+      float cost = acc.area() * c + right_area[k + 1] * right_cnt[k + 1];
+      if (cost < best_cost) { best_cost = cost; best_axis = axis; best_split = k; }
+    }
+  }
+  int mid;
+  if (best_axis < 0) {
+    mid = (begin + end) / 2; // coincident centroids
+  } else {
+    float ext = cb.hi[best_axis] - cb.lo[best_axis];
+    auto it = std::partition(items.begin() + begin, items.begin() + end, [&](const BuildItem &b) {
+      int k = std::min(NB - 1, (int)(NB * (b.cen[best_axis] - cb.lo[best_axis]) / ext));
+      return k <= best_split;
+    });
+    mid = (int)(it - items.begin());
+    if (mid == begin || mid == end) mid = (begin + end) / 2;
+  }
+  int me = (int)(out.nodes.size() / 16);
+  out.nodes.resize(out.nodes.size() + 16, 0.f);
+  Box3 b0, b1;
+  int32_t c0 = make_child(items, begin, mid, out, b0);
+  int32_t c1 = make_child(items, mid, end, out, b1);
+  float *n = &out.nodes[(size_t)me * 16];
+  n[0] = b0.lo[0]; n[1] = b0.lo[1]; n[2] = b0.lo[2]; n[3] = b0.hi[0];
+  n[4] = b0.hi[1]; n[5] = b0.hi[2]; n[6] = b1.lo[0]; n[7] = b1.lo[1];
+  n[8] = b1.lo[2]; n[9] = b1.hi[0]; n[10] = b1.hi[1]; n[11] = b1.hi[2];
+  std::memcpy(&n[12], &c0, 4);
+  std::memcpy(&n[13], &c1, 4);
+  return me;
+}
+
+void build_fast_bvh(const tpt_scene_desc *d, FastBvh &out) {
+  std::vector<BuildItem> items;
+  std::vector<char> seen(d->n_prims, 0);
+  int skip_until = -1;
+  for (int i = 0; i < d->n_nodes; i++) {
+    const tpt_node &nd = d->nodes[i];
+    int k = nd.kind & 0xff;
+    if (i < skip_until) continue;
+    if (nd.kind & TPT_NODE_DUP) {
+      if (k != TPT_NODE_LEAF) skip_until = nd.end_or_prim;
+      continue;
+    }
+    if (k != TPT_NODE_LEAF || seen[nd.end_or_prim]) continue;
+    seen[nd.end_or_prim] = 1;
+    BuildItem it;
+    it.box = world_box(d, nd);
+    for (int c = 0; c < 3; c++) it.cen[c] = 0.5f * (it.box.lo[c] + it.box.hi[c]);
+    it.prim = nd.end_or_prim;
+    const tpt_prim &p = d->prims[it.prim];
+    if (p.kind == TPT_PRIM_MOVING_SPHERE) {
+      out.has_moving = true;
+      out.moving_t0 = std::min(out.moving_t0, std::min(p.p[7], p.p[8]));
+      out.moving_t1 = std::max(out.moving_t1, std::max(p.p[7], p.p[8]));
+    }
+    items.push_back(it);
+  }
+  if (items.size() < 2) return;
+  Box3 root;
+  build_fbvh_rec(items, 0, (int)items.size(), out, root);
 }
 
 // Group the non-duplicate leaves by transform chain and primitive kind (xy, xz, yz rect, sphere).
@@ -383,8 +564,6 @@ int make_plan(tpt_scene *s, const tpt_camera *cam, const tpt_render_params *p, P
   if (per_slice <= 0) return fail(TPT_ERR_INVALID, "ns < slices (the reference would divide by zero, main.cpp:113,127)");
   if (p->mode != TPT_MODE_PARITY && p->mode != TPT_MODE_FAST) return fail(TPT_ERR_INVALID, "unknown mode");
   if (p->kernel != TPT_KERNEL_MEGA && p->kernel != TPT_KERNEL_WAVEFRONT) return fail(TPT_ERR_UNSUPPORTED, "unknown kernel variant");
-  if (p->kernel == TPT_KERNEL_WAVEFRONT && !s->use_smem)
-    return fail(TPT_ERR_UNSUPPORTED, "wavefront variant needs a shared-memory resident scene (<= 64 KB)");
   plan.wavefront = p->kernel == TPT_KERNEL_WAVEFRONT;
   if (p->part_count <= 0 || p->part_index < 0 || p->part_index >= p->part_count) return fail(TPT_ERR_INVALID, "bad part_index/part_count");
   if (p->part_count > TPT_MAX_BATCHES) return fail(TPT_ERR_UNSUPPORTED, "part_count above TPT_MAX_BATCHES");
@@ -394,6 +573,10 @@ int make_plan(tpt_scene *s, const tpt_camera *cam, const tpt_render_params *p, P
   std::memset(&A, 0, sizeof(A));
   A.scene = s->layout;
   A.small = s->small;
+  // moving-sphere boxes of the fast BVH cover the spheres' own [time0,time1]; a shutter interval
+  // outside it extrapolates the centres, so fall back to the reference tree for that render
+  if (s->fbvh_has_moving && !(std::min(cam->time0, cam->time1) >= s->fbvh_t0 && std::max(cam->time0, cam->time1) <= s->fbvh_t1))
+    A.scene.fbvh_time_ok = 0;
   auto v3 = [](const float *f) { return V3{f[0], f[1], f[2]}; };
   A.cam.origin = v3(cam->origin);
   A.cam.llc = v3(cam->lower_left_corner);
@@ -497,7 +680,7 @@ int run_plan(tpt_scene *s, Plan &plan, bool want_sum, bool want_rgb8, bool want_
   int bps = 0;
   const bool small = s->small.enabled != 0;
   if (plan.wavefront)
-    CK(plan.parity ? wave_occupancy_parity(A, small, &bps) : wave_occupancy_fast(A, small, &bps));
+    CK(plan.parity ? wave_occupancy_parity(A, small, s->use_smem, &bps) : wave_occupancy_fast(A, small, s->use_smem, &bps));
   else
     CK(plan.parity ? mega_occupancy_parity(s->use_smem, small, smem, &bps)
                    : mega_occupancy_fast(s->use_smem, small, smem, &bps));
@@ -508,7 +691,7 @@ int run_plan(tpt_scene *s, Plan &plan, bool want_sum, bool want_rgb8, bool want_
   CK(cudaMemsetAsync(s->d_counters, 0, 8 * sizeof(unsigned long long), s->stream));
   CK(cudaEventRecord(s->ev[0], s->stream));
   if (plan.wavefront)
-    CK(plan.parity ? launch_wave_parity(A, small, plan.blocks, s->stream) : launch_wave_fast(A, small, plan.blocks, s->stream));
+    CK(plan.parity ? launch_wave_parity(A, small, s->use_smem, plan.blocks, s->stream) : launch_wave_fast(A, small, s->use_smem, plan.blocks, s->stream));
   else
     CK(plan.parity ? launch_mega_parity(A, s->use_smem, small, plan.blocks, s->stream)
                    : launch_mega_fast(A, s->use_smem, small, plan.blocks, s->stream));
@@ -629,14 +812,14 @@ int launch_batch(tpt_scene *s, const tpt_camera *cam, const tpt_render_params *p
   int bps = 0;
   const bool small = s->small.enabled != 0;
   if (plan.wavefront)
-    CK(plan.parity ? wave_occupancy_parity(A, small, &bps) : wave_occupancy_fast(A, small, &bps));
+    CK(plan.parity ? wave_occupancy_parity(A, small, s->use_smem, &bps) : wave_occupancy_fast(A, small, s->use_smem, &bps));
   else
     CK(plan.parity ? mega_occupancy_parity(s->use_smem, small, smem, &bps)
                    : mega_occupancy_fast(s->use_smem, small, smem, &bps));
   if (bps < 1) return fail(TPT_ERR_CUDA, "render kernel does not fit on an SM");
   int blocks = bps * s->prop.multiProcessorCount;
   if (plan.wavefront)
-    CK(plan.parity ? launch_wave_parity(A, small, blocks, s->stream) : launch_wave_fast(A, small, blocks, s->stream));
+    CK(plan.parity ? launch_wave_parity(A, small, s->use_smem, blocks, s->stream) : launch_wave_fast(A, small, s->use_smem, blocks, s->stream));
   else
     CK(plan.parity ? launch_mega_parity(A, s->use_smem, small, blocks, s->stream)
                    : launch_mega_fast(A, s->use_smem, small, blocks, s->stream));
@@ -878,6 +1061,17 @@ int tpt_scene_create(const tpt_scene_desc *d, int device, tpt_scene **out) {
     append(blob, d->perlin->perm_y, 256);
     append(blob, d->perlin->perm_z, 256);
   }
+  FastBvh fb;
+  if (d->n_prims > TPT_SMALL_MAX_PRIMS) build_fast_bvh(d, fb);
+  L.off_fbvh = words();
+  append(blob, fb.nodes.data(), fb.nodes.size());
+  L.off_fleaf = words();
+  append(blob, fb.leaf_prims.data(), fb.leaf_prims.size());
+  L.n_fbvh = (int)(fb.nodes.size() / 16);
+  L.fbvh_time_ok = 1;
+  s->fbvh_has_moving = fb.has_moving;
+  s->fbvh_t0 = fb.moving_t0;
+  s->fbvh_t1 = fb.moving_t1;
   L.blob_words = words();
   L.n_nodes = d->n_nodes;
   L.n_prims = d->n_prims;

@@ -33,6 +33,7 @@ struct SceneLayout { // host-computed, lives in kernel parameter (constant) spac
   const float4 *blob_global;
   int blob_words; // float4 count
   int off_nodes, off_prims, off_chains, off_ops, off_mats, off_texs, off_lights, off_perlin;
+  int off_fbvh, off_fleaf, n_fbvh, fbvh_time_ok; // FAST-mode SAH BVH over world-space leaf boxes (0 nodes = none)
   int n_nodes, n_prims, n_lights, background;
   cudaTextureObject_t images[TPT_MAX_IMAGES];
   int image_w[TPT_MAX_IMAGES], image_h[TPT_MAX_IMAGES];
@@ -578,6 +579,72 @@ TPT_DEV bool closest_hit_uniform(const SceneView &S, const Ray &r, float tmin, f
 }
 
 // ------------------------------------------------------------------------------------------
+// Larger scenes, FAST mode: a binned-SAH BVH2 built by the library at scene upload over the
+// WORLD-space boxes of the leaves (the reference's own tree is a random-axis median split that
+// costs 54 box + 12 primitive tests per ray on random_scene). 64-byte nodes hold both
+// children's boxes; traversal is per lane, nearest child first, t_max shrinking, short stack.
+// Closest hit is independent of the acceleration structure (ties aside), so the estimator is
+// unchanged; PARITY mode keeps replaying the reference's tree.
+// ------------------------------------------------------------------------------------------
+TPT_DEV bool closest_hit_fbvh(const SceneView &S, const Ray &r, float tmin, float tmax, float &t_out, int &prim_out) {
+  const float4 *N = S.blob + S.L->off_fbvh;
+  const int *leaf_prims = reinterpret_cast<const int *>(S.blob + S.L->off_fleaf);
+  const float ix = 1.0f / r.d.x, iy = 1.0f / r.d.y, iz = 1.0f / r.d.z;
+  const float ox = -r.o.x * ix, oy = -r.o.y * iy, oz = -r.o.z * iz; // t = p * inv + (-o * inv)
+  XRay x;
+  x.chain = -1;
+  float best = tmax;
+  int best_prim = -1;
+  int stack[32];
+  int sp = 0;
+  int node = 0;
+  for (;;) {
+    int next = -1; // inner node to descend into without touching the stack
+    if (node >= 0) {
+      const float4 a = N[4 * node], b = N[4 * node + 1], c = N[4 * node + 2], d = N[4 * node + 3];
+      // child 0: lo = (a.x,a.y,a.z) hi = (a.w,b.x,b.y) ; child 1: lo = (b.z,b.w,c.x) hi = (c.y,c.z,c.w)
+      float t0x = fmaf(a.x, ix, ox), t1x = fmaf(a.w, ix, ox);
+      float t0y = fmaf(a.y, iy, oy), t1y = fmaf(b.x, iy, oy);
+      float t0z = fmaf(a.z, iz, oz), t1z = fmaf(b.y, iz, oz);
+      float n0 = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), tmin));
+      float f0 = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), best));
+      t0x = fmaf(b.z, ix, ox); t1x = fmaf(c.y, ix, ox);
+      t0y = fmaf(b.w, iy, oy); t1y = fmaf(c.z, iy, oy);
+      t0z = fmaf(c.x, iz, oz); t1z = fmaf(c.w, iz, oz);
+      float n1 = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), tmin));
+      float f1 = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), best));
+      const bool h0 = n0 <= f0, h1 = n1 <= f1;
+      int i0 = __float_as_int(d.x), i1 = __float_as_int(d.y);
+      if (h0 && h1) {
+        if (n1 < n0) { int t = i0; i0 = i1; i1 = t; } // i0 = nearer
+        stack[sp++] = i1;
+        next = i0;
+      } else if (h0) next = i0;
+      else if (h1) next = i1;
+      else next = sp > 0 ? stack[--sp] : 0x7fffffff;
+    } else {
+      // leaf: ~node = first << 3 | (count - 1)
+      const int code = ~node, first = code >> 3, count = (code & 7) + 1;
+      for (int k = 0; k < count; k++) {
+        const int prim = leaf_prims[first + k];
+        to_chain<false>(S, r, __float_as_int(S.blob[S.L->off_prims + 4 * prim].z), x);
+        float t;
+        if (prim_test<false>(S, prim, x, r.time, tmin, best, t)) {
+          best = t;
+          best_prim = prim;
+        }
+      }
+      next = sp > 0 ? stack[--sp] : 0x7fffffff;
+    }
+    if (next == 0x7fffffff) break;
+    node = next;
+  }
+  t_out = best;
+  prim_out = best_prim;
+  return best_prim >= 0;
+}
+
+// ------------------------------------------------------------------------------------------
 // hit_record of the winning leaf, recomputed from (prim, t) with the leaf's own arithmetic
 // ------------------------------------------------------------------------------------------
 struct HitRec {
@@ -988,8 +1055,10 @@ TPT_DEV bool dead_channel(float t) { return t == 0.0f || isnan(t); }
 template <bool PAR, bool SMALL>
 TPT_DEV int extend(const SceneView &S, const PathState &ps, int max_depth, float t_min, float &t, int &prim,
                    V3 &radiance) {
-  bool any_hit = (SMALL && !PAR) ? closest_hit_uniform(S, ps.ray, t_min, FLT_MAX, t, prim)
-                                 : closest_hit<PAR>(S, ps.ray, t_min, FLT_MAX, t, prim);
+  bool any_hit;
+  if (SMALL && !PAR) any_hit = closest_hit_uniform(S, ps.ray, t_min, FLT_MAX, t, prim);
+  else if (!PAR && S.L->n_fbvh > 0 && S.L->fbvh_time_ok) any_hit = closest_hit_fbvh(S, ps.ray, t_min, FLT_MAX, t, prim);
+  else any_hit = closest_hit<PAR>(S, ps.ray, t_min, FLT_MAX, t, prim);
   radiance = mk(0, 0, 0);
   if (!any_hit) {
     if (S.L->background == TPT_BG_SKY) {

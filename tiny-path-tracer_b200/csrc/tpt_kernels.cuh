@@ -45,8 +45,10 @@ __global__ void __launch_bounds__(128) intersect_kernel(const __grid_constant__ 
   out.n[0] = out.n[1] = out.n[2] = 0.f;
   float t;
   int prim;
-  bool any_hit = (SMALL && !PAR) ? closest_hit_uniform(S, r, A.tmin, A.tmax, t, prim)
-                                 : closest_hit<PAR>(S, r, A.tmin, A.tmax, t, prim);
+  bool any_hit;
+  if (SMALL && !PAR) any_hit = closest_hit_uniform(S, r, A.tmin, A.tmax, t, prim);
+  else if (!PAR && A.scene.n_fbvh > 0) any_hit = closest_hit_fbvh(S, r, A.tmin, A.tmax, t, prim);
+  else any_hit = closest_hit<PAR>(S, r, A.tmin, A.tmax, t, prim);
   if (any_hit) {
     HitRec h;
     fill_hit<PAR>(S, r, prim, t, true, h);
@@ -202,16 +204,16 @@ __global__ void __launch_bounds__(TPT_MEGA_THREADS) render_mega_kernel(const __g
 // ------------------------------------------------------------------------------------------
 #define TPT_WAVE_NQ 4 // queues: 0 lambertian, 1 metal, 2 dielectric (= TPT_MAT_*), 3 generate
 
-template <bool PAR, bool SMALL>
+template <bool PAR, bool SMALL, bool SMEM>
 __global__ void __launch_bounds__(TPT_WAVE_THREADS, TPT_WAVE_MIN_BLOCKS) render_wave_kernel(const __grid_constant__ RenderArgs A) {
   extern __shared__ float4 sblob[];
   SceneView S;
-  S.blob = stage_scene<true>(A.scene, sblob);
+  S.blob = stage_scene<SMEM>(A.scene, sblob); // scenes above 64 KB stay in global memory (L1-cached)
   S.L = &A.scene;
   S.small = &A.small;
   constexpr int NSLOT = TPT_WAVE_SLOTS;
   constexpr int NWARP = TPT_WAVE_THREADS / 32;
-  float *sf = reinterpret_cast<float *>(sblob + A.scene.blob_words);
+  float *sf = reinterpret_cast<float *>(sblob + (SMEM ? A.scene.blob_words : 0));
   int *si = reinterpret_cast<int *>(sf);
   // structure-of-arrays slot state: field f of slot s at sf[f * NSLOT + s]
   enum { F_OX, F_OY, F_OZ, F_DX, F_DY, F_DZ, F_TIME, F_TX, F_TY, F_TZ, F_AX, F_AY, F_AZ,
@@ -512,23 +514,24 @@ cudaError_t TPT_FN(launch_mega_)(const RenderArgs &A, bool smem, bool small, int
 }
 
 typedef void (*wave_fn)(RenderArgs);
-static wave_fn wave_variant(bool small) {
-  return small ? render_wave_kernel<TPT_PAR, true> : render_wave_kernel<TPT_PAR, false>;
+static wave_fn wave_variant(bool small, bool smem) {
+  if (!smem) return render_wave_kernel<TPT_PAR, false, false>;
+  return small ? render_wave_kernel<TPT_PAR, true, true> : render_wave_kernel<TPT_PAR, false, true>;
 }
-static size_t wave_smem_bytes(const RenderArgs &A) {
-  return (size_t)A.scene.blob_words * 16 + (size_t)TPT_WAVE_SLOTS * (21 * 4 + 2 * TPT_WAVE_NQ * 2);
+static size_t wave_smem_bytes(const RenderArgs &A, bool smem) {
+  return (smem ? (size_t)A.scene.blob_words * 16 : 0) + (size_t)TPT_WAVE_SLOTS * (21 * 4 + 2 * TPT_WAVE_NQ * 2);
 }
 
-cudaError_t TPT_FN(wave_occupancy_)(const RenderArgs &A, bool small, int *blocks_per_sm) {
-  wave_fn k = wave_variant(small);
-  size_t bytes = wave_smem_bytes(A);
+cudaError_t TPT_FN(wave_occupancy_)(const RenderArgs &A, bool small, bool smem, int *blocks_per_sm) {
+  wave_fn k = wave_variant(small, smem);
+  size_t bytes = wave_smem_bytes(A, smem);
   cudaError_t e = allow_smem(k, bytes);
   if (e != cudaSuccess) return e;
   return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k, TPT_WAVE_THREADS, bytes);
 }
 
-cudaError_t TPT_FN(launch_wave_)(const RenderArgs &A, bool small, int blocks, cudaStream_t st) {
-  wave_variant(small)<<<blocks, TPT_WAVE_THREADS, wave_smem_bytes(A), st>>>(A);
+cudaError_t TPT_FN(launch_wave_)(const RenderArgs &A, bool small, bool smem, int blocks, cudaStream_t st) {
+  wave_variant(small, smem)<<<blocks, TPT_WAVE_THREADS, wave_smem_bytes(A, smem), st>>>(A);
   return cudaGetLastError();
 }
 

@@ -58,11 +58,11 @@ cudaError_t mega_occupancy_parity(bool smem, bool small, size_t smem_bytes, int 
 cudaError_t mega_occupancy_fast(bool smem, bool small, size_t smem_bytes, int *blocks_per_sm);
 cudaError_t launch_mega_parity(const RenderArgs &A, bool smem, bool small, int blocks, cudaStream_t st);
 cudaError_t launch_mega_fast(const RenderArgs &A, bool smem, bool small, int blocks, cudaStream_t st);
-// persistent wavefront variant (scene must be shared-memory resident)
-cudaError_t wave_occupancy_parity(const RenderArgs &A, bool small, int *blocks_per_sm);
-cudaError_t wave_occupancy_fast(const RenderArgs &A, bool small, int *blocks_per_sm);
-cudaError_t launch_wave_parity(const RenderArgs &A, bool small, int blocks, cudaStream_t st);
-cudaError_t launch_wave_fast(const RenderArgs &A, bool small, int blocks, cudaStream_t st);
+// persistent wavefront variant (`smem`: scene tables staged in shared memory, else read through L1)
+cudaError_t wave_occupancy_parity(const RenderArgs &A, bool small, bool smem, int *blocks_per_sm);
+cudaError_t wave_occupancy_fast(const RenderArgs &A, bool small, bool smem, int *blocks_per_sm);
+cudaError_t launch_wave_parity(const RenderArgs &A, bool small, bool smem, int blocks, cudaStream_t st);
+cudaError_t launch_wave_fast(const RenderArgs &A, bool small, bool smem, int blocks, cudaStream_t st);
 cudaError_t launch_texture_probe_parity(const TextureProbeArgs &A, cudaStream_t st);
 cudaError_t launch_texture_probe_fast(const TextureProbeArgs &A, cudaStream_t st);
 cudaError_t launch_philox_probe(const uint32_t ctr[4], const uint32_t key[2], uint32_t *d_out, cudaStream_t st);
