@@ -128,11 +128,16 @@ int main(int, char **) {
     return 3;
   }
   tpt_scene_desc desc = flat.desc();
-  tpt_scene *scene = nullptr;
-  if (tpt_scene_create(&desc, 0, &scene) != TPT_OK) {
-    std::cerr << "tpt_scene_create: " << tpt_last_error() << std::endl;
-    return 3;
+  if (gpus < 1) gpus = 1;
+  if (gpus > tpt_device_count()) gpus = tpt_device_count() > 0 ? tpt_device_count() : 1;
+  std::vector<tpt_scene *> scenes(gpus, nullptr); // the (tiny) scene is replicated on every GPU used
+  for (int g = 0; g < gpus; g++) {
+    if (tpt_scene_create(&desc, g, &scenes[g]) != TPT_OK) {
+      std::cerr << "tpt_scene_create: " << tpt_last_error() << std::endl;
+      return 3;
+    }
   }
+  tpt_scene *scene = scenes[0];
   tpt_camera cam_desc = tpt::make_camera_desc(cam);
   tpt_render_params rp{};
   rp.nx = nx;
@@ -148,13 +153,14 @@ int main(int, char **) {
   rp.part_index = 0;
   rp.part_count = 1;
   rp.device = 0;
-  rp.reserved[0] = gpus; // >1: in-process multi-GPU (static tile split + stealing)
   std::vector<uint8_t> rgb8((size_t)nx * ny * 3);
   std::vector<uint8_t> rgb8_slices(allow_bonus_pic ? (size_t)rp.slices * nx * ny * 3 : 0);
   tpt_image img{};
   img.rgb8 = rgb8.data();
   img.rgb8_slices = allow_bonus_pic ? rgb8_slices.data() : nullptr;
-  if (tpt_render(scene, &cam_desc, &rp, &img) != TPT_OK) {
+  // one GPU: tpt_render; several: static tile split + work stealing + NVLink gather
+  int rc = gpus > 1 ? tpt_render_multi(scenes.data(), gpus, &cam_desc, &rp, &img) : tpt_render(scene, &cam_desc, &rp, &img);
+  if (rc != TPT_OK) {
     std::cerr << "tpt_render: " << tpt_last_error() << std::endl;
     return 4;
   }
@@ -176,7 +182,7 @@ int main(int, char **) {
   std::cout << "time: "
             << std::chrono::duration_cast<std::chrono::milliseconds>(end - start).count() / 1000.0f
             << " s" << std::endl;
-  tpt_scene_destroy(scene);
+  for (tpt_scene *sc : scenes) tpt_scene_destroy(sc);
 #ifdef __linux__
   tpt::merge_with_convert(filenames);
 #endif
