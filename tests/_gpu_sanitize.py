@@ -1,0 +1,20 @@
+# scratch: tiny renders of every kernel variant for compute-sanitizer (memcheck / racecheck / initcheck)
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import numpy as np
+import tpt_b200 as T, common, raygen
+for scene, camf in (("cornell_box", T.cornell_camera), ("random_scene", T.book_camera), ("textured_lit", T.book_camera)):
+    hs = common.host_scene(T, scene, perlin=common.perlin_struct(T, common.golden("textures")),
+                           lights=common.TEXTURED_LIGHTS if scene == "textured_lit" else None)
+    sc = T.Scene(hs)
+    cam = camf(40, 24)
+    for mode in (T.MODE_PARITY, T.MODE_FAST):
+        for kern in (T.KERNEL_MEGA, T.KERNEL_WAVEFRONT):
+            r = sc.render(cam, T.make_params(40, 24, 4, 8, mode=mode, seed=1, kernel=kern, slices=2), want_slices=True)
+            print(scene, mode, kern, r.stats["paths"], float(r.sum_rgb.mean()))
+        sc.intersect(raygen.primary_batch(scene, 200, 200, seed=1), mode=mode)
+    sc.close()
+scs = [T.Scene(common.host_scene(T, "cornell_box"), device=0)]
+r = T.render_multi(scs, T.cornell_camera(40, 24), T.make_params(40, 24, 4, 8, kernel=T.KERNEL_WAVEFRONT))
+print("multi", r.stats["paths"])
