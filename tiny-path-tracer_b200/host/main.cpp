@@ -34,7 +34,7 @@ int main(int, char **) {
   float fov = 90.0f;
   int allow_bonus_pic = 0, bonus_pic = 10;
   std::string scene_name = "cornell_box", background = "black", image_file = "earthmap.jpg";
-  std::string mode = "fast", kernel = "mega";
+  std::string mode = "fast", kernel = "wavefront";
   unsigned long long seed = 0x5EEDULL;
   int gpus = 1;
 
