@@ -81,7 +81,11 @@ enum {
   TPT_PRIM_MOVING_SPHERE = 1, /* p = c0.xyz, radius, c1.xyz, time0, time1          (headers/sphere.h:36-39)  */
   TPT_PRIM_XY_RECT = 2,       /* p = x0,x1,y0,y1,k                                  (headers/rect_box.h:14)   */
   TPT_PRIM_XZ_RECT = 3,       /* p = x0,x1,z0,z1,k                                  (headers/rect_box.h:29)   */
-  TPT_PRIM_YZ_RECT = 4        /* p = y0,y1,z0,z1,k                                  (headers/rect_box.h:41)   */
+  TPT_PRIM_YZ_RECT = 4,       /* p = y0,y1,z0,z1,k                                  (headers/rect_box.h:41)   */
+  TPT_PRIM_MEDIUM = 5         /* constant_medium (headers/hitable.h:58-69): p[0] = density_, p[1], p[2] = the
+                                 boundary's node range [first, end) as int32 bit patterns; `material` = its
+                                 phase function. The boundary sub-tree lives BEHIND the root tree in `nodes`
+                                 (indices >= n_root_nodes) and is only reached through this primitive. */
 };
 enum { TPT_PRIM_FLIP = 1 }; /* odd number of flip_normal wrappers above the leaf */
 
@@ -98,7 +102,10 @@ enum {
   TPT_MAT_METAL = 1,         /* albedo, fuzz                  (headers/material.h:39-52) */
   TPT_MAT_DIELECTRIC = 2,    /* ref_idx                       (headers/material.h:53-59) */
   TPT_MAT_DIFFUSE_LIGHT = 3, /* texture                       (headers/material.h:61-72) */
-  TPT_MAT_ABSORBER = 4       /* base material / isotropic at HEAD: scatter()==false, emitted()==0 */
+  TPT_MAT_ABSORBER = 4,      /* base material: scatter()==false, emitted()==0 (headers/material.h:13-24) */
+  TPT_MAT_ISOTROPIC = 5      /* isotropic(texture) (headers/material.h:74-80). At the reference's HEAD its scatter()
+                                has a stale signature and never overrides material::scatter, so it behaves as an
+                                absorber; the texture is carried but not evaluated */
 };
 typedef struct tpt_material {
   int32_t kind;
@@ -162,7 +169,7 @@ typedef struct tpt_scene_desc {
   const tpt_perlin_tables *perlin; /* may be NULL when no PERLIN texture exists */
   const tpt_light *lights;
   int32_t background;
-  int32_t reserved;
+  int32_t n_root_nodes; /* nodes [0, n_root_nodes) are the world tree; 0 means n_nodes (no medium boundaries) */
 } tpt_scene_desc;
 
 /* public fields of camera_with_blur after its ctor ran on the host (headers/camera.h:14-20) */

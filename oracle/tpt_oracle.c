@@ -186,6 +186,40 @@ static int prim_hit(const tpt_scene_desc *d, int id, const ray_t *r, float t_min
   return ok;
 }
 
+static int node_hit(ctx_t *cx, int i, const ray_t *r_in, int from_nops, float t_min, float t_max, rec_t *rec);
+
+/* constant_medium::hit src/hitable.cc:98-128. `r` is the ray in the medium's own space; the
+ * boundary is the sub-tree stored at nodes [first, end) (its chains extend the medium's). */
+static int medium_hit(ctx_t *cx, int id, const ray_t *r, int from_nops, float t_min, float t_max, rec_t *rec) {
+  const tpt_prim *q = &cx->d->prims[id];
+  if (!cx->g) return 0; /* hit batches carry no stream */
+  int32_t first;
+  memcpy(&first, &q->p[1], 4);
+  rec_t rec1, rec2;
+  if (node_hit(cx, first, r, from_nops, -FLT_MAX, FLT_MAX, &rec1)) {
+    if (node_hit(cx, first, r, from_nops, (float)(rec1.t + 0.0001), FLT_MAX, &rec2)) {
+      if (rec1.t < t_min) rec1.t = t_min;
+      if (rec2.t > t_max) rec2.t = t_max;
+      if (rec1.t >= rec2.t) return 0;
+      float distance_inside_boundary = (rec2.t - rec1.t) * vlen(r->d);
+      float hit_distance = (float)((-1 / q->p[0]) * log(drand_r(cx->g)));
+      if (hit_distance < distance_inside_boundary) {
+        rec->t = rec1.t + hit_distance / vlen(r->d);
+        rec->p = point_at(r, rec->t);
+        float z = (float)drand_r(cx->g), y = (float)drand_r(cx->g), x = (float)drand_r(cx->g); /* right to left */
+        v3 n = V(x, y, z);
+        float k = (float)(1.0 / vlen(n)); /* vec3::make_unit_vector headers/vec3.h:95-100 */
+        rec->n = vscale(n, k);
+        rec->u = rec->v = 0;
+        rec->mat = q->material;
+        rec->prim = id;
+        return 1;
+      }
+    }
+  }
+  return 0;
+}
+
 /* the hitable at node i, seen from a ray expressed in the space of chain `from` */
 static int node_hit(ctx_t *cx, int i, const ray_t *r_in, int from_nops, float t_min, float t_max, rec_t *rec) {
   const tpt_scene_desc *d = cx->d;
@@ -212,7 +246,10 @@ static int node_hit(ctx_t *cx, int i, const ray_t *r_in, int from_nops, float t_
   int hit = 0;
   int kind = node_kind(nd);
   if (kind == TPT_NODE_LEAF) {
-    hit = prim_hit(d, nd->end_or_prim, &r, t_min, t_max, rec);
+    if (d->prims[nd->end_or_prim].kind == TPT_PRIM_MEDIUM)
+      hit = medium_hit(cx, nd->end_or_prim, &r, ch->n_ops, t_min, t_max, rec);
+    else
+      hit = prim_hit(d, nd->end_or_prim, &r, t_min, t_max, rec);
   } else if (kind == TPT_NODE_BVH) { /* src/hitable.cc:63-90 */
     if (aabb_hit(nd->bmin, nd->bmax, &r, t_min, t_max)) {
       int left = i + 1;

@@ -21,6 +21,7 @@ RENDER_CASES = {
     "light_spheres": dict(scene="light_spheres", cam=dict(BOOK_CAM, vfov=40.0), nx=40, ny=40, ns=8, depth=15, seed=4),
     "textured_lit": dict(scene="textured_lit", cam=dict(BOOK_CAM, vfov=50.0), nx=40, ny=40, ns=8, depth=15, seed=6,
                          lights=TEXTURED_LIGHTS),
+    "cornell_smoke": dict(scene="cornell_box_smoke", cam=dict(CORNELL_CAM, vfov=61.93), nx=40, ny=40, ns=8, depth=15, seed=12),
 }
 HIT_SCENES = ["cornell_box", "sphere_cornell_box", "random_scene", "random_scene_list", "two_perlin_spheres",
               "light_spheres", "earth", "textured_lit"]

@@ -59,6 +59,7 @@ def main():
         "light_spheres": dict(scene="light_spheres", cam=dict(O.BOOK_CAM, vfov=40.0), nx=40, ny=40, ns=8, depth=15, seed=4),
         "textured_lit": dict(scene="textured_lit", cam=dict(O.BOOK_CAM, vfov=50.0), nx=40, ny=40, ns=8, depth=15, seed=6,
                              lights=[(0, (-2.0, 2.0, -2.0, 2.0, 7.0)), (1, (-3.0, 6.0, 4.0, 2.0, 0.0))]),
+        "cornell_smoke": dict(scene="cornell_box_smoke", cam=dict(O.CORNELL_CAM, vfov=61.93), nx=40, ny=40, ns=8, depth=15, seed=12),
     }
     for name, c in cases.items():
         img = earth if c["scene"] in ("earth", "textured_lit") else None

@@ -42,6 +42,27 @@ def test_parity_radiance_vs_golden(T, gpu, case):
         assert res.sum_rgb.max() > 0
 
 
+def test_media_scene_fast_mode_and_hit_batch(T, gpu):
+    """cornell_box_smoke: fast mode tests the media after the surfaces (same distribution, other
+    stream positions), so it is compared statistically with parity mode; both kernel variants;
+    a deterministic hit batch does not exist for a scene whose hit() draws random numbers."""
+    hs = common.host_scene(T, "cornell_box_smoke")
+    sc = T.Scene(hs)
+    cam = common.product_camera(T, dict(common.CORNELL_CAM, vfov=61.93), 64, 64)
+    ref = sc.render(cam, T.make_params(64, 64, 256, 15, mode=T.MODE_PARITY, seed=1, kernel=T.KERNEL_MEGA)).sum_rgb[0] / 256
+    for kernel in (T.KERNEL_MEGA, T.KERNEL_WAVEFRONT):
+        par = sc.render(cam, T.make_params(64, 64, 64, 15, mode=T.MODE_PARITY, seed=7, kernel=kernel))
+        par0 = sc.render(cam, T.make_params(64, 64, 64, 15, mode=T.MODE_PARITY, seed=7, kernel=T.KERNEL_MEGA))
+        assert np.array_equal(par.sum_rgb, par0.sum_rgb)
+        fast = sc.render(cam, T.make_params(64, 64, 256, 15, mode=T.MODE_FAST, seed=2, kernel=kernel)).sum_rgb[0] / 256
+        assert abs(np.clip(fast, 0, 4).mean() - np.clip(ref, 0, 4).mean()) < 0.03 * np.clip(ref, 0, 4).mean()
+        d = np.sqrt(np.clip(fast, 0, 1)) - np.sqrt(np.clip(ref, 0, 1))
+        assert float(np.sqrt((d ** 2).mean())) < 0.06
+    with pytest.raises(T.TptError) as e:
+        sc.intersect(np.zeros((4, 7), np.float32))
+    assert e.value.code == -4
+
+
 @pytest.mark.parametrize("case", ["cornell_A", "cornell_B", "light_spheres", "textured_lit"])
 def test_fast_radiance_vs_golden(T, gpu, case):
     res, g, c = run_case(T, case, T.MODE_FAST)

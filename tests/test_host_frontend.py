@@ -97,9 +97,30 @@ def test_cornell_box_layout(T):
     assert sum(flips) == 3 + 3 + 3  # right wall, ceiling, lamp + three faces per box
 
 
-def test_constant_medium_is_rejected_not_approximated(T):
-    with pytest.raises(RuntimeError, match="constant_medium"):
-        T.HostScene("cornell_box_smoke")
+def test_constant_medium_flattening(T):
+    """cornell_box_smoke (src/utils.cc:321-357): three constant_medium objects become MEDIUM
+    primitives in the root list; their boundaries (two transformed boxes, one sphere) are kept
+    behind the root tree and are reachable only through them."""
+    import ctypes as C
+    hs = T.HostScene("cornell_box_smoke")
+    d = hs.desc.contents
+    assert d.n_root_nodes == 10 and d.n_nodes == 25
+    med = [i for i in range(d.n_prims) if d.prims[i].kind == 5]
+    assert len(med) == 3
+    dens = [np.float32(d.prims[i].p[0]) for i in med]
+    assert dens == [np.float32(0.05), np.float32(0.01), np.float32(0.0001)]
+    covered = []
+    for i in med:
+        first, end = (C.c_int32 * 2).from_buffer_copy(bytes(d.prims[i].p)[4:12])
+        assert d.n_root_nodes <= first < end <= d.n_nodes
+        covered += list(range(first, end))
+        assert d.materials[d.prims[i].material].kind == 5  # isotropic (an absorber at HEAD)
+    assert covered == list(range(d.n_root_nodes, d.n_nodes))
+    root_leaves = [d.nodes[i].end_or_prim for i in range(d.n_root_nodes) if (d.nodes[i].kind & 0xFF) == 2]
+    assert set(med) <= set(root_leaves)
+    for i in range(d.n_root_nodes, d.n_nodes):  # boundary primitives never appear in the root tree
+        if (d.nodes[i].kind & 0xFF) == 2:
+            assert d.nodes[i].end_or_prim not in root_leaves
 
 
 @pytest.mark.parametrize("args", [

@@ -100,7 +100,7 @@ class SceneDesc(C.Structure):
                 ("xform_ops", C.POINTER(XformOp)), ("materials", C.POINTER(Material)),
                 ("textures", C.POINTER(Texture)), ("images", C.POINTER(ImageDesc)),
                 ("perlin", C.POINTER(PerlinTables)), ("lights", C.POINTER(Light)),
-                ("background", C.c_int32), ("reserved", C.c_int32)]
+                ("background", C.c_int32), ("n_root_nodes", C.c_int32)]
 
 
 class Camera(C.Structure):

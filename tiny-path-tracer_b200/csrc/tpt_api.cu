@@ -126,6 +126,7 @@ struct tpt_scene {
   std::vector<cudaArray_t> arrays;
   std::vector<cudaTextureObject_t> textures;
   bool has_lights = false;
+  int n_mediums = 0;
   bool fbvh_has_moving = false; // the fast BVH boxes moving spheres over [fbvh_t0, fbvh_t1] only
   float fbvh_t0 = 0, fbvh_t1 = 0;
   // render products (device)
@@ -158,11 +159,14 @@ int validate_desc(const tpt_scene_desc *d, int &depth_out) {
   if (d->n_materials <= 0 || !d->materials) return fail(TPT_ERR_INVALID, "scene has no materials");
   if (d->n_images > TPT_MAX_IMAGES) return fail(TPT_ERR_UNSUPPORTED, "too many image textures");
   if (d->n_lights < 0 || (d->n_lights > 0 && !d->lights)) return fail(TPT_ERR_INVALID, "bad light list");
-  // structural walk: every group's end must nest properly
+  // structural walk: every group's end must nest properly (root tree, then medium boundaries)
+  const int n_root = d->n_root_nodes > 0 ? d->n_root_nodes : d->n_nodes;
+  if (n_root > d->n_nodes) return fail(TPT_ERR_INVALID, "n_root_nodes exceeds n_nodes");
   std::vector<int> ends;
   int depth = 0;
   for (int i = 0; i < d->n_nodes; i++) {
     while (!ends.empty() && ends.back() == i) ends.pop_back();
+    if (i == n_root && !ends.empty()) return fail(TPT_ERR_INVALID, "root tree does not close at n_root_nodes");
     const tpt_node &n = d->nodes[i];
     int k = n.kind & 0xff, chain = n.kind >> 16;
     if (chain < 0 || chain >= d->n_chains) return fail(TPT_ERR_INVALID, "node chain out of range");
@@ -181,7 +185,17 @@ int validate_desc(const tpt_scene_desc *d, int &depth_out) {
   depth_out = depth;
   for (int i = 0; i < d->n_prims; i++) {
     const tpt_prim &p = d->prims[i];
-    if (p.kind < TPT_PRIM_SPHERE || p.kind > TPT_PRIM_YZ_RECT) return fail(TPT_ERR_UNSUPPORTED, "unknown primitive kind");
+    if (p.kind < TPT_PRIM_SPHERE || p.kind > TPT_PRIM_MEDIUM) return fail(TPT_ERR_UNSUPPORTED, "unknown primitive kind");
+    if (p.kind == TPT_PRIM_MEDIUM) {
+      int32_t bf, be;
+      std::memcpy(&bf, &p.p[1], 4);
+      std::memcpy(&be, &p.p[2], 4);
+      if (bf < n_root || be <= bf || be > d->n_nodes) return fail(TPT_ERR_INVALID, "medium boundary range out of bounds");
+      if (!(p.p[0] > 0)) return fail(TPT_ERR_INVALID, "medium density must be positive");
+      for (int k = bf; k < be; k++)
+        if ((d->nodes[k].kind & 0xff) == TPT_NODE_LEAF && d->prims[d->nodes[k].end_or_prim].kind == TPT_PRIM_MEDIUM)
+          return fail(TPT_ERR_UNSUPPORTED, "medium inside a medium boundary");
+    }
     if (p.material < 0 || p.material >= d->n_materials) return fail(TPT_ERR_INVALID, "prim material out of range");
     if (p.chain < 0 || p.chain >= d->n_chains) return fail(TPT_ERR_INVALID, "prim chain out of range");
   }
@@ -203,7 +217,7 @@ int validate_desc(const tpt_scene_desc *d, int &depth_out) {
   if (needs_perlin && !d->perlin) return fail(TPT_ERR_INVALID, "perlin texture without tables");
   for (int i = 0; i < d->n_materials; i++) {
     const tpt_material &m = d->materials[i];
-    if (m.kind < TPT_MAT_LAMBERTIAN || m.kind > TPT_MAT_ABSORBER) return fail(TPT_ERR_UNSUPPORTED, "unknown material kind");
+    if (m.kind < TPT_MAT_LAMBERTIAN || m.kind > TPT_MAT_ISOTROPIC) return fail(TPT_ERR_UNSUPPORTED, "unknown material kind");
     if ((m.kind == TPT_MAT_LAMBERTIAN || m.kind == TPT_MAT_DIFFUSE_LIGHT) && (m.texture < 0 || m.texture >= d->n_textures))
       return fail(TPT_ERR_INVALID, "material texture out of range");
   }
@@ -360,11 +374,12 @@ int32_t build_fbvh_rec(std::vector<BuildItem> &items, int begin, int end, FastBv
   return me;
 }
 
-void build_fast_bvh(const tpt_scene_desc *d, FastBvh &out) {
-  std::vector<BuildItem> items;
+// surface primitives reachable from the root tree (media and their boundaries excluded)
+std::vector<int> root_surface_prims(const tpt_scene_desc *d, int n_root) {
+  std::vector<int> ids;
   std::vector<char> seen(d->n_prims, 0);
   int skip_until = -1;
-  for (int i = 0; i < d->n_nodes; i++) {
+  for (int i = 0; i < n_root; i++) {
     const tpt_node &nd = d->nodes[i];
     int k = nd.kind & 0xff;
     if (i < skip_until) continue;
@@ -372,7 +387,27 @@ void build_fast_bvh(const tpt_scene_desc *d, FastBvh &out) {
       if (k != TPT_NODE_LEAF) skip_until = nd.end_or_prim;
       continue;
     }
-    if (k != TPT_NODE_LEAF || seen[nd.end_or_prim]) continue;
+    if (k != TPT_NODE_LEAF || seen[nd.end_or_prim] || d->prims[nd.end_or_prim].kind == TPT_PRIM_MEDIUM) continue;
+    seen[nd.end_or_prim] = 1;
+    ids.push_back(nd.end_or_prim);
+  }
+  return ids;
+}
+int count_root_surface_prims(const tpt_scene_desc *d, int n_root) { return (int)root_surface_prims(d, n_root).size(); }
+
+void build_fast_bvh(const tpt_scene_desc *d, int n_root, FastBvh &out) {
+  std::vector<BuildItem> items;
+  std::vector<char> seen(d->n_prims, 0);
+  int skip_until = -1;
+  for (int i = 0; i < n_root; i++) {
+    const tpt_node &nd = d->nodes[i];
+    int k = nd.kind & 0xff;
+    if (i < skip_until) continue;
+    if (nd.kind & TPT_NODE_DUP) {
+      if (k != TPT_NODE_LEAF) skip_until = nd.end_or_prim;
+      continue;
+    }
+    if (k != TPT_NODE_LEAF || seen[nd.end_or_prim] || d->prims[nd.end_or_prim].kind == TPT_PRIM_MEDIUM) continue;
     seen[nd.end_or_prim] = 1;
     BuildItem it;
     it.box = world_box(d, nd);
@@ -394,13 +429,16 @@ void build_fast_bvh(const tpt_scene_desc *d, FastBvh &out) {
 // Group the non-duplicate leaves by transform chain and primitive kind (xy, xz, yz rect, sphere).
 // Closest-hit does not depend on the order except on exact ties, which FAST mode does not
 // promise to resolve like the reference.
-void build_small_scene(const tpt_scene_desc *d, bool smem_ok, SmallScene &Q) {
+void build_small_scene(const tpt_scene_desc *d, int n_root, bool smem_ok, SmallScene &Q) {
   std::memset(&Q, 0, sizeof(Q));
-  if (!smem_ok || d->n_prims > TPT_SMALL_MAX_PRIMS || d->n_chains > TPT_SMALL_MAX_GROUPS ||
+  const std::vector<int> surface = root_surface_prims(d, n_root);
+  std::vector<char> is_surface(d->n_prims, 0);
+  for (int id : surface) is_surface[id] = 1;
+  if (!smem_ok || (int)surface.size() > TPT_SMALL_MAX_PRIMS || d->n_chains > TPT_SMALL_MAX_GROUPS ||
       d->n_xform_ops > TPT_SMALL_MAX_OPS)
     return;
-  for (int i = 0; i < d->n_prims; i++)
-    if (d->prims[i].kind == TPT_PRIM_MOVING_SPHERE) return;
+  for (int id : surface)
+    if (d->prims[id].kind == TPT_PRIM_MOVING_SPHERE) return;
   for (int i = 0; i < d->n_xform_ops; i++) {
     const tpt_xform_op &op = d->xform_ops[i];
     int32_t kind = op.kind;
@@ -412,7 +450,7 @@ void build_small_scene(const tpt_scene_desc *d, bool smem_ok, SmallScene &Q) {
   // exactly the faces of an axis-aligned block (src/rect_box.cc:93-115) ----
   std::vector<int> in_box(d->n_prims, -1);
   int nb = 0;
-  for (int i = 0; i < d->n_nodes && nb < TPT_SMALL_MAX_BOXES; i++) {
+  for (int i = 0; i < n_root && nb < TPT_SMALL_MAX_BOXES; i++) {
     const tpt_node &g = d->nodes[i];
     if ((g.kind & 0xff) != TPT_NODE_LIST || (g.kind & TPT_NODE_DUP) || g.end_or_prim - i - 1 != 6) continue;
     int ids[6];
@@ -500,7 +538,7 @@ void build_small_scene(const tpt_scene_desc *d, bool smem_ok, SmallScene &Q) {
     for (int o = 0; o < 4; o++) {
       for (int i = 0; i < d->n_prims; i++) {
         const tpt_prim &p = d->prims[i];
-        if (p.chain != c || p.kind != order[o] || in_box[i] >= 0) continue;
+        if (!is_surface[i] || p.chain != c || p.kind != order[o] || in_box[i] >= 0) continue;
         int32_t id = i;
         float idf;
         std::memcpy(&idf, &id, 4);
@@ -678,12 +716,13 @@ int run_plan(tpt_scene *s, Plan &plan, bool want_sum, bool want_rgb8, bool want_
 
   size_t smem = s->use_smem ? s->blob_bytes : 0;
   int bps = 0;
-  const bool small = s->small.enabled != 0;
+  const bool media = s->n_mediums > 0;
+  const bool small = s->small.enabled != 0 && !media;
   if (plan.wavefront)
-    CK(plan.parity ? wave_occupancy_parity(A, small, s->use_smem, &bps) : wave_occupancy_fast(A, small, s->use_smem, &bps));
+    CK(plan.parity ? wave_occupancy_parity(A, small, s->use_smem, media, &bps) : wave_occupancy_fast(A, small, s->use_smem, media, &bps));
   else
-    CK(plan.parity ? mega_occupancy_parity(s->use_smem, small, smem, &bps)
-                   : mega_occupancy_fast(s->use_smem, small, smem, &bps));
+    CK(plan.parity ? mega_occupancy_parity(s->use_smem, small, media, smem, &bps)
+                   : mega_occupancy_fast(s->use_smem, small, media, smem, &bps));
   if (bps < 1) return fail(TPT_ERR_CUDA, "render kernel does not fit on an SM");
   plan.blocks_per_sm = bps;
   plan.blocks = bps * s->prop.multiProcessorCount;
@@ -691,10 +730,10 @@ int run_plan(tpt_scene *s, Plan &plan, bool want_sum, bool want_rgb8, bool want_
   CK(cudaMemsetAsync(s->d_counters, 0, 8 * sizeof(unsigned long long), s->stream));
   CK(cudaEventRecord(s->ev[0], s->stream));
   if (plan.wavefront)
-    CK(plan.parity ? launch_wave_parity(A, small, s->use_smem, plan.blocks, s->stream) : launch_wave_fast(A, small, s->use_smem, plan.blocks, s->stream));
+    CK(plan.parity ? launch_wave_parity(A, small, s->use_smem, media, plan.blocks, s->stream) : launch_wave_fast(A, small, s->use_smem, media, plan.blocks, s->stream));
   else
-    CK(plan.parity ? launch_mega_parity(A, s->use_smem, small, plan.blocks, s->stream)
-                   : launch_mega_fast(A, s->use_smem, small, plan.blocks, s->stream));
+    CK(plan.parity ? launch_mega_parity(A, s->use_smem, small, media, plan.blocks, s->stream)
+                   : launch_mega_fast(A, s->use_smem, small, media, plan.blocks, s->stream));
   CK(cudaEventRecord(s->ev[1], s->stream));
   int rb = (int)((plan.npix + 255) / 256);
   resolve_kernel<<<rb, 256, 0, s->stream>>>(R);
@@ -810,19 +849,20 @@ int launch_batch(tpt_scene *s, const tpt_camera *cam, const tpt_render_params *p
   A.counters = s->d_counters + (size_t)batch * 8;
   size_t smem = s->use_smem ? s->blob_bytes : 0;
   int bps = 0;
-  const bool small = s->small.enabled != 0;
+  const bool media = s->n_mediums > 0;
+  const bool small = s->small.enabled != 0 && !media;
   if (plan.wavefront)
-    CK(plan.parity ? wave_occupancy_parity(A, small, s->use_smem, &bps) : wave_occupancy_fast(A, small, s->use_smem, &bps));
+    CK(plan.parity ? wave_occupancy_parity(A, small, s->use_smem, media, &bps) : wave_occupancy_fast(A, small, s->use_smem, media, &bps));
   else
-    CK(plan.parity ? mega_occupancy_parity(s->use_smem, small, smem, &bps)
-                   : mega_occupancy_fast(s->use_smem, small, smem, &bps));
+    CK(plan.parity ? mega_occupancy_parity(s->use_smem, small, media, smem, &bps)
+                   : mega_occupancy_fast(s->use_smem, small, media, smem, &bps));
   if (bps < 1) return fail(TPT_ERR_CUDA, "render kernel does not fit on an SM");
   int blocks = bps * s->prop.multiProcessorCount;
   if (plan.wavefront)
-    CK(plan.parity ? launch_wave_parity(A, small, s->use_smem, blocks, s->stream) : launch_wave_fast(A, small, s->use_smem, blocks, s->stream));
+    CK(plan.parity ? launch_wave_parity(A, small, s->use_smem, media, blocks, s->stream) : launch_wave_fast(A, small, s->use_smem, media, blocks, s->stream));
   else
-    CK(plan.parity ? launch_mega_parity(A, s->use_smem, small, blocks, s->stream)
-                   : launch_mega_fast(A, s->use_smem, small, blocks, s->stream));
+    CK(plan.parity ? launch_mega_parity(A, s->use_smem, small, media, blocks, s->stream)
+                   : launch_mega_fast(A, s->use_smem, small, media, blocks, s->stream));
   s->stats.blocks = blocks;
   return TPT_OK;
 }
@@ -1061,8 +1101,20 @@ int tpt_scene_create(const tpt_scene_desc *d, int device, tpt_scene **out) {
     append(blob, d->perlin->perm_y, 256);
     append(blob, d->perlin->perm_z, 256);
   }
+  const int n_root = d->n_root_nodes > 0 ? d->n_root_nodes : d->n_nodes;
+  std::vector<int32_t> mediums; // MEDIUM primitives in DFS order of the root tree
+  for (int i = 0; i < n_root; i++) {
+    const tpt_node &nd = d->nodes[i];
+    if ((nd.kind & 0xff) == TPT_NODE_LEAF && !(nd.kind & TPT_NODE_DUP) && d->prims[nd.end_or_prim].kind == TPT_PRIM_MEDIUM &&
+        std::find(mediums.begin(), mediums.end(), nd.end_or_prim) == mediums.end())
+      mediums.push_back(nd.end_or_prim);
+  }
+  L.off_mediums = words();
+  append(blob, mediums.data(), mediums.size());
+  L.n_mediums = (int)mediums.size();
+  s->n_mediums = L.n_mediums;
   FastBvh fb;
-  if (d->n_prims > TPT_SMALL_MAX_PRIMS) build_fast_bvh(d, fb);
+  if (count_root_surface_prims(d, n_root) > TPT_SMALL_MAX_PRIMS) build_fast_bvh(d, n_root, fb);
   L.off_fbvh = words();
   append(blob, fb.nodes.data(), fb.nodes.size());
   L.off_fleaf = words();
@@ -1073,7 +1125,7 @@ int tpt_scene_create(const tpt_scene_desc *d, int device, tpt_scene **out) {
   s->fbvh_t0 = fb.moving_t0;
   s->fbvh_t1 = fb.moving_t1;
   L.blob_words = words();
-  L.n_nodes = d->n_nodes;
+  L.n_nodes = n_root; // world->hit walks the root tree only; boundaries are reached through their medium
   L.n_prims = d->n_prims;
   L.n_lights = d->n_lights;
   L.background = d->background;
@@ -1084,7 +1136,7 @@ int tpt_scene_create(const tpt_scene_desc *d, int device, tpt_scene **out) {
   CK(cudaStreamSynchronize(s->stream));
   L.blob_global = s->d_blob;
   s->use_smem = blob.size() <= 64 * 1024;
-  build_small_scene(d, s->use_smem, s->small);
+  build_small_scene(d, n_root, s->use_smem, s->small);
 
   // ---- image textures: RGB -> RGBA8 cudaArray, point sampling, clamp, unnormalised coords ----
   for (int i = 0; i < d->n_images; i++) {
@@ -1145,6 +1197,8 @@ int tpt_intersect_batch(const tpt_scene *cs, const tpt_ray *rays, size_t n, floa
   if (!s || (!rays && n) || (!out && n)) return fail(TPT_ERR_INVALID, "null argument");
   if (mode != TPT_MODE_PARITY && mode != TPT_MODE_FAST) return fail(TPT_ERR_INVALID, "unknown mode");
   if (n == 0) return TPT_OK;
+  if (s->n_mediums > 0)
+    return fail(TPT_ERR_UNSUPPORTED, "constant_medium::hit draws random numbers: a scene with media has no deterministic hit batch");
   static_assert(sizeof(tpt_ray) == 28, "tpt_ray layout");
   CK(cudaSetDevice(s->device));
   float *d_rays = nullptr;

@@ -22,6 +22,7 @@ namespace tptd {
 
 #define TPT_DEV __device__ __forceinline__
 #define TPT_MAX_FRAMES 32
+#define TPT_MAX_BOUNDARY_FRAMES 8 // nesting inside a constant_medium boundary (sphere / box / small list)
 #define TPT_MAX_IMAGES 8
 #define TPT_MAX_RANGES 256
 
@@ -33,6 +34,7 @@ struct SceneLayout { // host-computed, lives in kernel parameter (constant) spac
   const float4 *blob_global;
   int blob_words; // float4 count
   int off_nodes, off_prims, off_chains, off_ops, off_mats, off_texs, off_lights, off_perlin;
+  int off_mediums, n_mediums; // MEDIUM primitive ids in DFS order (int list); boundaries live behind n_nodes
   int off_fbvh, off_fleaf, n_fbvh, fbvh_time_ok; // FAST-mode SAH BVH over world-space leaf boxes (0 nodes = none)
   int n_nodes, n_prims, n_lights, background;
   cudaTextureObject_t images[TPT_MAX_IMAGES];
@@ -143,6 +145,7 @@ static __device__ __noinline__ uint4 philox_block_slow(uint32_t c0, uint32_t c1,
 
 struct Rng {
   uint32_t k0, k1, pixel, sample, stage, ndraw;
+  uint32_t fresh; // draw index whose block is already loaded (set_stage: 0, set_stage_at(n): n & ~3)
   uint32_t b0, b1, b2, b3;
   TPT_DEV void begin(uint32_t seed_lo, uint32_t seed_hi, uint32_t pix, uint32_t smp) {
     k0 = seed_lo;
@@ -151,6 +154,7 @@ struct Rng {
     sample = smp;
     stage = 0;
     ndraw = 0;
+    fresh = 0;
   }
   // Start a stage and generate its first block right away: camera (u, v, lens y, lens x),
   // lambertian (mixture pick, light index, 2 coordinates), dielectric (1) and the first round of
@@ -160,8 +164,22 @@ struct Rng {
   TPT_DEV void set_stage(uint32_t s) {
     stage = s;
     ndraw = 0;
+    fresh = 0;
     uint32_t o[4];
     philox4x32_10(pixel, sample, stage, 0u, k0, k1, o);
+    b0 = o[0];
+    b1 = o[1];
+    b2 = o[2];
+    b3 = o[3];
+  }
+  // resume a stage after `n` draws were already consumed (constant_medium::hit draws inside
+  // world->hit, before the material's own draws of the same stage)
+  TPT_DEV void set_stage_at(uint32_t s, uint32_t n) {
+    stage = s;
+    ndraw = n;
+    fresh = n & ~3u;
+    uint32_t o[4];
+    philox4x32_10(pixel, sample, stage, n >> 2, k0, k1, o);
     b0 = o[0];
     b1 = o[1];
     b2 = o[2];
@@ -177,7 +195,7 @@ struct Rng {
   // next uniform in [0,1): (x >> 8) * 2^-24, exactly representable in fp32
   TPT_DEV float next() {
     uint32_t lane = ndraw & 3u;
-    if (lane == 0 && ndraw != 0) refill();
+    if (lane == 0 && ndraw != fresh) refill();
     uint32_t x = lane == 0 ? b0 : (lane == 1 ? b1 : (lane == 2 ? b2 : b3));
     ndraw++;
     return (float)(x >> 8) * 5.9604644775390625e-8f;
@@ -376,6 +394,7 @@ TPT_DEV bool prim_test(const SceneView &S, int prim, const XRay &x, float time, 
   const float4 *P = S.blob + S.L->off_prims + 4 * prim;
   float4 h = P[0], a = P[1];
   int kind = __float_as_int(h.x);
+  if (kind > TPT_PRIM_YZ_RECT) return false; // MEDIUM: handled by medium_test where a stream exists
   if (kind == TPT_PRIM_SPHERE) {
     return sphere_test<PAR>(mk(a.x, a.y, a.z), a.w, x, tmin, tmax, t);
   } else if (kind == TPT_PRIM_MOVING_SPHERE) {
@@ -403,21 +422,69 @@ struct Frame {
   int best_prim, end_list; // end index | (is_list << 31)
 };
 
+template <bool PAR, bool MED>
+TPT_DEV bool walk_range(const SceneView &S, const Ray &r, int first, int end_all, float tmin, float tmax, float &t_out,
+                        int &prim_out, Rng *g);
+
+// constant_medium::hit (src/hitable.cc:98-128). `x` is the ray in the medium's own space, the
+// boundary sub-tree [bf, be) is walked from the world ray (its nodes carry absolute chains; t is
+// the same in every space). Draws: one for the free-flight distance, three for the "arbitrary"
+// normal -- consumed inside world->hit, i.e. before the material's draws of the same stage.
 template <bool PAR>
-TPT_DEV bool closest_hit(const SceneView &S, const Ray &r, float tmin, float tmax, float &t_out,
-                         int &prim_out) {
+TPT_DEV bool medium_test(const SceneView &S, int prim, const XRay &x, const Ray &r, float tmin, float tmax, float &t,
+                         Rng *g) {
+  if (!g) return false; // closest-hit batches have no stream: media are refused by the API
+  const float4 *P = S.blob + S.L->off_prims + 4 * prim;
+  const float4 a = P[1];
+  const float density = a.x;
+  const int bf = __float_as_int(a.y), be = __float_as_int(a.z);
+  float t1, t2;
+  int dummy;
+  if (!walk_range<PAR, false>(S, r, bf, be, -FLT_MAX, FLT_MAX, t1, dummy, nullptr)) return false;
+  const float tmin2 = PAR ? (float)((double)t1 + 0.0001) : t1 + 0.0001f;
+  if (!walk_range<PAR, false>(S, r, bf, be, tmin2, FLT_MAX, t2, dummy, nullptr)) return false;
+  if (t1 < tmin) t1 = tmin;
+  if (t2 > tmax) t2 = tmax;
+  if (t1 >= t2) return false;
+  const float len = length(x.d);
+  const float inside = (t2 - t1) * len;
+  const float u = g->next();
+  // (-1 / density_) * std::log(drand_r()): float * double -> float
+  const float hit_distance = PAR ? (float)((double)(-1 / density) * log((double)u)) : (-1.0f / density) * __logf(u);
+  if (hit_distance < inside) {
+    t = t1 + hit_distance / len;
+    g->next(); // rec.normal = vec3(drand_r(), drand_r(), drand_r()): never used (isotropic is an
+    g->next(); // absorber at HEAD) but the stream advances
+    g->next();
+    return true;
+  }
+  return false;
+}
+
+template <bool PAR, bool MED>
+TPT_DEV bool any_prim_test(const SceneView &S, int prim, const XRay &x, const Ray &r, float tmin, float tmax, float &t,
+                           Rng *g) {
+  if (MED && __float_as_int(S.blob[S.L->off_prims + 4 * prim].x) == TPT_PRIM_MEDIUM)
+    return medium_test<PAR>(S, prim, x, r, tmin, tmax, t, g);
+  return prim_test<PAR>(S, prim, x, r.time, tmin, tmax, t);
+}
+
+// hit() of the sub-tree stored at nodes [first, end_all)
+template <bool PAR, bool MED>
+TPT_DEV bool walk_range(const SceneView &S, const Ray &r, int first, int end_all, float tmin, float tmax, float &t_out,
+                        int &prim_out, Rng *g) {
   XRay x;
   x.chain = -1;
   const float4 *N = S.blob + S.L->off_nodes;
-  const int n = S.L->n_nodes;
+  const int n = end_all;
   if (PAR) {
-    Frame fr[TPT_MAX_FRAMES];
+    Frame fr[MED ? TPT_MAX_FRAMES : TPT_MAX_BOUNDARY_FRAMES];
     int sp = 1;
     fr[0].tmax_in = tmax;
     fr[0].best_t = 0.f;
     fr[0].best_prim = -1;
     fr[0].end_list = n | (int)0x80000000;
-    int i = 0;
+    int i = first;
     for (;;) {
       // close finished groups, handing their result to the parent
       while (sp > 1 && i == (fr[sp - 1].end_list & 0x7fffffff)) {
@@ -442,7 +509,7 @@ TPT_DEV bool closest_hit(const SceneView &S, const Ray &r, float tmin, float tma
       if (k == TPT_NODE_LEAF) {
         float t;
         int prim = __float_as_int(n1.w);
-        if (prim_test<PAR>(S, prim, x, r.time, tmin, ctx, t)) {
+        if (any_prim_test<PAR, MED>(S, prim, x, r, tmin, ctx, t, g)) {
           bool take = (P.end_list < 0) || (P.best_prim < 0) || !(P.best_t < t);
           if (take) {
             P.best_t = t;
@@ -470,7 +537,7 @@ TPT_DEV bool closest_hit(const SceneView &S, const Ray &r, float tmin, float tma
   } else {
     float best = tmax;
     int best_prim = -1;
-    int i = 0;
+    int i = first;
     while (i < n) {
       float4 n0 = N[2 * i], n1 = N[2 * i + 1];
       int kind = __float_as_int(n0.w);
@@ -483,7 +550,7 @@ TPT_DEV bool closest_hit(const SceneView &S, const Ray &r, float tmin, float tma
       to_chain<PAR>(S, r, kind >> 16, x);
       if (k == TPT_NODE_LEAF) {
         float t;
-        if (prim_test<PAR>(S, payload, x, r.time, tmin, best, t)) {
+        if (any_prim_test<PAR, MED>(S, payload, x, r, tmin, best, t, g)) {
           best = t;
           best_prim = payload;
         }
@@ -495,6 +562,31 @@ TPT_DEV bool closest_hit(const SceneView &S, const Ray &r, float tmin, float tma
     t_out = best;
     prim_out = best_prim;
     return best_prim >= 0;
+  }
+}
+
+// world->hit: the root tree is nodes [0, n_nodes)
+template <bool PAR>
+TPT_DEV bool closest_hit(const SceneView &S, const Ray &r, float tmin, float tmax, float &t_out, int &prim_out,
+                         Rng *g = nullptr) {
+  return walk_range<PAR, true>(S, r, 0, S.L->n_nodes, tmin, tmax, t_out, prim_out, g);
+}
+
+// FAST mode: media are tested after the surfaces, in their DFS order, against the closest surface
+// found (statistically identical to the reference's list order: a free-flight distance beyond a
+// closer surface loses to it either way)
+TPT_DEV void fast_media_pass(const SceneView &S, const Ray &r, float tmin, float &best, int &best_prim, Rng *g) {
+  const int *ids = reinterpret_cast<const int *>(S.blob + S.L->off_mediums);
+  XRay x;
+  x.chain = -1;
+  for (int m = 0; m < S.L->n_mediums; m++) {
+    const int prim = ids[m];
+    to_chain<false>(S, r, __float_as_int(S.blob[S.L->off_prims + 4 * prim].z), x);
+    float t;
+    if (medium_test<false>(S, prim, x, r, tmin, best, t, g)) {
+      best = t;
+      best_prim = prim;
+    }
   }
 }
 
@@ -1052,13 +1144,35 @@ TPT_DEV bool dead_channel(float t) { return t == 0.0f || isnan(t); }
 // (src/utils.cc:61-66,82-86). Returns TPT_EXT_DONE with the sample's radiance, or the kind of the
 // scattering material (LAMBERTIAN / METAL / DIELECTRIC) with (prim, t) of the hit.
 #define TPT_EXT_DONE (-1)
-template <bool PAR, bool SMALL>
+// MEDIA is a compile-time switch: only kernels instantiated for scenes with participating media
+// carry the stream through world->hit (taking the Rng's address costs registers everywhere else).
+template <bool PAR, bool SMALL, bool MEDIA>
 TPT_DEV int extend(const SceneView &S, const PathState &ps, int max_depth, float t_min, float &t, int &prim,
-                   V3 &radiance) {
+                   V3 &radiance, Rng &g, uint32_t &ndraw_out) {
+  // scenes with participating media draw inside world->hit: the stage's stream starts here
+  const bool media = MEDIA;
+  Rng *gp = nullptr;
+  if (MEDIA) {
+    g.set_stage((uint32_t)ps.depth + 1u);
+    gp = &g;
+  }
   bool any_hit;
-  if (SMALL && !PAR) any_hit = closest_hit_uniform(S, ps.ray, t_min, FLT_MAX, t, prim);
-  else if (!PAR && S.L->n_fbvh > 0 && S.L->fbvh_time_ok) any_hit = closest_hit_fbvh(S, ps.ray, t_min, FLT_MAX, t, prim);
-  else any_hit = closest_hit<PAR>(S, ps.ray, t_min, FLT_MAX, t, prim);
+  if (PAR) {
+    any_hit = closest_hit<PAR>(S, ps.ray, t_min, FLT_MAX, t, prim, gp);
+  } else {
+    if (SMALL) any_hit = closest_hit_uniform(S, ps.ray, t_min, FLT_MAX, t, prim);
+    else if (S.L->n_fbvh > 0 && S.L->fbvh_time_ok) any_hit = closest_hit_fbvh(S, ps.ray, t_min, FLT_MAX, t, prim);
+    else any_hit = walk_range<false, false>(S, ps.ray, 0, S.L->n_nodes, t_min, FLT_MAX, t, prim, nullptr);
+    if (media) {
+      if (!any_hit) {
+        t = FLT_MAX;
+        prim = -1;
+      }
+      fast_media_pass(S, ps.ray, t_min, t, prim, gp);
+      any_hit = prim >= 0;
+    }
+  }
+  ndraw_out = media ? g.ndraw : 0u;
   radiance = mk(0, 0, 0);
   if (!any_hit) {
     if (S.L->background == TPT_BG_SKY) {
@@ -1082,14 +1196,17 @@ TPT_DEV int extend(const SceneView &S, const PathState &ps, int max_depth, float
     if (dot(h.n, ps.ray.d) < 0) radiance = ps.T * texture_value<PAR>(S, mtex, h.u, h.v, h.p);
     return TPT_EXT_DONE;
   }
-  if (mkind == TPT_MAT_ABSORBER || ps.depth >= max_depth) return TPT_EXT_DONE; // emitted == 0
+  if (mkind == TPT_MAT_ABSORBER || mkind == TPT_MAT_ISOTROPIC || ps.depth >= max_depth) return TPT_EXT_DONE; // emitted == 0
   return mkind;
 }
 
 // shade(): material::scatter + the mixture-pdf step of color() for the hit (prim, t).
 // Returns true while the path continues (ps holds the next ray, throughput, depth).
-template <bool PAR> TPT_DEV bool shade(const SceneView &S, PathState &ps, Rng &g, int prim, float t) {
-  g.set_stage((uint32_t)ps.depth + 1u); // stage d+1 = the draws color() makes at depth d
+template <bool PAR> TPT_DEV bool shade(const SceneView &S, PathState &ps, Rng &g, int prim, float t, uint32_t ndraw0) {
+  // stage d+1 = the draws color() makes at depth d; ndraw0 of them were already taken inside
+  // world->hit by participating media (0 in scenes without any)
+  if (ndraw0 == 0u) g.set_stage((uint32_t)ps.depth + 1u);
+  else g.set_stage_at((uint32_t)ps.depth + 1u, ndraw0);
   const int mat = __float_as_int(S.blob[S.L->off_prims + 4 * prim].y);
   const float4 m0 = S.blob[S.L->off_mats + 2 * mat];
   const float4 m1 = S.blob[S.L->off_mats + 2 * mat + 1];
@@ -1163,13 +1280,14 @@ template <bool PAR> TPT_DEV bool shade(const SceneView &S, PathState &ps, Rng &g
 }
 
 // one bounce = extend + shade (megakernel form)
-template <bool PAR, bool SMALL>
+template <bool PAR, bool SMALL, bool MEDIA>
 TPT_DEV bool bounce(const SceneView &S, PathState &ps, Rng &g, int max_depth, float t_min, V3 &radiance) {
   float t;
   int prim;
-  int cls = extend<PAR, SMALL>(S, ps, max_depth, t_min, t, prim, radiance);
+  uint32_t ndraw0;
+  int cls = extend<PAR, SMALL, MEDIA>(S, ps, max_depth, t_min, t, prim, radiance, g, ndraw0);
   if (cls == TPT_EXT_DONE) return false;
-  return shade<PAR>(S, ps, g, prim, t);
+  return shade<PAR>(S, ps, g, prim, t, ndraw0);
 }
 
 } // namespace tptd

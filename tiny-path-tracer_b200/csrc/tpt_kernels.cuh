@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(128) intersect_kernel(const __grid_constant__ 
   bool any_hit;
   if (SMALL && !PAR) any_hit = closest_hit_uniform(S, r, A.tmin, A.tmax, t, prim);
   else if (!PAR && A.scene.n_fbvh > 0) any_hit = closest_hit_fbvh(S, r, A.tmin, A.tmax, t, prim);
-  else any_hit = closest_hit<PAR>(S, r, A.tmin, A.tmax, t, prim);
+  else any_hit = closest_hit<PAR>(S, r, A.tmin, A.tmax, t, prim, nullptr);
   if (any_hit) {
     HitRec h;
     fill_hit<PAR>(S, r, prim, t, true, h);
@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(128) intersect_kernel(const __grid_constant__ 
 // Bins are ordered tile-major with the pixel index fastest: the 32 lanes of a warp work on 32
 // neighbouring pixels of one tile.
 // ------------------------------------------------------------------------------------------
-template <bool PAR, bool SMEM, bool SMALL>
+template <bool PAR, bool SMEM, bool SMALL, bool MEDIA>
 __global__ void __launch_bounds__(TPT_MEGA_THREADS) render_mega_kernel(const __grid_constant__ RenderArgs A) {
   extern __shared__ float4 sblob[];
   SceneView S;
@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(TPT_MEGA_THREADS) render_mega_kernel(const __g
     if (active) {
       V3 rad;
       n_rays++;
-      if (!bounce<PAR, SMALL>(S, ps, rng, A.max_depth, A.t_min, rad)) {
+      if (!bounce<PAR, SMALL, MEDIA>(S, ps, rng, A.max_depth, A.t_min, rad)) {
         // col += de_nan(tmp): main.cpp:126, headers/utils.h:100-109
         bool nan_any = isnan(rad.x) || isnan(rad.y) || isnan(rad.z) || isnan(ps.T.x) ||
                        isnan(ps.T.y) || isnan(ps.T.z);
@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(TPT_MEGA_THREADS) render_mega_kernel(const __g
 // ------------------------------------------------------------------------------------------
 #define TPT_WAVE_NQ 4 // queues: 0 lambertian, 1 metal, 2 dielectric (= TPT_MAT_*), 3 generate
 
-template <bool PAR, bool SMALL, bool SMEM>
+template <bool PAR, bool SMALL, bool SMEM, bool MEDIA>
 __global__ void __launch_bounds__(TPT_WAVE_THREADS, TPT_WAVE_MIN_BLOCKS) render_wave_kernel(const __grid_constant__ RenderArgs A) {
   extern __shared__ float4 sblob[];
   SceneView S;
@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(TPT_WAVE_THREADS, TPT_WAVE_MIN_BLOCKS) render_
   int *si = reinterpret_cast<int *>(sf);
   // structure-of-arrays slot state: field f of slot s at sf[f * NSLOT + s]
   enum { F_OX, F_OY, F_OZ, F_DX, F_DY, F_DZ, F_TIME, F_TX, F_TY, F_TZ, F_AX, F_AY, F_AZ,
-         F_PIXEL, F_K, F_KEND, F_ACCIDX, F_DEPTH, F_HPRIM, F_HT, F_ACTIVE, F_COUNT };
+         F_PIXEL, F_K, F_KEND, F_ACCIDX, F_DEPTH, F_HPRIM, F_HT, F_ACTIVE, F_NDRAW, F_COUNT };
   // queue[parity][q][NSLOT] slot ids; counters packed 4 x 16 bit in one 64-bit word per parity
   unsigned short *queue = reinterpret_cast<unsigned short *>(sf + F_COUNT * NSLOT);
   __shared__ unsigned long long q_packed[2];
@@ -264,7 +264,10 @@ __global__ void __launch_bounds__(TPT_WAVE_THREADS, TPT_WAVE_MIN_BLOCKS) render_
         int prim;
         V3 rad;
         n_rays++;
-        cls = extend<PAR, SMALL>(S, ps, A.max_depth, A.t_min, t, prim, rad);
+        Rng rng; // only participating media draw during extend
+        rng.begin(A.seed_lo, A.seed_hi, (uint32_t)SI(F_PIXEL, s), (uint32_t)SI(F_K, s));
+        uint32_t ndraw0;
+        cls = extend<PAR, SMALL, MEDIA>(S, ps, A.max_depth, A.t_min, t, prim, rad, rng, ndraw0);
         if (cls == TPT_EXT_DONE) {
           // col += de_nan(tmp): main.cpp:126, headers/utils.h:100-109
           if (isnan(rad.x) || isnan(rad.y) || isnan(rad.z)) n_nan++;
@@ -275,6 +278,7 @@ __global__ void __launch_bounds__(TPT_WAVE_THREADS, TPT_WAVE_MIN_BLOCKS) render_
         } else {
           SI(F_HPRIM, s) = prim;
           SF(F_HT, s) = t;
+          if (MEDIA) SI(F_NDRAW, s) = (int)ndraw0;
         }
       }
       // queue of this slot: TPT_MAT_LAMBERTIAN=0, METAL=1, DIELECTRIC=2, done -> 3 (generate)
@@ -330,7 +334,7 @@ __global__ void __launch_bounds__(TPT_WAVE_THREADS, TPT_WAVE_MIN_BLOCKS) render_
             ps.depth = SI(F_DEPTH, s);
             Rng rng;
             rng.begin(A.seed_lo, A.seed_hi, (uint32_t)SI(F_PIXEL, s), (uint32_t)SI(F_K, s));
-            bool alive = shade<PAR>(S, ps, rng, SI(F_HPRIM, s), SF(F_HT, s));
+            bool alive = shade<PAR>(S, ps, rng, SI(F_HPRIM, s), SF(F_HT, s), MEDIA ? (uint32_t)SI(F_NDRAW, s) : 0u);
             if (alive) {
               SF(F_OX, s) = ps.ray.o.x; SF(F_OY, s) = ps.ray.o.y; SF(F_OZ, s) = ps.ray.o.z;
               SF(F_DX, s) = ps.ray.d.x; SF(F_DY, s) = ps.ray.d.y; SF(F_DZ, s) = ps.ray.d.z;
@@ -493,45 +497,47 @@ cudaError_t TPT_FN(launch_intersect_)(const IntersectArgs &A, bool smem, bool sm
   return cudaGetLastError();
 }
 
-// kernel variant table: [smem][small]
+// kernel variant table: [smem][small], or the media build (generic walk, scene staged when it fits)
 typedef void (*mega_fn)(RenderArgs);
-static mega_fn mega_variant(bool smem, bool small) {
-  if (smem) return small ? render_mega_kernel<TPT_PAR, true, true> : render_mega_kernel<TPT_PAR, true, false>;
-  return small ? render_mega_kernel<TPT_PAR, false, true> : render_mega_kernel<TPT_PAR, false, false>;
+static mega_fn mega_variant(bool smem, bool small, bool media) {
+  if (media) return smem ? render_mega_kernel<TPT_PAR, true, false, true> : render_mega_kernel<TPT_PAR, false, false, true>;
+  if (smem) return small ? render_mega_kernel<TPT_PAR, true, true, false> : render_mega_kernel<TPT_PAR, true, false, false>;
+  return render_mega_kernel<TPT_PAR, false, false, false>;
 }
 
-cudaError_t TPT_FN(mega_occupancy_)(bool smem, bool small, size_t smem_bytes, int *blocks_per_sm) {
-  mega_fn k = mega_variant(smem, small);
+cudaError_t TPT_FN(mega_occupancy_)(bool smem, bool small, bool media, size_t smem_bytes, int *blocks_per_sm) {
+  mega_fn k = mega_variant(smem, small, media);
   cudaError_t e;
   if (smem && (e = allow_smem(k, smem_bytes)) != cudaSuccess) return e;
   return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k, TPT_MEGA_THREADS, smem ? smem_bytes : 0);
 }
 
-cudaError_t TPT_FN(launch_mega_)(const RenderArgs &A, bool smem, bool small, int blocks, cudaStream_t st) {
+cudaError_t TPT_FN(launch_mega_)(const RenderArgs &A, bool smem, bool small, bool media, int blocks, cudaStream_t st) {
   size_t bytes = smem ? (size_t)A.scene.blob_words * 16 : 0;
-  mega_variant(smem, small)<<<blocks, TPT_MEGA_THREADS, bytes, st>>>(A);
+  mega_variant(smem, small, media)<<<blocks, TPT_MEGA_THREADS, bytes, st>>>(A);
   return cudaGetLastError();
 }
 
 typedef void (*wave_fn)(RenderArgs);
-static wave_fn wave_variant(bool small, bool smem) {
-  if (!smem) return render_wave_kernel<TPT_PAR, false, false>;
-  return small ? render_wave_kernel<TPT_PAR, true, true> : render_wave_kernel<TPT_PAR, false, true>;
+static wave_fn wave_variant(bool small, bool smem, bool media) {
+  if (media) return smem ? render_wave_kernel<TPT_PAR, false, true, true> : render_wave_kernel<TPT_PAR, false, false, true>;
+  if (!smem) return render_wave_kernel<TPT_PAR, false, false, false>;
+  return small ? render_wave_kernel<TPT_PAR, true, true, false> : render_wave_kernel<TPT_PAR, false, true, false>;
 }
 static size_t wave_smem_bytes(const RenderArgs &A, bool smem) {
-  return (smem ? (size_t)A.scene.blob_words * 16 : 0) + (size_t)TPT_WAVE_SLOTS * (21 * 4 + 2 * TPT_WAVE_NQ * 2);
+  return (smem ? (size_t)A.scene.blob_words * 16 : 0) + (size_t)TPT_WAVE_SLOTS * (22 * 4 + 2 * TPT_WAVE_NQ * 2);
 }
 
-cudaError_t TPT_FN(wave_occupancy_)(const RenderArgs &A, bool small, bool smem, int *blocks_per_sm) {
-  wave_fn k = wave_variant(small, smem);
+cudaError_t TPT_FN(wave_occupancy_)(const RenderArgs &A, bool small, bool smem, bool media, int *blocks_per_sm) {
+  wave_fn k = wave_variant(small, smem, media);
   size_t bytes = wave_smem_bytes(A, smem);
   cudaError_t e = allow_smem(k, bytes);
   if (e != cudaSuccess) return e;
   return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k, TPT_WAVE_THREADS, bytes);
 }
 
-cudaError_t TPT_FN(launch_wave_)(const RenderArgs &A, bool small, bool smem, int blocks, cudaStream_t st) {
-  wave_variant(small, smem)<<<blocks, TPT_WAVE_THREADS, wave_smem_bytes(A, smem), st>>>(A);
+cudaError_t TPT_FN(launch_wave_)(const RenderArgs &A, bool small, bool smem, bool media, int blocks, cudaStream_t st) {
+  wave_variant(small, smem, media)<<<blocks, TPT_WAVE_THREADS, wave_smem_bytes(A, smem), st>>>(A);
   return cudaGetLastError();
 }
 

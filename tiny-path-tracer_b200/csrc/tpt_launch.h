@@ -53,16 +53,17 @@ struct TextureProbeArgs {
 
 cudaError_t launch_intersect_parity(const IntersectArgs &A, bool smem, bool small, cudaStream_t st);
 cudaError_t launch_intersect_fast(const IntersectArgs &A, bool smem, bool small, cudaStream_t st);
+// `media`: scene has constant_medium primitives (the stream is threaded through world->hit)
 // `small`: scene has few enough primitives for the warp-uniform brute-force closest hit
-cudaError_t mega_occupancy_parity(bool smem, bool small, size_t smem_bytes, int *blocks_per_sm);
-cudaError_t mega_occupancy_fast(bool smem, bool small, size_t smem_bytes, int *blocks_per_sm);
-cudaError_t launch_mega_parity(const RenderArgs &A, bool smem, bool small, int blocks, cudaStream_t st);
-cudaError_t launch_mega_fast(const RenderArgs &A, bool smem, bool small, int blocks, cudaStream_t st);
+cudaError_t mega_occupancy_parity(bool smem, bool small, bool media, size_t smem_bytes, int *blocks_per_sm);
+cudaError_t mega_occupancy_fast(bool smem, bool small, bool media, size_t smem_bytes, int *blocks_per_sm);
+cudaError_t launch_mega_parity(const RenderArgs &A, bool smem, bool small, bool media, int blocks, cudaStream_t st);
+cudaError_t launch_mega_fast(const RenderArgs &A, bool smem, bool small, bool media, int blocks, cudaStream_t st);
 // persistent wavefront variant (`smem`: scene tables staged in shared memory, else read through L1)
-cudaError_t wave_occupancy_parity(const RenderArgs &A, bool small, bool smem, int *blocks_per_sm);
-cudaError_t wave_occupancy_fast(const RenderArgs &A, bool small, bool smem, int *blocks_per_sm);
-cudaError_t launch_wave_parity(const RenderArgs &A, bool small, bool smem, int blocks, cudaStream_t st);
-cudaError_t launch_wave_fast(const RenderArgs &A, bool small, bool smem, int blocks, cudaStream_t st);
+cudaError_t wave_occupancy_parity(const RenderArgs &A, bool small, bool smem, bool media, int *blocks_per_sm);
+cudaError_t wave_occupancy_fast(const RenderArgs &A, bool small, bool smem, bool media, int *blocks_per_sm);
+cudaError_t launch_wave_parity(const RenderArgs &A, bool small, bool smem, bool media, int blocks, cudaStream_t st);
+cudaError_t launch_wave_fast(const RenderArgs &A, bool small, bool smem, bool media, int blocks, cudaStream_t st);
 cudaError_t launch_texture_probe_parity(const TextureProbeArgs &A, cudaStream_t st);
 cudaError_t launch_texture_probe_fast(const TextureProbeArgs &A, cudaStream_t st);
 cudaError_t launch_philox_probe(const uint32_t ctr[4], const uint32_t key[2], uint32_t *d_out, cudaStream_t st);

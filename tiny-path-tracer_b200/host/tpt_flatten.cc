@@ -28,6 +28,7 @@ tpt_scene_desc FlatScene::desc() const {
   d.perlin = has_perlin ? &perlin : nullptr;
   d.lights = lights.data();
   d.background = background;
+  d.n_root_nodes = n_root_nodes;
   return d;
 }
 
@@ -114,6 +115,39 @@ void Flattener::leaf(const hitable *self, int prim_kind, const float *params, in
   out_.nodes.push_back(n);
 }
 
+// constant_medium(boundary, density, texture) (headers/hitable.h:58-69, src/hitable.cc:92-128):
+// a MEDIUM primitive in the world tree; its boundary is an ordinary sub-tree kept apart, because
+// constant_medium::hit queries it on its own (twice, with its own t ranges).
+void Flattener::medium(const hitable *self, const hitable *boundary, float density, const material *phase) {
+  // emit the boundary into a scratch node list (same transform chain / flip context)
+  std::vector<tpt_node> saved;
+  saved.swap(out_.nodes);
+  int saved_depth = depth_;
+  depth_ = 0;
+  boundary->emit(*this);
+  depth_ = saved_depth;
+  std::vector<tpt_node> sub;
+  sub.swap(out_.nodes);
+  out_.nodes.swap(saved);
+  for (const tpt_node &n : sub)
+    if ((n.kind & 0xff) == TPT_NODE_LEAF && out_.prims[n.end_or_prim].kind == TPT_PRIM_MEDIUM) {
+      fail("constant_medium inside a constant_medium boundary is not supported");
+      return;
+    }
+  float params[3] = {density, 0.f, 0.f}; // p[1], p[2] patched with the boundary's node range at the end
+  AABB b;
+  if (!boundary->bounding_box(0, 0, b)) {
+    float m = 3.4028234663852886e38f;
+    b = AABB(vec3(-m, -m, -m), vec3(m, m, m));
+  }
+  int before = (int)out_.prims.size();
+  leaf(self, TPT_PRIM_MEDIUM, params, 3, phase, b);
+  if ((int)out_.prims.size() > before) { // first time this medium is seen
+    boundaries_.push_back(sub);
+    boundary_prims_.push_back(before);
+  }
+}
+
 void Flattener::push_xform(const tpt_xform_op &op) { stack_.push_back(op); }
 void Flattener::pop_xform() { stack_.pop_back(); }
 
@@ -174,6 +208,19 @@ bool flatten_scene(const hitable *world, const hitable *light_shape, int backgro
   if (!f.ok()) {
     err = f.error();
     return false;
+  }
+  // medium boundaries go behind the world tree; group ends become absolute indices again
+  out.n_root_nodes = (int)out.nodes.size();
+  for (size_t m = 0; m < f.boundaries_.size(); m++) {
+    int base = (int)out.nodes.size();
+    for (tpt_node n : f.boundaries_[m]) {
+      if ((n.kind & 0xff) != TPT_NODE_LEAF) n.end_or_prim += base;
+      out.nodes.push_back(n);
+    }
+    int32_t first = base, end = (int32_t)out.nodes.size();
+    tpt_prim &p = out.prims[f.boundary_prims_[m]];
+    std::memcpy(&p.p[1], &first, 4);
+    std::memcpy(&p.p[2], &end, 4);
   }
   for (size_t i = 0; i < out.images.size(); i++) out.images[i].rgb = out.image_data[i].data();
   if (out.has_perlin) {

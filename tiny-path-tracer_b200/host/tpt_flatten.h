@@ -36,6 +36,7 @@ struct FlatScene {
   std::vector<tpt_light> lights;
   int background = TPT_BG_BLACK;
   int max_depth = 0; // deepest BVH/LIST nesting (frames the parity walk needs)
+  int n_root_nodes = 0; // nodes behind this index are medium boundaries
 
   tpt_scene_desc desc() const; // pointers into this object; valid while it lives unmodified
 };
@@ -51,6 +52,8 @@ public:
             const material *mat, const AABB &bounds);
   void push_xform(const tpt_xform_op &op);
   void pop_xform();
+  // constant_medium: `boundary` is emitted into a side list that ends up behind the root tree
+  void medium(const hitable *self, const hitable *boundary, float density, const material *phase);
   void toggle_flip() { flip_ = !flip_; }
   void mark_next_dup() { dup_next_ = true; }
   void fail(const std::string &why);
@@ -81,6 +84,9 @@ private:
   std::map<const texture *, int> tex_ids_;
   std::map<const unsigned char *, int> image_ids_;
   std::map<std::pair<const hitable *, std::pair<int, int>>, int> prim_ids_;
+  std::vector<std::vector<tpt_node>> boundaries_; // one pre-order sub-tree per medium
+  std::vector<int> boundary_prims_;               // the MEDIUM primitive that owns boundaries_[i]
+  friend bool flatten_scene(const hitable *, const hitable *, int, FlatScene &, std::string &);
   bool flip_ = false;
   bool dup_next_ = false;
   int depth_ = 0;

@@ -88,6 +88,11 @@ static tpt_material blank_material(int kind) {
   return m;
 }
 int material::emit(tpt::Flattener &f) const { return f.add_material(blank_material(TPT_MAT_ABSORBER)); }
+int isotropic::emit(tpt::Flattener &f) const {
+  tpt_material m = blank_material(TPT_MAT_ISOTROPIC);
+  m.texture = f.texture_id(albedo_);
+  return f.add_material(m);
+}
 int lambertian::emit(tpt::Flattener &f) const {
   tpt_material m = blank_material(TPT_MAT_LAMBERTIAN);
   m.texture = f.texture_id(albedo_);
@@ -304,9 +309,7 @@ void rotate_y::emit(tpt::Flattener &f) const {
   ptr_->emit(f);
   f.pop_xform();
 }
-void constant_medium::emit(tpt::Flattener &f) const {
-  f.fail("constant_medium is outside the accelerated path (SURVEY 8f row 1)");
-}
+void constant_medium::emit(tpt::Flattener &f) const { f.medium(this, boundary_, density_, phase_funcion_); }
 
 // ---------------------------------------------------------------------------- scene builders
 namespace {

@@ -122,6 +122,7 @@ public:
 class isotropic : public material {
 public:
   isotropic(texture *t) : albedo_(t) {}
+  int emit(tpt::Flattener &f) const override;
   texture *albedo_;
 };
 
@@ -266,9 +267,8 @@ public:
   AABB box_;
 };
 
-// Participating medium (headers/hitable.h:58-69). Outside the accelerated path:
-// constructing one is allowed, flattening a scene that contains one fails with
-// TPT_ERR_UNSUPPORTED instead of silently rendering something else.
+// Participating medium (headers/hitable.h:58-69): flattened to a MEDIUM primitive whose boundary
+// sub-tree is kept behind the world tree (tpt_flatten.cc).
 class constant_medium : public hitable {
 public:
   constant_medium(hitable *boundary, float density, texture *tex)
