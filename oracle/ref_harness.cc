@@ -162,6 +162,7 @@ hitable *build_named(const std::string &name, ref_scene *sc, const unsigned char
   if (name == "cornell_box") return cornell_box();               // src/utils.cc:287
   if (name == "sphere_cornell_box") return sphere_cornell_box(); // src/utils.cc:257
   if (name == "cornell_box_smoke") return cornell_box_smoke();   // src/utils.cc:321 (constant_medium)
+  if (name == "oneweek_final") return oneweek_final();           // src/utils.cc:359 (stbi_load("earthmap.jpg") from the CWD)
   if (name == "random_scene") return random_scene();             // src/utils.cc:96 (bvh)
   if (name == "random_scene_list") {
     // the "no BVH" alternative is the commented line src/utils.cc:139: same leaves, flat list.

@@ -28,9 +28,10 @@ for kern in kernels:
             except T.TptError as e:
                 print("kernel", kern, "ERR", e); continue
             print(f"kernel {kern} variant {variant} mode {mode}: {st['render_ms']:.2f} ms  {st['paths']/st['render_ms']/1e3:.0f} Mpaths/s  {st['rays']/st['render_ms']/1e3:.0f} Mrays/s  rays/path {st['rays']/st['paths']:.3f} blocks {st['blocks']}")
-for scene, camf in (("random_scene", T.book_camera), ("random_scene_list", T.book_camera), ("textured_lit", T.book_camera)):
+for scene, camf in (("random_scene", T.book_camera), ("random_scene_list", T.book_camera), ("textured_lit", T.book_camera),
+                    ("cornell_box_smoke", T.cornell_camera), ("oneweek_final", lambda nx, ny, fov: T.make_camera((478, 278, -600), (278, 278, 0), (0, 1, 0), 40.0, 1.0, 0.0, 10.0, 0.0, 1.0))):
     s2 = T.Scene(common.host_scene(T, scene, perlin=common.perlin_struct(T, common.golden("textures")), lights=common.TEXTURED_LIGHTS if scene == "textured_lit" else None))
-    cam3 = camf(800, 800, fov=20.0 if "random" in scene else 50.0)
+    cam3 = camf(800, 800, fov=20.0 if "random" in scene else 50.0) if scene != "oneweek_final" else camf(800, 800, 40.0)
     for mode, kern in ((T.MODE_FAST, 0), (T.MODE_FAST, 1), (T.MODE_PARITY, 0), (T.MODE_PARITY, 1)):
         p = T.make_params(800, 800, 16, 15, mode=mode, seed=1, kernel=kern)
         st = s2.render_device(cam3, p); st = s2.render_device(cam3, p)

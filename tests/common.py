@@ -22,6 +22,8 @@ RENDER_CASES = {
     "textured_lit": dict(scene="textured_lit", cam=dict(BOOK_CAM, vfov=50.0), nx=40, ny=40, ns=8, depth=15, seed=6,
                          lights=TEXTURED_LIGHTS),
     "cornell_smoke": dict(scene="cornell_box_smoke", cam=dict(CORNELL_CAM, vfov=61.93), nx=40, ny=40, ns=8, depth=15, seed=12),
+    "oneweek_final": dict(scene="oneweek_final", cam=dict(lookfrom=(478, 278, -600), lookat=(278, 278, 0), vup=(0, 1, 0), vfov=40.0,
+                          aperture=0.0, focus_dist=10.0, t0=0.0, t1=1.0), nx=36, ny=36, ns=4, depth=10, seed=21),
 }
 HIT_SCENES = ["cornell_box", "sphere_cornell_box", "random_scene", "random_scene_list", "two_perlin_spheres",
               "light_spheres", "earth", "textured_lit"]
@@ -46,8 +48,15 @@ def perlin_struct(T, g):
     return pt
 
 
+def earth_jpg_decoded():
+    """tests/golden/earthmap.jpg as the reference's stb_image decodes it (what oneweek_final() loads)"""
+    return golden("earth_jpg_decoded")["rgb"]
+
+
 def host_scene(T, scene, perlin=None, lights=None, background=0):
     img = earth_small() if scene in ("earth", "textured_lit") else None
+    if scene == "oneweek_final":
+        img = earth_jpg_decoded()
     return T.HostScene(scene, image=img, perlin=perlin, lights=lights, background=background)
 
 

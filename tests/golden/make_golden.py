@@ -30,10 +30,26 @@ def small_earth():
     return full, np.ascontiguousarray(full[::4, ::4])
 
 
+def oneweek_fixture(earth):
+    """oneweek_final() (src/utils.cc:359-414) does stbi_load("earthmap.jpg") from the CWD: write the
+    decimated picture as tests/golden/earthmap.jpg (a derived 256x128 file), let the reference
+    decode THAT, and keep the decoded bytes for the product side."""
+    from PIL import Image
+    jpg = os.path.join(HERE, "earthmap.jpg")
+    Image.fromarray(earth).save(jpg, quality=90)
+    L = O.ref_lib(True)
+    w, h, ch = C.c_int(), C.c_int(), C.c_int()
+    p = L.ref_load_image(jpg.encode(), C.byref(w), C.byref(h), C.byref(ch))
+    assert p and ch.value == 3
+    return np.ctypeslib.as_array(p, shape=(h.value, w.value, 3)).copy()
+
+
 def main():
     full, earth = small_earth()
     np.savez_compressed(os.path.join(HERE, "earth_small.npz"), rgb=earth, full_shape=np.array(full.shape),
                         full_checksum=np.array([int(full.astype(np.uint64).sum())]))
+    earth_jpg = oneweek_fixture(earth)
+    np.savez_compressed(os.path.join(HERE, "earth_jpg_decoded.npz"), rgb=earth_jpg)
     # ---- gate 1: hit records ------------------------------------------------------------
     for scene, (n_cam, n_int) in {"cornell_box": (1500, 1500), "sphere_cornell_box": (600, 600),
                                   "random_scene": (1500, 1500), "random_scene_list": (400, 400),
@@ -60,10 +76,15 @@ def main():
         "textured_lit": dict(scene="textured_lit", cam=dict(O.BOOK_CAM, vfov=50.0), nx=40, ny=40, ns=8, depth=15, seed=6,
                              lights=[(0, (-2.0, 2.0, -2.0, 2.0, 7.0)), (1, (-3.0, 6.0, 4.0, 2.0, 0.0))]),
         "cornell_smoke": dict(scene="cornell_box_smoke", cam=dict(O.CORNELL_CAM, vfov=61.93), nx=40, ny=40, ns=8, depth=15, seed=12),
+        "oneweek_final": dict(scene="oneweek_final", cam=dict(lookfrom=(478, 278, -600), lookat=(278, 278, 0), vup=(0, 1, 0), vfov=40.0,
+                              aperture=0.0, focus_dist=10.0, t0=0.0, t1=1.0), nx=36, ny=36, ns=4, depth=10, seed=21),
     }
     for name, c in cases.items():
         img = earth if c["scene"] in ("earth", "textured_lit") else None
+        cwd = os.getcwd()
+        os.chdir(HERE)  # oneweek_final() loads ./earthmap.jpg
         rs = O.RefScene(c["scene"], image=img)
+        os.chdir(cwd)
         rv, px, py, pz = rs.perlin_tables()
         out, samples, st = rs.render(c["cam"], c["nx"], c["ny"], c["ns"], c["depth"], slices=c.get("slices", 1),
                                      lights=c.get("lights", O.REFERENCE_LIGHTS), seed=c["seed"], per_sample=True)

@@ -13,6 +13,7 @@ def test_cases_in_sync_with_generator():
     src = open(common.GOLDEN + "/make_golden.py").read()
     for name, c in common.RENDER_CASES.items():
         assert f'"{name}": dict(scene="{c["scene"]}"' in src
+        assert f'nx={c["nx"]}, ny={c["ny"]}, ns={c["ns"]}, depth={c["depth"]}, seed={c["seed"]}' in src
 
 
 @pytest.mark.parametrize("scene", common.HIT_SCENES)
@@ -39,11 +40,13 @@ def test_ray_generator_is_deterministic():
     assert common.same_float(g[: len(full)], full).all()
 
 
-@pytest.mark.parametrize("case", ["cornell_A", "cornell_slices", "light_spheres", "textured_lit"])
-def test_ref_reproduces_golden_radiance(O, case):
+@pytest.mark.parametrize("case", ["cornell_A", "cornell_slices", "light_spheres", "textured_lit", "cornell_smoke",
+                                  "oneweek_final"])
+def test_ref_reproduces_golden_radiance(O, case, monkeypatch):
     c = common.RENDER_CASES[case]
     g = common.golden("render_" + case)
     img = common.earth_small() if c["scene"] in ("earth", "textured_lit") else None
+    monkeypatch.chdir(common.GOLDEN)  # oneweek_final() loads ./earthmap.jpg (src/utils.cc:400)
     rs = O.RefScene(c["scene"], image=img)
     # the perlin tables are wall-clock seeded (src/perlin_noise.cc:15-17): put the golden ones back
     tabs = [np.ascontiguousarray(g[k]) for k in ("ranvec", "perm_x", "perm_y", "perm_z")]  # keep alive

@@ -154,3 +154,37 @@ def test_parity_vs_port_both_kernels(T, gpu):
         n_bad, n, worst = outliers(res.sum_rgb, ref, 12)
         assert n_bad == 0, (kernel, n_bad, worst)
         assert res.stats["rays"] < st["rays"]  # zombies skipped
+
+
+def test_oneweek_final_vs_port(T, gpu):
+    """oneweek_final (src/utils.cc:359-414): 400 boxes under a bvh, 1000 spheres in a bvh under
+    rotate_y + translate, moving sphere, glass, metal, two participating media, image + marble
+    textures -- every construct at once. At HEAD it renders black (its lamp faces up and
+    diffuse_light emits on one side only), so the radiance comparison uses the sky background,
+    for which the plain-C restatement (bit-for-bit pinned to the reference on the black version,
+    tests/test_oracle_port.py) is the checker."""
+    import oracle_port as P
+    if not P.available():
+        pytest.skip("oracle/_build/libtptoracle.so not built")
+    c = common.RENDER_CASES["oneweek_final"]
+    g = common.golden("render_oneweek_final")
+    perlin = common.perlin_struct(T, g)
+    cam = common.product_camera(T, c["cam"], c["nx"], c["ny"])
+    # black (HEAD): identical zeros and no more rays than the reference traced
+    hs = common.host_scene(T, "oneweek_final", perlin=perlin)
+    res = T.Scene(hs).render(cam, T.make_params(c["nx"], c["ny"], c["ns"], c["depth"], mode=T.MODE_PARITY, seed=c["seed"]))
+    assert np.array_equal(res.sum_rgb, g["sum_rgb"]) and res.stats["rays"] <= int(g["rays"][0])
+    # sky: non-trivial radiance through every material and both media
+    hs = common.host_scene(T, "oneweek_final", perlin=perlin, background=T.BG_SKY)
+    sc = T.Scene(hs)
+    p = T.make_params(c["nx"], c["ny"], c["ns"], c["depth"], mode=T.MODE_PARITY, seed=c["seed"])
+    ref, _, st = P.render(T, hs, cam, p, threads=8)
+    assert ref.mean() > 0.01
+    for kernel in (T.KERNEL_MEGA, T.KERNEL_WAVEFRONT):
+        p = T.make_params(c["nx"], c["ny"], c["ns"], c["depth"], mode=T.MODE_PARITY, seed=c["seed"], kernel=kernel)
+        res = sc.render(cam, p)
+        n_bad, n, worst = outliers(res.sum_rgb, ref, c["ns"])
+        assert n_bad == 0, (kernel, n_bad, worst)
+    fast = sc.render(cam, T.make_params(c["nx"], c["ny"], 256, c["depth"], mode=T.MODE_FAST, seed=5))
+    slow = sc.render(cam, T.make_params(c["nx"], c["ny"], 256, c["depth"], mode=T.MODE_PARITY, seed=6))
+    assert abs(fast.sum_rgb.mean() - slow.sum_rgb.mean()) < 0.03 * slow.sum_rgb.mean()

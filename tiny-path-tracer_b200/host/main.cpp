@@ -93,6 +93,8 @@ int main(int, char **) {
     else if (scene_name == "two_perlin_spheres") world = two_perlin_spheres();
     else if (scene_name == "two_checker_spheres") world = two_checker_spheres();
     else if (scene_name == "light_spheres") world = light_spheres();
+    else if (scene_name == "cornell_box_smoke") world = cornell_box_smoke();
+    else if (scene_name == "oneweek_final") world = oneweek_final();
     else if (scene_name == "earth") {
       int w, h, ch;
       unsigned char *data = load_image_texture(image_file, w, h, ch);
@@ -105,7 +107,11 @@ int main(int, char **) {
       std::cerr << "unknown scene " << scene_name << std::endl;
       return 2;
     }
-    if (scene_name != "sphere_cornell_box") {
+    if (scene_name == "oneweek_final") { // the book's camera for this scene (not in the reference's main.cpp)
+      lookfrom = vec3(478, 278, -600);
+      lookat = vec3(278, 278, 0);
+      dist_to_focus = 10.0f;
+    } else if (scene_name != "sphere_cornell_box" && scene_name != "cornell_box_smoke") {
       lookfrom = vec3(13, 2, 3);
       dist_to_focus = (lookfrom - lookat).length();
     }

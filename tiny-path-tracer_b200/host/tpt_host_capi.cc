@@ -45,6 +45,12 @@ hitable *build_named(const std::string &name, const unsigned char *img, int iw, 
   if (name == "two_checker_spheres") return two_checker_spheres();
   if (name == "light_spheres") return light_spheres();
   if (name == "cornell_box_smoke") return cornell_box_smoke();
+  if (name == "oneweek_final") { // src/utils.cc:359-414; the earth texture is passed in by the caller
+    if (!img) return nullptr;
+    unsigned char *copy = new unsigned char[(size_t)iw * ih * 3];
+    std::memcpy(copy, img, (size_t)iw * ih * 3);
+    return oneweek_final_with(copy, iw, ih);
+  }
   if (name == "textured_lit") {
     // test scene: every texture class under real light (HEAD's own textured scenes are black)
     if (!img) return nullptr;

@@ -446,3 +446,54 @@ hitable *cornell_box_smoke() { // src/utils.cc:321-357 (constant_medium: not acc
   s.add(new constant_medium(mist, 0.0001, new constant_texture(vec3(1.0, 1.0, 1.0))));
   return new hitable_list(s.items, s.n);
 }
+
+// src/utils.cc:359-414: 20x20 random-height boxes under a bvh, lamp, moving sphere, glass, metal
+// (fuzz 10 clamps to 1), a glass sphere filled with blue fog, a global mist, the earth, a marble
+// sphere and 1000 small spheres in a rotated + translated bvh. Draw order (scene must equal the
+// reference's for seed 5489): one draw per box height, then three per small sphere with the vec3
+// constructor arguments evaluated right to left.
+hitable *oneweek_final_with(unsigned char *tex_data, int nx, int ny) {
+  const int nb = 20;
+  scene_list top(30), boxes(10000), balls(10000);
+  material *white = matte(0.73, 0.73, 0.73);
+  material *ground = matte(0.48, 0.83, 0.53);
+  for (int i = 0; i < nb; i++) {
+    for (int j = 0; j < nb; j++) {
+      float w = 100;
+      float x0 = -1000 + i * w;
+      float z0 = -1000 + j * w;
+      float y0 = 0;
+      float x1 = x0 + w;
+      float y1 = 100 * (drand_r() + 0.01);
+      float z1 = z0 + w;
+      boxes.add(new box(vec3(x0, y0, z0), vec3(x1, y1, z1), ground));
+    }
+  }
+  top.add(new bvh_node(boxes.items, boxes.n, 0, 1));
+  material *light = new diffuse_light(new constant_texture(vec3(7, 7, 7)));
+  top.add(new xz_rect(123, 423, 147, 412, 554, light));
+  vec3 center(400, 400, 200);
+  top.add(new moving_sphere(center, center + vec3(30, 0, 0), 0, 1, 50, matte(0.7, 0.3, 0.1)));
+  top.add(new sphere(vec3(260, 150, 45), 50, new dielectric(1.5)));
+  top.add(new sphere(vec3(0, 150, 145), 50, new metal(vec3(0.8, 0.8, 0.9), 10.0)));
+  hitable *boundary = new sphere(vec3(360, 150, 145), 70, new dielectric(1.5));
+  top.add(boundary);
+  top.add(new constant_medium(boundary, 0.2, new constant_texture(vec3(0.2, 0.4, 0.9))));
+  boundary = new sphere(vec3(0, 0, 0), 5000, new dielectric(1.5));
+  top.add(new constant_medium(boundary, 0.0001, new constant_texture(vec3(1.0, 1.0, 1.0))));
+  material *emat = new lambertian(new image_texture(tex_data, nx, ny));
+  top.add(new sphere(vec3(400, 200, 400), 100, emat));
+  texture *pertext = new perlin_noise_texture(0.1);
+  top.add(new sphere(vec3(220, 280, 300), 80, new lambertian(pertext)));
+  const int ns = 1000;
+  for (int j = 0; j < ns; j++)
+    balls.add(new sphere(vec3(165 * drand_r(), 165 * drand_r(), 165 * drand_r()), 10, white));
+  top.add(new translate(new rotate_y(new bvh_node(balls.items, ns, 0.0, 1.0), 15), vec3(-100, 270, 395)));
+  return new hitable_list(top.items, top.n);
+}
+
+hitable *oneweek_final() {
+  int nx = 0, ny = 0, nn = 0;
+  unsigned char *tex_data = load_image_texture("earthmap.jpg", nx, ny, nn);
+  return oneweek_final_with(tex_data, nx, ny); // a missing picture is reported by the flattener
+}

@@ -304,6 +304,8 @@ hitable *light_spheres();
 hitable *sphere_cornell_box();
 hitable *cornell_box();
 hitable *cornell_box_smoke();
+hitable *oneweek_final();                                   // loads ./earthmap.jpg like the reference
+hitable *oneweek_final_with(unsigned char *rgb, int w, int h); // same scene, texture bytes supplied
 
 // decoded picture, 3 bytes per pixel; supports binary PPM (P6) and baseline JPEG
 unsigned char *load_image_texture(std::string filename, int &width, int &height, int &channels);
