@@ -190,3 +190,17 @@ def test_depth_zero_and_one_sample(T, cornell):
     assert 0 < lit.mean() < 0.2  # only the lamp is visible
     one = cornell.render(T.cornell_camera(1, 1), T.make_params(1, 1, 1, 15, seed=1))
     assert one.stats["paths"] == 1
+
+
+def test_config5_frame_size(T, cornell):
+    """BASELINE configs[4]: 4096x4096 (68.7 G paths at 4096 spp). One sample per pixel here: the
+    bin decode, accumulator planes and resolve kernel at 16.7 M pixels, and a 3-way partition of it."""
+    nx = ny = 4096
+    cam = T.cornell_camera(nx, ny)
+    st = cornell.render_device(cam, T.make_params(nx, ny, 1, 15, seed=1, kernel=T.KERNEL_WAVEFRONT))
+    assert st["paths"] == nx * ny
+    paths = sum(cornell.render_device(cam, T.make_params(nx, ny, 1, 15, seed=1, kernel=T.KERNEL_WAVEFRONT, part_index=i,
+                                                         part_count=3))["paths"] for i in range(3))
+    assert paths == nx * ny
+    r = cornell.fetch(T.make_params(nx, ny, 1, 15), want_sum=False)
+    assert r.rgb8.shape == (ny, nx, 3)
