@@ -46,6 +46,10 @@ struct SceneLayout { // host-computed, lives in kernel parameter (constant) spac
 // parameters. Parameter space is the constant bank: the warp-uniform brute-force closest hit
 // below reads it through the uniform datapath (ULDC / constant operands), so a primitive test
 // costs no load instruction on the main pipes. FAST mode only.
+#ifndef TPT_RECT_UNROLL
+#define TPT_RECT_UNROLL 1 // a group holds 1-3 rects per axis: unrolling only adds remainder-loop overhead
+#endif
+constexpr int kRectUnroll = TPT_RECT_UNROLL;
 #define TPT_SMALL_MAX_PRIMS 48
 #define TPT_SMALL_MAX_GROUPS 8
 #define TPT_SMALL_MAX_OPS 16
@@ -600,6 +604,7 @@ TPT_DEV void fast_media_pass(const SceneView &S, const Ray &r, float tmin, float
 template <int K, int A, int B>
 TPT_DEV void small_rects(const SmallScene &Q, int begin, int end, const float (&o)[3], const float (&d)[3],
                          const float (&inv)[3], float tmin, float &best, int &best_prim) {
+#pragma unroll kRectUnroll
   for (int i = begin; i < end; i++) {
     const float4 g = Q.geo[i];
     const float2 w = Q.aux[i];
