@@ -36,7 +36,7 @@ def oneweek_fixture(earth):
     decode THAT, and keep the decoded bytes for the product side."""
     from PIL import Image
     jpg = os.path.join(HERE, "earthmap.jpg")
-    Image.fromarray(earth).save(jpg, quality=90)
+    Image.fromarray(earth).save(jpg, quality=90, subsampling=0)  # 4:4:4 like the reference's earthmap.jpg
     L = O.ref_lib(True)
     w, h, ch = C.c_int(), C.c_int(), C.c_int()
     p = L.ref_load_image(jpg.encode(), C.byref(w), C.byref(h), C.byref(ch))

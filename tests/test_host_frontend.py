@@ -190,3 +190,32 @@ def test_ini_reader_semantics(T, tmp_path):
     assert out[0] == "400 400 50 50 90 0.1 1 2"  # two bad lines: 'bad line' and the duplicate width
     assert out[1:] == ["[BLUR]", "aperture=0.1", "[CAM_MOTION]", "end_time=x", "start_time=0.0", "[DEFAULT]",
                        "fov=90.0", "height=400", "recur_depth=", "sample=50", "width=400"]  # operator[] inserts, as std::map does for inipp
+
+
+def test_builtin_jpeg_decoder_matches_stb(T, O):
+    """load_image_texture decodes baseline JPEG itself (host/tpt_jpeg.cc). The bytes must be the
+    ones the reference's stb_image yields (they are what the GPU samples): checked on the derived
+    fixture tests/golden/earthmap.jpg against its stb decode stored in the golden set, and, where
+    the reference tree is present, on the real resources/earthmap.jpg against stb live."""
+    import common
+    H = T.host()
+    H.tpt_host_load_image.restype = C.POINTER(C.c_uint8)
+    H.tpt_host_load_image.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    H.tpt_host_free.argtypes = [C.c_void_p]
+
+    def mine(path):
+        w, h, ch = C.c_int(), C.c_int(), C.c_int()
+        p = H.tpt_host_load_image(path.encode(), C.byref(w), C.byref(h), C.byref(ch))
+        assert p and ch.value == 3
+        a = np.ctypeslib.as_array(p, shape=(h.value, w.value, 3)).copy()
+        H.tpt_host_free(p)
+        return a
+
+    assert np.array_equal(mine(os.path.join(common.GOLDEN, "earthmap.jpg")), common.earth_jpg_decoded())
+    real = "/root/reference/resources/earthmap.jpg"
+    if os.path.exists(real):
+        L = O.ref_lib(True)
+        w, h, ch = C.c_int(), C.c_int(), C.c_int()
+        q = L.ref_load_image(real.encode(), C.byref(w), C.byref(h), C.byref(ch))
+        ref = np.ctypeslib.as_array(q, shape=(h.value, w.value, 3)).copy()
+        assert ref.shape == (512, 1024, 3) and np.array_equal(mine(real), ref)

@@ -5,6 +5,7 @@
 #include "tpt_image_io.h"
 #include "tpt_scene.h"
 
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <thread>
@@ -144,6 +145,13 @@ void tpt_host_make_camera(const float *lookfrom, const float *lookat, const floa
              vec3(vup[0], vup[1], vup[2]), vfov, aspect, aperture, focus_dist, t0, t1);
   *out = tpt::make_camera_desc(cam);
 }
+
+// load_image_texture (the reference's wrapper around stbi_load, src/utils.cc:236-240): returns
+// malloc'ed RGB bytes, caller frees with tpt_host_free
+unsigned char *tpt_host_load_image(const char *path, int *w, int *h, int *ch) {
+  return load_image_texture(path, *w, *h, *ch);
+}
+void tpt_host_free(void *p) { std::free(p); }
 
 // picture writers in the reference's formats (main.cpp:69,183-189 and :197-211)
 int tpt_host_write_ppm(const char *path, const unsigned char *rgb8, int nx, int ny, int bonus_format) {

@@ -103,14 +103,21 @@ bool read_ppm(const std::string &path, std::vector<uint8_t> &rgb, int &w, int &h
 } // namespace tpt
 
 // Texture input. The reference decodes through stb_image (src/utils.cc:236-240); the decoded
-// RGB bytes are what crosses the boundary (tpt_image_desc), so any decoder that yields them
-// can feed the core. This front end reads binary/ASCII PPM directly; for JPEG/PNG it shells out
-// to ImageMagick (`convert <file> ppm:-`), the same external tool the reference's output stage
-// already depends on (main.cpp:224-245). Returns malloc'ed memory like stbi_load, or nullptr.
+// RGB bytes are what crosses the boundary (tpt_image_desc). This front end decodes baseline JPEG
+// itself (tpt_jpeg.cc: same integer IDCT / colour conversion, byte-identical on earthmap.jpg),
+// reads binary/ASCII PPM directly, and for anything else shells out to ImageMagick
+// (`convert`), the external tool the reference's output stage already depends on
+// (main.cpp:224-245). Returns malloc'ed memory like stbi_load, or nullptr.
 unsigned char *load_image_texture(std::string filename, int &width, int &height, int &channels) {
   std::vector<uint8_t> rgb;
   std::string path = filename;
   bool is_ppm = filename.size() > 4 && filename.substr(filename.size() - 4) == ".ppm";
+  if (!is_ppm && tpt::read_jpeg(filename, rgb, width, height)) { // the built-in baseline decoder
+    channels = 3;
+    unsigned char *out = static_cast<unsigned char *>(std::malloc(rgb.size()));
+    if (out) std::memcpy(out, rgb.data(), rgb.size());
+    return out;
+  }
   if (!is_ppm) {
     std::string tmp = filename + ".tpt_decoded.ppm";
     std::string cmd = "convert '" + filename + "' -depth 8 '" + tmp + "' 2>/dev/null";

@@ -13,6 +13,8 @@ bool write_ppm_main(const std::string &path, const uint8_t *rgb8, int nx, int ny
 bool write_ppm_bonus(const std::string &path, const uint8_t *rgb8, int nx, int ny);
 // `convert a.ppm b.ppm ... +append img.jpg` (main.cpp:224-245); returns the system() status.
 int merge_with_convert(const std::vector<std::string> &files);
+// baseline JPEG (8-bit, 1 or 3 components, no chroma subsampling): tpt_jpeg.cc
+bool read_jpeg(const std::string &path, std::vector<uint8_t> &rgb, int &w, int &h);
 // PPM (P6/P3) reader used by tests and as a texture source
 bool read_ppm(const std::string &path, std::vector<uint8_t> &rgb, int &w, int &h);
 } // namespace tpt
