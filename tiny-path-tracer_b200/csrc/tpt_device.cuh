@@ -1145,6 +1145,43 @@ struct PathState {
 
 TPT_DEV bool dead_channel(float t) { return t == 0.0f || isnan(t); }
 
+// May a ray hit anything at all? Used on freshly generated camera rays so that the ones that leave
+// the scene's bounds (64 % of the headline frame: the camera sees past the box) never enter the
+// extend queue. PARITY: only when the root is a bvh_node, with the reference's own first test
+// (bvh_node::hit -> box_.hit(r, t_min, FLT_MAX), src/hitable.cc:65) -- exactly the rays for which
+// world->hit returns false there. FAST: the root's bounds, padded, NaN-safe (a NaN keeps the ray).
+template <bool PAR> TPT_DEV bool may_hit_world(const SceneView &S, const Ray &r, float t_min) {
+  const float4 n0 = S.blob[S.L->off_nodes], n1 = S.blob[S.L->off_nodes + 1];
+  const int kind = __float_as_int(n0.w);
+  if (PAR) {
+    if ((kind & 0xff) != TPT_NODE_BVH || (kind >> 16) != 0) return true;
+    XRay x;
+    x.o = r.o;
+    x.d = r.d;
+    x.chain = 0;
+    return aabb_hit<true>(x, n0, n1, t_min, FLT_MAX);
+  }
+  if ((kind >> 16) != 0) return true;
+  const float px = 1e-3f * fmaxf(fabsf(n0.x), fabsf(n1.x)) + 1e-3f, py = 1e-3f * fmaxf(fabsf(n0.y), fabsf(n1.y)) + 1e-3f;
+  const float pz = 1e-3f * fmaxf(fabsf(n0.z), fabsf(n1.z)) + 1e-3f;
+  const float ix = 1.0f / r.d.x, iy = 1.0f / r.d.y, iz = 1.0f / r.d.z;
+  const float ax = (n0.x - px - r.o.x) * ix, bx = (n1.x + px - r.o.x) * ix;
+  const float ay = (n0.y - py - r.o.y) * iy, by = (n1.y + py - r.o.y) * iy;
+  const float az = (n0.z - pz - r.o.z) * iz, bz = (n1.z + pz - r.o.z) * iz;
+  const float t0 = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), t_min));
+  const float t1 = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
+  return !(t0 > t1); // any NaN compares false -> keep the ray
+}
+
+// radiance of a ray that leaves the scene (src/utils.cc:85-90)
+template <bool PAR> TPT_DEV V3 background_radiance(const SceneView &S, const Ray &r, V3 T) {
+  if (S.L->background != TPT_BG_SKY) return mk(0, 0, 0);
+  V3 ud = unit<PAR>(r.d);
+  float tt = PAR ? (float)(((double)ud.y + 1.0) * 0.5) : (ud.y + 1.0f) * 0.5f;
+  V3 sky = 0.1f * ((1 - tt) * mk(1.0f, 1.0f, 1.0f) + tt * mk(0.5f, 0.7f, 1.0f));
+  return T * sky;
+}
+
 // extend(): world->hit plus every outcome that ends the path without a scatter() call
 // (src/utils.cc:61-66,82-86). Returns TPT_EXT_DONE with the sample's radiance, or the kind of the
 // scattering material (LAMBERTIAN / METAL / DIELECTRIC) with (prim, t) of the hit.
@@ -1180,13 +1217,7 @@ TPT_DEV int extend(const SceneView &S, const PathState &ps, int max_depth, float
   ndraw_out = media ? g.ndraw : 0u;
   radiance = mk(0, 0, 0);
   if (!any_hit) {
-    if (S.L->background == TPT_BG_SKY) {
-      // the commented gradient src/utils.cc:87-90
-      V3 ud = unit<PAR>(ps.ray.d);
-      float tt = PAR ? (float)(((double)ud.y + 1.0) * 0.5) : (ud.y + 1.0f) * 0.5f;
-      V3 sky = 0.1f * ((1 - tt) * mk(1.0f, 1.0f, 1.0f) + tt * mk(0.5f, 0.7f, 1.0f));
-      radiance = ps.T * sky;
-    }
+    radiance = background_radiance<PAR>(S, ps.ray, ps.T); // black at HEAD, or the commented gradient
     return TPT_EXT_DONE;
   }
   // tpt_material = {kind, texture, albedo[3], fuzz, ref_idx, pad}

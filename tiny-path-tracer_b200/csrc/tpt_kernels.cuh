@@ -417,6 +417,23 @@ __global__ void __launch_bounds__(TPT_WAVE_THREADS, TPT_WAVE_MIN_BLOCKS) render_
               rng.begin(A.seed_lo, A.seed_hi, (uint32_t)pixel, (uint32_t)k);
               const int py = pixel / A.nx, px = pixel - py * A.nx;
               Ray r = camera_sample<PAR>(A.cam, px, py, A.nx, A.ny, rng);
+              // A camera ray that cannot hit the scene's bounds (64 % of the headline frame looks past
+              // the box) ends its path right here -- world->hit is false for it -- and the lane draws
+              // its pixel's next sample instead of spending an extend pass on it. Bounded retries:
+              // the last ray of the budget (or of the bin) goes to extend like any other.
+              if (!MEDIA) {
+                for (int attempt = 1; attempt < TPT_WAVE_CAMERA_TRIES && k + 1 < k_end && !may_hit_world<PAR>(S, r, A.t_min); attempt++) {
+                  V3 bg = background_radiance<PAR>(S, r, mk(1.f, 1.f, 1.f));
+                  SF(F_AX, s) += bg.x;
+                  SF(F_AY, s) += bg.y;
+                  SF(F_AZ, s) += bg.z;
+                  n_paths++;
+                  n_rays++;
+                  k++;
+                  rng.begin(A.seed_lo, A.seed_hi, (uint32_t)pixel, (uint32_t)k);
+                  r = camera_sample<PAR>(A.cam, px, py, A.nx, A.ny, rng);
+                }
+              }
               SF(F_OX, s) = r.o.x; SF(F_OY, s) = r.o.y; SF(F_OZ, s) = r.o.z;
               SF(F_DX, s) = r.d.x; SF(F_DY, s) = r.d.y; SF(F_DZ, s) = r.d.z;
               SF(F_TIME, s) = r.time;

@@ -10,6 +10,9 @@
 #ifndef TPT_WAVE_MIN_BLOCKS
 #define TPT_WAVE_MIN_BLOCKS 3 // __launch_bounds__ min blocks per SM: 80 registers, 3 CTAs (measured best)
 #endif
+#ifndef TPT_WAVE_CAMERA_TRIES
+#define TPT_WAVE_CAMERA_TRIES 1 // >1: redraw camera rays that miss the scene bounds inside generate (measured: no gain)
+#endif
 #ifndef TPT_WAVE_THREADS
 #define TPT_WAVE_THREADS 256
 #endif
