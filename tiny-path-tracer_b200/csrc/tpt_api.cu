@@ -962,6 +962,20 @@ int render_multi(tpt_scene *const *scenes, int n, const tpt_camera *cam, const t
         if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
         else if (e != cudaSuccess) can = 0;
       }
+      if (can) {
+        // the products live in GPU g's stream-ordered pool: pools are private to their device
+        // until access is granted explicitly (cudaDeviceEnablePeerAccess does not cover them)
+        cudaMemPool_t pool;
+        cudaMemAccessDesc acc_desc{};
+        acc_desc.location.type = cudaMemLocationTypeDevice;
+        acc_desc.location.id = s0->device;
+        acc_desc.flags = cudaMemAccessFlagsProtReadWrite;
+        if (cudaDeviceGetDefaultMemPool(&pool, scenes[g]->device) != cudaSuccess ||
+            cudaMemPoolSetAccess(pool, &acc_desc, 1) != cudaSuccess) {
+          cudaGetLastError();
+          can = 0;
+        }
+      }
       const float *src_f = scenes[g]->d_sum;
       const uint8_t *src_b = scenes[g]->d_rgb8, *src_s = scenes[g]->d_rgb8_slices;
       if (can) {
