@@ -1,9 +1,9 @@
 #!/bin/bash
-# scratch: build tuning variants of libtpt.so into gpurun-visible dirs
-cd /root/repo/tiny-path-tracer_b200/csrc
+# developer tool: build tuning variants of libtpt.so into gpurun-visible dirs
+cd "$(dirname "$0")/../tiny-path-tracer_b200/csrc"
 i=0
 while read -r flags; do
-  d=/root/repo/gpurun_variants/v$i
+  d="$(cd ../.. && pwd)/gpurun_variants/v$i"
   mkdir -p $d
   make -s -j3 LIB=$d EXTRA="$flags" >/dev/null 2>&1 || echo "build failed: $flags"
   echo "$flags" > $d/flags.txt

@@ -1,7 +1,7 @@
-# scratch script (not a pytest): first end-to-end look on the GPU
+# developer tool (run on a GPU box via gpurun): first end-to-end look on the GPU
 import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 import numpy as np
 import tpt_b200 as T
 import oracle_ref as O

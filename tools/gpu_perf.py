@@ -1,7 +1,7 @@
-# scratch perf probe (not a pytest)
+# developer tool: perf probe (run on a GPU box via gpurun)
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 import numpy as np
 import tpt_b200 as T
 import common

@@ -1,5 +1,5 @@
 #!/bin/bash
-# scratch: ncu metrics for both kernel variants (fast mode, Cornell A, 1200x1200 @ 64 spp)
+# developer tool: ncu metrics for both kernel variants (fast mode, Cornell A, 1200x1200 @ 64 spp)
 cat > /tmp/run_variant.py <<'PY'
 import sys, os
 sys.path.insert(0, os.getcwd()); sys.path.insert(0, os.path.join(os.getcwd(), "tests"))

@@ -1,5 +1,5 @@
 #!/bin/bash
-# scratch: one GPU session = tests + smoke + bench (both arms) + ncu evidence
+# developer tool: one GPU session = tests + smoke + bench (both arms) + ncu evidence
 python -m pytest tests -m gpu -q 2>&1 | tail -3
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
 python bench.py --steps 3 --warmup 3 > gpurun_out/bench_ours.json 2> gpurun_out/bench_ours.err; tail -c 400 gpurun_out/bench_ours.json; tail -3 gpurun_out/bench_ours.err

@@ -1,7 +1,7 @@
-# scratch: tiny renders of every kernel variant for compute-sanitizer (memcheck / racecheck / initcheck)
+# developer tool: tiny renders of every kernel variant for compute-sanitizer (memcheck / racecheck / initcheck)
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 import numpy as np
 import tpt_b200 as T, common, raygen
 for scene, camf in (("cornell_box", T.cornell_camera), ("random_scene", T.book_camera), ("textured_lit", T.book_camera)):

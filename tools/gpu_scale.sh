@@ -4,4 +4,4 @@ python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127
 python -c "
 import json; d=json.loads(open('gpurun_out/bench_n$n.json').read().strip().splitlines()[-1]); print($n, 'value', round(d['value']), 'ms/step', round(d['ms_per_step'],2), 'wall s/step', round(d['wall_seconds_per_step'],4), 'e2e', round(d['e2e']['value']), round(d['e2e']['seconds_per_step'],4), d['clocks'])"
 done
-python tests/_gpu_multi_perf.py 2>&1 | tail -3
+python tools/gpu_multi_perf.py 2>&1 | tail -3

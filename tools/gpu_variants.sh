@@ -1,5 +1,5 @@
 #!/bin/bash
-# scratch: measure every tuning build under gpurun_variants/
+# developer tool: measure every tuning build under gpurun_variants/
 cat > /tmp/run_one.py <<'PY'
 import sys, os
 sys.path.insert(0, os.getcwd()); sys.path.insert(0, os.path.join(os.getcwd(), "tests"))
