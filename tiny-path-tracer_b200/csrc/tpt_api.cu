@@ -603,6 +603,8 @@ int make_plan(tpt_scene *s, const tpt_camera *cam, const tpt_render_params *p, P
   if (p->mode != TPT_MODE_PARITY && p->mode != TPT_MODE_FAST) return fail(TPT_ERR_INVALID, "unknown mode");
   if (p->kernel != TPT_KERNEL_MEGA && p->kernel != TPT_KERNEL_WAVEFRONT) return fail(TPT_ERR_UNSUPPORTED, "unknown kernel variant");
   plan.wavefront = p->kernel == TPT_KERNEL_WAVEFRONT;
+  if (plan.wavefront && (p->nx > 32767 || p->ny > 32767))
+    return fail(TPT_ERR_UNSUPPORTED, "wavefront variant packs pixel coordinates in 16 bits: use TPT_KERNEL_MEGA above 32767");
   if (p->part_count <= 0 || p->part_index < 0 || p->part_index >= p->part_count) return fail(TPT_ERR_INVALID, "bad part_index/part_count");
   if (p->part_count > TPT_MAX_BATCHES) return fail(TPT_ERR_UNSUPPORTED, "part_count above TPT_MAX_BATCHES");
   if (!s->has_lights) return fail(TPT_ERR_INVALID, "light-sampling list is empty (color() needs light_shape, main.cpp:99-106)");

@@ -207,19 +207,24 @@ __global__ void __launch_bounds__(TPT_MEGA_THREADS) render_mega_kernel(const __g
 template <bool PAR, bool SMALL, bool SMEM, bool MEDIA>
 __global__ void __launch_bounds__(TPT_WAVE_THREADS, TPT_WAVE_MIN_BLOCKS) render_wave_kernel(const __grid_constant__ RenderArgs A) {
   extern __shared__ float4 sblob[];
-  SceneView S;
-  S.blob = stage_scene<SMEM>(A.scene, sblob); // scenes above 64 KB stay in global memory (L1-cached)
-  S.L = &A.scene;
-  S.small = &A.small;
   constexpr int NSLOT = TPT_WAVE_SLOTS;
   constexpr int NWARP = TPT_WAVE_THREADS / 32;
-  float *sf = reinterpret_cast<float *>(sblob + (SMEM ? A.scene.blob_words : 0));
-  int *si = reinterpret_cast<int *>(sf);
   // structure-of-arrays slot state: field f of slot s at sf[f * NSLOT + s]
   enum { F_OX, F_OY, F_OZ, F_DX, F_DY, F_DZ, F_TIME, F_TX, F_TY, F_TZ, F_AX, F_AY, F_AZ,
          F_PIXEL, F_K, F_KEND, F_ACCIDX, F_DEPTH, F_HPRIM, F_HT, F_ACTIVE, F_NDRAW, F_COUNT };
+  // dynamic shared memory: [slot state | queues | scene blob]. State and queues sit at
+  // compile-time offsets (plain LDS/STS with immediate offsets); the blob, whose size is only known
+  // at run time, comes last.
+  constexpr int STATE_BYTES = F_COUNT * NSLOT * 4, QUEUE_BYTES = 2 * TPT_WAVE_NQ * NSLOT * 2;
+  static_assert((STATE_BYTES + QUEUE_BYTES) % 16 == 0, "scene blob must stay 16-byte aligned");
+  float *sf = reinterpret_cast<float *>(sblob);
+  int *si = reinterpret_cast<int *>(sblob);
   // queue[parity][q][NSLOT] slot ids; counters packed 4 x 16 bit in one 64-bit word per parity
-  unsigned short *queue = reinterpret_cast<unsigned short *>(sf + F_COUNT * NSLOT);
+  unsigned short *queue = reinterpret_cast<unsigned short *>(reinterpret_cast<char *>(sblob) + STATE_BYTES);
+  SceneView S;
+  S.blob = stage_scene<SMEM>(A.scene, sblob + (STATE_BYTES + QUEUE_BYTES) / 16); // > 64 KB: stays in global memory
+  S.L = &A.scene;
+  S.small = &A.small;
   __shared__ unsigned long long q_packed[2];
   __shared__ int n_idle;
 #define SF(f, s) sf[(f) * NSLOT + (s)]
@@ -265,7 +270,8 @@ __global__ void __launch_bounds__(TPT_WAVE_THREADS, TPT_WAVE_MIN_BLOCKS) render_
         V3 rad;
         n_rays++;
         Rng rng; // only participating media draw during extend
-        rng.begin(A.seed_lo, A.seed_hi, (uint32_t)SI(F_PIXEL, s), (uint32_t)SI(F_K, s));
+        const int pk = SI(F_PIXEL, s);
+        rng.begin(A.seed_lo, A.seed_hi, (uint32_t)((pk >> 16) * A.nx + (pk & 0xffff)), (uint32_t)SI(F_K, s));
         uint32_t ndraw0;
         cls = extend<PAR, SMALL, MEDIA>(S, ps, A.max_depth, A.t_min, t, prim, rad, rng, ndraw0);
         if (cls == TPT_EXT_DONE) {
@@ -333,7 +339,8 @@ __global__ void __launch_bounds__(TPT_WAVE_THREADS, TPT_WAVE_MIN_BLOCKS) render_
             ps.T = mk(SF(F_TX, s), SF(F_TY, s), SF(F_TZ, s));
             ps.depth = SI(F_DEPTH, s);
             Rng rng;
-            rng.begin(A.seed_lo, A.seed_hi, (uint32_t)SI(F_PIXEL, s), (uint32_t)SI(F_K, s));
+            const int pk = SI(F_PIXEL, s);
+            rng.begin(A.seed_lo, A.seed_hi, (uint32_t)((pk >> 16) * A.nx + (pk & 0xffff)), (uint32_t)SI(F_K, s));
             bool alive = shade<PAR>(S, ps, rng, SI(F_HPRIM, s), SF(F_HT, s), MEDIA ? (uint32_t)SI(F_NDRAW, s) : 0u);
             if (alive) {
               SF(F_OX, s) = ps.ray.o.x; SF(F_OY, s) = ps.ray.o.y; SF(F_OZ, s) = ps.ray.o.z;
@@ -398,12 +405,12 @@ __global__ void __launch_bounds__(TPT_WAVE_THREADS, TPT_WAVE_MIN_BLOCKS) render_
                 if (px < A.nx && py < A.ny) {
                   need = false;
                   have_bin = true;
-                  pixel = py * A.nx + px;
+                  pixel = px | (py << 16); // packed: no division when the camera ray is generated
                   k = A.range_bounds[range];
                   k_end = A.range_bounds[range + 1];
                   SI(F_PIXEL, s) = pixel;
                   SI(F_KEND, s) = k_end;
-                  SI(F_ACCIDX, s) = (int)(range * (unsigned)(A.nx * A.ny) + (unsigned)pixel);
+                  SI(F_ACCIDX, s) = (int)(range * (unsigned)(A.nx * A.ny) + (unsigned)(py * A.nx + px));
                   SF(F_AX, s) = 0.f;
                   SF(F_AY, s) = 0.f;
                   SF(F_AZ, s) = 0.f;
@@ -414,8 +421,8 @@ __global__ void __launch_bounds__(TPT_WAVE_THREADS, TPT_WAVE_MIN_BLOCKS) render_
           if (mine) {
             if (have_bin) {
               Rng rng;
-              rng.begin(A.seed_lo, A.seed_hi, (uint32_t)pixel, (uint32_t)k);
-              const int py = pixel / A.nx, px = pixel - py * A.nx;
+              const int py = pixel >> 16, px = pixel & 0xffff;
+              rng.begin(A.seed_lo, A.seed_hi, (uint32_t)(py * A.nx + px), (uint32_t)k);
               Ray r = camera_sample<PAR>(A.cam, px, py, A.nx, A.ny, rng);
               // A camera ray that cannot hit the scene's bounds (64 % of the headline frame looks past
               // the box) ends its path right here -- world->hit is false for it -- and the lane draws
@@ -430,7 +437,7 @@ __global__ void __launch_bounds__(TPT_WAVE_THREADS, TPT_WAVE_MIN_BLOCKS) render_
                   n_paths++;
                   n_rays++;
                   k++;
-                  rng.begin(A.seed_lo, A.seed_hi, (uint32_t)pixel, (uint32_t)k);
+                  rng.begin(A.seed_lo, A.seed_hi, (uint32_t)(py * A.nx + px), (uint32_t)k);
                   r = camera_sample<PAR>(A.cam, px, py, A.nx, A.ny, rng);
                 }
               }
