@@ -1134,7 +1134,28 @@ int tpt_scene_create(const tpt_scene_desc *d, int device, tpt_scene **out) {
   L.off_fbvh = words();
   append(blob, fb.nodes.data(), fb.nodes.size());
   L.off_fleaf = words();
-  append(blob, fb.leaf_prims.data(), fb.leaf_prims.size());
+  {
+    // leaf records in leaf order, 3 float4 each (read by closest_hit_fbvh):
+    //   q0 = primitive words p[0..3]; q1 = {kind | exact << 8, primitive id, chain, rect k or time0};
+    //   q2 = moving sphere {center1, time1}
+    std::vector<float> rec(fb.leaf_prims.size() * 12, 0.f);
+    for (size_t i = 0; i < fb.leaf_prims.size(); i++) {
+      const int32_t id = fb.leaf_prims[i];
+      const tpt_prim &p = d->prims[id];
+      float *q = &rec[i * 12];
+      std::memcpy(q, p.p, 16);
+      const bool sph = p.kind == TPT_PRIM_SPHERE || p.kind == TPT_PRIM_MOVING_SPHERE;
+      int32_t kf = p.kind | (sph && p.p[3] >= 500.0f ? 0x100 : 0); // huge "wall" spheres: exact roots
+      std::memcpy(q + 4, &kf, 4);
+      std::memcpy(q + 5, &id, 4);
+      std::memcpy(q + 6, &p.chain, 4);
+      q[7] = p.kind == TPT_PRIM_MOVING_SPHERE ? p.p[7] : p.p[4];
+      if (p.kind == TPT_PRIM_MOVING_SPHERE) {
+        q[8] = p.p[4]; q[9] = p.p[5]; q[10] = p.p[6]; q[11] = p.p[8];
+      }
+    }
+    append(blob, rec.data(), rec.size());
+  }
   L.n_fbvh = (int)(fb.nodes.size() / 16);
   L.fbvh_time_ok = 1;
   s->fbvh_has_moving = fb.has_moving;

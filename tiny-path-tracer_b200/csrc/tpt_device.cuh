@@ -683,9 +683,32 @@ TPT_DEV bool closest_hit_uniform(const SceneView &S, const Ray &r, float tmin, f
 // Closest hit is independent of the acceleration structure (ties aside), so the estimator is
 // unchanged; PARITY mode keeps replaying the reference's tree.
 // ------------------------------------------------------------------------------------------
+// ordinary spheres in FAST mode: contracted discriminant of the half-b form, MUFU roots
+TPT_DEV bool sphere_test_quick(V3 center, float radius, const XRay &x, float tmin, float tmax, float &t) {
+  const V3 oc = x.o - center;
+  const float a = dot(x.d, x.d), hb = dot(oc, x.d), c = dot(oc, oc) - radius * radius;
+  const float disc = hb * hb - a * c;
+  if (disc > 0) {
+    const float sq = sqrtf(disc), inv = 1.0f / a;
+    float temp = (-hb - sq) * inv;
+    if (temp < tmax && temp > tmin) {
+      t = temp;
+      return true;
+    }
+    temp = (-hb + sq) * inv;
+    if (temp < tmax && temp > tmin) {
+      t = temp;
+      return true;
+    }
+  }
+  return false;
+}
+
+// "while-while" traversal: every lane first descends to its next leaf, the warp reconverges, and
+// then the leaf tests run together (the one-loop form ran them at 3-4 active lanes per warp).
 TPT_DEV bool closest_hit_fbvh(const SceneView &S, const Ray &r, float tmin, float tmax, float &t_out, int &prim_out) {
   const float4 *N = S.blob + S.L->off_fbvh;
-  const int *leaf_prims = reinterpret_cast<const int *>(S.blob + S.L->off_fleaf);
+  const float4 *LF = S.blob + S.L->off_fleaf;
   const float ix = 1.0f / r.d.x, iy = 1.0f / r.d.y, iz = 1.0f / r.d.z;
   const float ox = -r.o.x * ix, oy = -r.o.y * iy, oz = -r.o.z * iz; // t = p * inv + (-o * inv)
   XRay x;
@@ -694,10 +717,10 @@ TPT_DEV bool closest_hit_fbvh(const SceneView &S, const Ray &r, float tmin, floa
   int best_prim = -1;
   int stack[32];
   int sp = 0;
+  const int DONE = 0x7fffffff;
   int node = 0;
-  for (;;) {
-    int next = -1; // inner node to descend into without touching the stack
-    if (node >= 0) {
+  while (node != DONE) {
+    while ((unsigned)node < (unsigned)DONE) {
       const float4 a = N[4 * node], b = N[4 * node + 1], c = N[4 * node + 2], d = N[4 * node + 3];
       // child 0: lo = (a.x,a.y,a.z) hi = (a.w,b.x,b.y) ; child 1: lo = (b.z,b.w,c.x) hi = (c.y,c.z,c.w)
       float t0x = fmaf(a.x, ix, ox), t1x = fmaf(a.w, ix, ox);
@@ -715,26 +738,39 @@ TPT_DEV bool closest_hit_fbvh(const SceneView &S, const Ray &r, float tmin, floa
       if (h0 && h1) {
         if (n1 < n0) { int t = i0; i0 = i1; i1 = t; } // i0 = nearer
         stack[sp++] = i1;
-        next = i0;
-      } else if (h0) next = i0;
-      else if (h1) next = i1;
-      else next = sp > 0 ? stack[--sp] : 0x7fffffff;
-    } else {
-      // leaf: ~node = first << 3 | (count - 1)
-      const int code = ~node, first = code >> 3, count = (code & 7) + 1;
-      for (int k = 0; k < count; k++) {
-        const int prim = leaf_prims[first + k];
-        to_chain<false>(S, r, __float_as_int(S.blob[S.L->off_prims + 4 * prim].z), x);
+        node = i0;
+      } else if (h0) node = i0;
+      else if (h1) node = i1;
+      else node = sp > 0 ? stack[--sp] : DONE;
+    }
+    if (node < 0) {
+      // leaf: ~node = first << 3 | (count - 1); records of 3 float4 (tpt_api.cu, off_fleaf)
+      const int code = ~node, count = (code & 7) + 1;
+      const float4 *Q = LF + 3 * (code >> 3);
+      for (int k = 0; k < count; k++, Q += 3) {
+        const float4 g = Q[0], h = Q[1];
+        const int kf = __float_as_int(h.x), kind = kf & 0xff;
+        to_chain<false>(S, r, __float_as_int(h.z), x);
         float t;
-        if (prim_test<false>(S, prim, x, r.time, tmin, best, t)) {
+        bool hit;
+        if (kind <= TPT_PRIM_MOVING_SPHERE) {
+          V3 cen = mk(g.x, g.y, g.z);
+          if (kind == TPT_PRIM_MOVING_SPHERE) {
+            const float4 m = Q[2];
+            cen = moving_center(g, make_float4(m.x, m.y, m.z, h.w), make_float4(m.w, 0.f, 0.f, 0.f), r.time);
+          }
+          hit = (kf & 0x100) ? sphere_test<false, true>(cen, g.w, x, tmin, best, t)
+                             : sphere_test_quick(cen, g.w, x, tmin, best, t);
+        } else {
+          hit = rect_test<false>(kind - TPT_PRIM_XY_RECT, g, h.w, x, tmin, best, t);
+        }
+        if (hit) {
           best = t;
-          best_prim = prim;
+          best_prim = __float_as_int(h.y);
         }
       }
-      next = sp > 0 ? stack[--sp] : 0x7fffffff;
+      node = sp > 0 ? stack[--sp] : DONE;
     }
-    if (next == 0x7fffffff) break;
-    node = next;
   }
   t_out = best;
   prim_out = best_prim;
