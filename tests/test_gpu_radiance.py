@@ -185,6 +185,9 @@ def test_oneweek_final_vs_port(T, gpu):
         res = sc.render(cam, p)
         n_bad, n, worst = outliers(res.sum_rgb, ref, c["ns"])
         assert n_bad == 0, (kernel, n_bad, worst)
-    fast = sc.render(cam, T.make_params(c["nx"], c["ny"], 256, c["depth"], mode=T.MODE_FAST, seed=5))
     slow = sc.render(cam, T.make_params(c["nx"], c["ny"], 256, c["depth"], mode=T.MODE_PARITY, seed=6))
-    assert abs(fast.sum_rgb.mean() - slow.sum_rgb.mean()) < 0.03 * slow.sum_rgb.mean()
+    # FAST: megakernel, and the wavefront kernel's SAH-BVH + media build (dynamic ray hand-out)
+    for kernel in (T.KERNEL_MEGA, T.KERNEL_WAVEFRONT):
+        fast = sc.render(cam, T.make_params(c["nx"], c["ny"], 256, c["depth"], mode=T.MODE_FAST, seed=5, kernel=kernel))
+        assert abs(fast.sum_rgb.mean() - slow.sum_rgb.mean()) < 0.03 * slow.sum_rgb.mean(), kernel
+        assert fast.stats["paths"] == c["nx"] * c["ny"] * 256

@@ -720,8 +720,9 @@ int run_plan(tpt_scene *s, Plan &plan, bool want_sum, bool want_rgb8, bool want_
   int bps = 0;
   const bool media = s->n_mediums > 0;
   const bool small = s->small.enabled != 0 && !media;
+  const bool trace = TPT_TRACE_ENABLE && !plan.parity && media && A.scene.n_fbvh > 0 && A.scene.fbvh_time_ok; // SAH BVH + media: 2-CTA variant with dynamic ray hand-out
   if (plan.wavefront)
-    CK(plan.parity ? wave_occupancy_parity(A, small, s->use_smem, media, &bps) : wave_occupancy_fast(A, small, s->use_smem, media, &bps));
+    CK(plan.parity ? wave_occupancy_parity(A, small, s->use_smem, media, trace, &bps) : wave_occupancy_fast(A, small, s->use_smem, media, trace, &bps));
   else
     CK(plan.parity ? mega_occupancy_parity(s->use_smem, small, media, smem, &bps)
                    : mega_occupancy_fast(s->use_smem, small, media, smem, &bps));
@@ -732,7 +733,7 @@ int run_plan(tpt_scene *s, Plan &plan, bool want_sum, bool want_rgb8, bool want_
   CK(cudaMemsetAsync(s->d_counters, 0, 8 * sizeof(unsigned long long), s->stream));
   CK(cudaEventRecord(s->ev[0], s->stream));
   if (plan.wavefront)
-    CK(plan.parity ? launch_wave_parity(A, small, s->use_smem, media, plan.blocks, s->stream) : launch_wave_fast(A, small, s->use_smem, media, plan.blocks, s->stream));
+    CK(plan.parity ? launch_wave_parity(A, small, s->use_smem, media, trace, plan.blocks, s->stream) : launch_wave_fast(A, small, s->use_smem, media, trace, plan.blocks, s->stream));
   else
     CK(plan.parity ? launch_mega_parity(A, s->use_smem, small, media, plan.blocks, s->stream)
                    : launch_mega_fast(A, s->use_smem, small, media, plan.blocks, s->stream));
@@ -853,15 +854,16 @@ int launch_batch(tpt_scene *s, const tpt_camera *cam, const tpt_render_params *p
   int bps = 0;
   const bool media = s->n_mediums > 0;
   const bool small = s->small.enabled != 0 && !media;
+  const bool trace = TPT_TRACE_ENABLE && !plan.parity && media && A.scene.n_fbvh > 0 && A.scene.fbvh_time_ok; // SAH BVH + media: 2-CTA variant with dynamic ray hand-out
   if (plan.wavefront)
-    CK(plan.parity ? wave_occupancy_parity(A, small, s->use_smem, media, &bps) : wave_occupancy_fast(A, small, s->use_smem, media, &bps));
+    CK(plan.parity ? wave_occupancy_parity(A, small, s->use_smem, media, trace, &bps) : wave_occupancy_fast(A, small, s->use_smem, media, trace, &bps));
   else
     CK(plan.parity ? mega_occupancy_parity(s->use_smem, small, media, smem, &bps)
                    : mega_occupancy_fast(s->use_smem, small, media, smem, &bps));
   if (bps < 1) return fail(TPT_ERR_CUDA, "render kernel does not fit on an SM");
   int blocks = bps * s->prop.multiProcessorCount;
   if (plan.wavefront)
-    CK(plan.parity ? launch_wave_parity(A, small, s->use_smem, media, blocks, s->stream) : launch_wave_fast(A, small, s->use_smem, media, blocks, s->stream));
+    CK(plan.parity ? launch_wave_parity(A, small, s->use_smem, media, trace, blocks, s->stream) : launch_wave_fast(A, small, s->use_smem, media, trace, blocks, s->stream));
   else
     CK(plan.parity ? launch_mega_parity(A, s->use_smem, small, media, blocks, s->stream)
                    : launch_mega_fast(A, s->use_smem, small, media, blocks, s->stream));

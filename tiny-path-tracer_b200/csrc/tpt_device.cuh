@@ -706,21 +706,29 @@ TPT_DEV bool sphere_test_quick(V3 center, float radius, const XRay &x, float tmi
 
 // "while-while" traversal: every lane first descends to its next leaf, the warp reconverges, and
 // then the leaf tests run together (the one-loop form ran them at 3-4 active lanes per warp).
-TPT_DEV bool closest_hit_fbvh(const SceneView &S, const Ray &r, float tmin, float tmax, float &t_out, int &prim_out) {
-  const float4 *N = S.blob + S.L->off_fbvh;
-  const float4 *LF = S.blob + S.L->off_fleaf;
-  const float ix = 1.0f / r.d.x, iy = 1.0f / r.d.y, iz = 1.0f / r.d.z;
-  const float ox = -r.o.x * ix, oy = -r.o.y * iy, oz = -r.o.z * iz; // t = p * inv + (-o * inv)
-  XRay x;
-  x.chain = -1;
-  float best = tmax;
-  int best_prim = -1;
-  int stack[32];
-  int sp = 0;
-  const int DONE = 0x7fffffff;
-  int node = 0;
-  while (node != DONE) {
-    while ((unsigned)node < (unsigned)DONE) {
+// The state is a struct so that a kernel can interleave traversal steps of many rays with other
+// work (render_mega_bvh_kernel postpones shading until enough lanes of the warp wait for it).
+#define TPT_FBVH_DONE 0x7fffffff
+#define TPT_FBVH_STACK 32
+struct FbvhTrav {
+  float ix, iy, iz, ox, oy, oz; // t = p * inv + (-o * inv)
+  float best;
+  int best_prim, node, sp;
+  // the node stack is a separate local array handed to step(): inside the struct its dynamic
+  // indexing kept the scalar members in local memory too (-9 % / -16 % measured)
+  TPT_DEV void start(const Ray &r, float tmax) {
+    ix = 1.0f / r.d.x; iy = 1.0f / r.d.y; iz = 1.0f / r.d.z;
+    ox = -r.o.x * ix; oy = -r.o.y * iy; oz = -r.o.z * iz;
+    best = tmax;
+    best_prim = -1;
+    node = 0;
+    sp = 0;
+  }
+  TPT_DEV bool done() const { return node == TPT_FBVH_DONE; }
+  // descend to the next leaf (or run out of nodes), then test that leaf's primitives
+  TPT_DEV void step(const SceneView &S, const Ray &r, float tmin, int *stack) {
+    const float4 *N = S.blob + S.L->off_fbvh;
+    while ((unsigned)node < (unsigned)TPT_FBVH_DONE) {
       const float4 a = N[4 * node], b = N[4 * node + 1], c = N[4 * node + 2], d = N[4 * node + 3];
       // child 0: lo = (a.x,a.y,a.z) hi = (a.w,b.x,b.y) ; child 1: lo = (b.z,b.w,c.x) hi = (c.y,c.z,c.w)
       float t0x = fmaf(a.x, ix, ox), t1x = fmaf(a.w, ix, ox);
@@ -741,12 +749,14 @@ TPT_DEV bool closest_hit_fbvh(const SceneView &S, const Ray &r, float tmin, floa
         node = i0;
       } else if (h0) node = i0;
       else if (h1) node = i1;
-      else node = sp > 0 ? stack[--sp] : DONE;
+      else node = sp > 0 ? stack[--sp] : TPT_FBVH_DONE;
     }
     if (node < 0) {
       // leaf: ~node = first << 3 | (count - 1); records of 3 float4 (tpt_api.cu, off_fleaf)
       const int code = ~node, count = (code & 7) + 1;
-      const float4 *Q = LF + 3 * (code >> 3);
+      const float4 *Q = S.blob + S.L->off_fleaf + 3 * (code >> 3);
+      XRay x;
+      x.chain = -1;
       for (int k = 0; k < count; k++, Q += 3) {
         const float4 g = Q[0], h = Q[1];
         const int kf = __float_as_int(h.x), kind = kf & 0xff;
@@ -769,12 +779,19 @@ TPT_DEV bool closest_hit_fbvh(const SceneView &S, const Ray &r, float tmin, floa
           best_prim = __float_as_int(h.y);
         }
       }
-      node = sp > 0 ? stack[--sp] : DONE;
+      node = sp > 0 ? stack[--sp] : TPT_FBVH_DONE;
     }
   }
-  t_out = best;
-  prim_out = best_prim;
-  return best_prim >= 0;
+};
+
+TPT_DEV bool closest_hit_fbvh(const SceneView &S, const Ray &r, float tmin, float tmax, float &t_out, int &prim_out) {
+  FbvhTrav tv;
+  int stack[TPT_FBVH_STACK];
+  tv.start(r, tmax);
+  while (!tv.done()) tv.step(S, r, tmin, stack);
+  t_out = tv.best;
+  prim_out = tv.best_prim;
+  return tv.best_prim >= 0;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1224,33 +1241,20 @@ template <bool PAR> TPT_DEV V3 background_radiance(const SceneView &S, const Ray
 #define TPT_EXT_DONE (-1)
 // MEDIA is a compile-time switch: only kernels instantiated for scenes with participating media
 // carry the stream through world->hit (taking the Rng's address costs registers everywhere else).
-template <bool PAR, bool SMALL, bool MEDIA>
-TPT_DEV int extend(const SceneView &S, const PathState &ps, int max_depth, float t_min, float &t, int &prim,
-                   V3 &radiance, Rng &g, uint32_t &ndraw_out) {
-  // scenes with participating media draw inside world->hit: the stage's stream starts here
-  const bool media = MEDIA;
-  Rng *gp = nullptr;
-  if (MEDIA) {
-    g.set_stage((uint32_t)ps.depth + 1u);
-    gp = &g;
-  }
-  bool any_hit;
-  if (PAR) {
-    any_hit = closest_hit<PAR>(S, ps.ray, t_min, FLT_MAX, t, prim, gp);
-  } else {
-    if (SMALL) any_hit = closest_hit_uniform(S, ps.ray, t_min, FLT_MAX, t, prim);
-    else if (S.L->n_fbvh > 0 && S.L->fbvh_time_ok) any_hit = closest_hit_fbvh(S, ps.ray, t_min, FLT_MAX, t, prim);
-    else any_hit = walk_range<false, false>(S, ps.ray, 0, S.L->n_nodes, t_min, FLT_MAX, t, prim, nullptr);
-    if (media) {
-      if (!any_hit) {
-        t = FLT_MAX;
-        prim = -1;
-      }
-      fast_media_pass(S, ps.ray, t_min, t, prim, gp);
-      any_hit = prim >= 0;
+// Everything extend() does once the closest surface hit (any_hit, t, prim) is known: the media
+// pass of FAST mode, the miss / lamp / absorber / depth-limit endings, else the material kind.
+template <bool PAR, bool MEDIA>
+TPT_DEV int extend_finish(const SceneView &S, const PathState &ps, int max_depth, float t_min, bool any_hit, float &t,
+                          int &prim, V3 &radiance, Rng &g, uint32_t &ndraw_out) {
+  if (!PAR && MEDIA) {
+    if (!any_hit) {
+      t = FLT_MAX;
+      prim = -1;
     }
+    fast_media_pass(S, ps.ray, t_min, t, prim, &g);
+    any_hit = prim >= 0;
   }
-  ndraw_out = media ? g.ndraw : 0u;
+  ndraw_out = MEDIA ? g.ndraw : 0u;
   radiance = mk(0, 0, 0);
   if (!any_hit) {
     radiance = background_radiance<PAR>(S, ps.ray, ps.T); // black at HEAD, or the commented gradient
@@ -1270,6 +1274,26 @@ TPT_DEV int extend(const SceneView &S, const PathState &ps, int max_depth, float
   }
   if (mkind == TPT_MAT_ABSORBER || mkind == TPT_MAT_ISOTROPIC || ps.depth >= max_depth) return TPT_EXT_DONE; // emitted == 0
   return mkind;
+}
+
+template <bool PAR, bool SMALL, bool MEDIA>
+TPT_DEV int extend(const SceneView &S, const PathState &ps, int max_depth, float t_min, float &t, int &prim,
+                   V3 &radiance, Rng &g, uint32_t &ndraw_out) {
+  // scenes with participating media draw inside world->hit: the stage's stream starts here
+  Rng *gp = nullptr;
+  if (MEDIA) {
+    g.set_stage((uint32_t)ps.depth + 1u);
+    gp = &g;
+  }
+  bool any_hit;
+  if (PAR) {
+    any_hit = closest_hit<PAR>(S, ps.ray, t_min, FLT_MAX, t, prim, gp);
+  } else {
+    if (SMALL) any_hit = closest_hit_uniform(S, ps.ray, t_min, FLT_MAX, t, prim);
+    else if (S.L->n_fbvh > 0 && S.L->fbvh_time_ok) any_hit = closest_hit_fbvh(S, ps.ray, t_min, FLT_MAX, t, prim);
+    else any_hit = walk_range<false, false>(S, ps.ray, 0, S.L->n_nodes, t_min, FLT_MAX, t, prim, nullptr);
+  }
+  return extend_finish<PAR, MEDIA>(S, ps, max_depth, t_min, any_hit, t, prim, radiance, g, ndraw_out);
 }
 
 // shade(): material::scatter + the mixture-pdf step of color() for the hit (prim, t).

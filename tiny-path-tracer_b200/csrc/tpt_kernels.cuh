@@ -68,6 +68,55 @@ __global__ void __launch_bounds__(128) intersect_kernel(const __grid_constant__ 
   A.out[idx] = out;
 }
 
+// One (pixel, sample range) bin per lane from the global work counter, warp-aggregated: the lanes
+// that `need` one share a single atomicAdd. A finished bin is stored first (one store per bin).
+struct LaneBin {
+  bool have_bin, exhausted;
+  int px, py, k, k_end;
+  unsigned acc_index;
+  V3 acc;
+};
+TPT_DEV void lane_bin_refill(const RenderArgs &A, LaneBin &B, bool need, unsigned lane, unsigned bins_per_tile) {
+  const unsigned FULL = 0xffffffffu;
+  if (need && B.have_bin) { // bin finished: one store per (pixel, range)
+    float *o = A.acc + (size_t)B.acc_index * 3;
+    o[0] = B.acc.x;
+    o[1] = B.acc.y;
+    o[2] = B.acc.z;
+    B.have_bin = false;
+  }
+  unsigned m = __ballot_sync(FULL, need);
+  if (m) {
+    unsigned long long base = 0;
+    int leader = __ffs(m) - 1;
+    if ((int)lane == leader) base = atomicAdd(A.counters + 0, (unsigned long long)__popc(m));
+    base = __shfl_sync(FULL, base, leader);
+    if (need) {
+      unsigned long long b = base + __popc(m & ((1u << lane) - 1u));
+      if (b >= A.n_bins) {
+        B.exhausted = true;
+      } else {
+        unsigned bb = (unsigned)b;
+        unsigned tile_local = bb / bins_per_tile;
+        unsigned rem = bb - tile_local * bins_per_tile;
+        unsigned range = rem / (unsigned)(TPT_TILE * TPT_TILE);
+        unsigned pit = rem - range * (unsigned)(TPT_TILE * TPT_TILE);
+        unsigned tile = (unsigned)A.part_index + tile_local * (unsigned)A.part_count;
+        unsigned ty = tile / (unsigned)A.tiles_x, tx = tile - ty * (unsigned)A.tiles_x;
+        B.px = (int)(tx * TPT_TILE + (pit & (TPT_TILE - 1)));
+        B.py = (int)(ty * TPT_TILE + (pit / TPT_TILE));
+        if (B.px < A.nx && B.py < A.ny) {
+          B.have_bin = true;
+          B.k = A.range_bounds[range];
+          B.k_end = A.range_bounds[range + 1];
+          B.acc = mk(0, 0, 0);
+          B.acc_index = range * (unsigned)(A.nx * A.ny) + (unsigned)(B.py * A.nx + B.px);
+        }
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // Persistent megakernel with per-lane path regeneration.
 //
@@ -90,63 +139,29 @@ __global__ void __launch_bounds__(TPT_MEGA_THREADS) render_mega_kernel(const __g
   const unsigned FULL = 0xffffffffu;
   const unsigned lane = threadIdx.x & 31u;
 
-  bool have_bin = false, exhausted = false, active = false;
-  int px = 0, py = 0, k = 0, k_end = 0;
-  unsigned acc_index = 0;
-  V3 acc = mk(0, 0, 0);
+  bool active = false;
+  LaneBin B;
+  B.have_bin = false;
+  B.exhausted = false;
+  B.px = B.py = B.k = B.k_end = 0;
+  B.acc_index = 0;
+  B.acc = mk(0, 0, 0);
   PathState ps;
   Rng rng;
   unsigned long long n_rays = 0, n_nan = 0, n_paths = 0;
   const unsigned bins_per_tile = (unsigned)(TPT_TILE * TPT_TILE) * (unsigned)A.n_ranges;
 
   for (;;) {
-    bool need = !active && !exhausted && (!have_bin || k >= k_end);
-    if (need && have_bin) { // bin finished: one store per (pixel, range)
-      float *o = A.acc + (size_t)acc_index * 3;
-      o[0] = acc.x;
-      o[1] = acc.y;
-      o[2] = acc.z;
-      have_bin = false;
-    }
-    unsigned m = __ballot_sync(FULL, need);
-    if (m) {
-      unsigned long long base = 0;
-      int leader = __ffs(m) - 1;
-      if ((int)lane == leader) base = atomicAdd(A.counters + 0, (unsigned long long)__popc(m));
-      base = __shfl_sync(FULL, base, leader);
-      if (need) {
-        unsigned long long b = base + __popc(m & ((1u << lane) - 1u));
-        if (b >= A.n_bins) {
-          exhausted = true;
-        } else {
-          unsigned bb = (unsigned)b;
-          unsigned tile_local = bb / bins_per_tile;
-          unsigned rem = bb - tile_local * bins_per_tile;
-          unsigned range = rem / (unsigned)(TPT_TILE * TPT_TILE);
-          unsigned pit = rem - range * (unsigned)(TPT_TILE * TPT_TILE);
-          unsigned tile = (unsigned)A.part_index + tile_local * (unsigned)A.part_count;
-          unsigned ty = tile / (unsigned)A.tiles_x, tx = tile - ty * (unsigned)A.tiles_x;
-          px = (int)(tx * TPT_TILE + (pit & (TPT_TILE - 1)));
-          py = (int)(ty * TPT_TILE + (pit / TPT_TILE));
-          if (px < A.nx && py < A.ny) {
-            have_bin = true;
-            k = A.range_bounds[range];
-            k_end = A.range_bounds[range + 1];
-            acc = mk(0, 0, 0);
-            acc_index = range * (unsigned)(A.nx * A.ny) + (unsigned)(py * A.nx + px);
-          }
-        }
-      }
-    }
-    if (!active && have_bin && k < k_end) { // next sample of this lane's pixel
-      rng.begin(A.seed_lo, A.seed_hi, (uint32_t)(py * A.nx + px), (uint32_t)k);
-      ps.ray = camera_sample<PAR>(A.cam, px, py, A.nx, A.ny, rng);
+    lane_bin_refill(A, B, !active && !B.exhausted && (!B.have_bin || B.k >= B.k_end), lane, bins_per_tile);
+    if (!active && B.have_bin && B.k < B.k_end) { // next sample of this lane's pixel
+      rng.begin(A.seed_lo, A.seed_hi, (uint32_t)(B.py * A.nx + B.px), (uint32_t)B.k);
+      ps.ray = camera_sample<PAR>(A.cam, B.px, B.py, A.nx, A.ny, rng);
       ps.T = mk(1.f, 1.f, 1.f);
       ps.depth = 0;
       active = true;
       n_paths++;
     }
-    if (__all_sync(FULL, !active && exhausted)) break;
+    if (__all_sync(FULL, !active && B.exhausted)) break;
     if (active) {
       V3 rad;
       n_rays++;
@@ -155,11 +170,11 @@ __global__ void __launch_bounds__(TPT_MEGA_THREADS) render_mega_kernel(const __g
         bool nan_any = isnan(rad.x) || isnan(rad.y) || isnan(rad.z) || isnan(ps.T.x) ||
                        isnan(ps.T.y) || isnan(ps.T.z);
         if (nan_any) n_nan++;
-        acc.x += isnan(rad.x) ? 0.f : rad.x;
-        acc.y += isnan(rad.y) ? 0.f : rad.y;
-        acc.z += isnan(rad.z) ? 0.f : rad.z;
+        B.acc.x += isnan(rad.x) ? 0.f : rad.x;
+        B.acc.y += isnan(rad.y) ? 0.f : rad.y;
+        B.acc.z += isnan(rad.z) ? 0.f : rad.z;
         active = false;
-        k++;
+        B.k++;
       }
     }
   }
@@ -204,10 +219,11 @@ __global__ void __launch_bounds__(TPT_MEGA_THREADS) render_mega_kernel(const __g
 // ------------------------------------------------------------------------------------------
 #define TPT_WAVE_NQ 4 // queues: 0 lambertian, 1 metal, 2 dielectric (= TPT_MAT_*), 3 generate
 
-template <bool PAR, bool SMALL, bool SMEM, bool MEDIA>
-__global__ void __launch_bounds__(TPT_WAVE_THREADS, TPT_WAVE_MIN_BLOCKS) render_wave_kernel(const __grid_constant__ RenderArgs A) {
+template <bool PAR, bool SMALL, bool SMEM, bool MEDIA, bool TRACE = false>
+__global__ void __launch_bounds__(TPT_WAVE_THREADS, TRACE ? TPT_TRACE_MIN_BLOCKS : TPT_WAVE_MIN_BLOCKS)
+render_wave_kernel(const __grid_constant__ RenderArgs A) {
   extern __shared__ float4 sblob[];
-  constexpr int NSLOT = TPT_WAVE_SLOTS;
+  constexpr int NSLOT = TRACE ? TPT_TRACE_SLOTS : TPT_WAVE_SLOTS;
   constexpr int NWARP = TPT_WAVE_THREADS / 32;
   // structure-of-arrays slot state: field f of slot s at sf[f * NSLOT + s]
   enum { F_OX, F_OY, F_OZ, F_DX, F_DY, F_DZ, F_TIME, F_TX, F_TY, F_TZ, F_AX, F_AY, F_AZ,
@@ -227,6 +243,7 @@ __global__ void __launch_bounds__(TPT_WAVE_THREADS, TPT_WAVE_MIN_BLOCKS) render_
   S.small = &A.small;
   __shared__ unsigned long long q_packed[2];
   __shared__ int n_idle;
+  __shared__ int trace_next; // TRACE: next slot whose ray nobody has taken yet
 #define SF(f, s) sf[(f) * NSLOT + (s)]
 #define SI(f, s) si[(f) * NSLOT + (s)]
 #define QUEUE(par, q) (queue + ((par) * TPT_WAVE_NQ + (q)) * NSLOT)
@@ -249,12 +266,58 @@ __global__ void __launch_bounds__(TPT_WAVE_THREADS, TPT_WAVE_MIN_BLOCKS) render_
     q_packed[0] = (unsigned long long)NSLOT << 48; // everything starts in GENERATE
     q_packed[1] = 0;
     n_idle = 0;
+    trace_next = 0;
   }
   __syncthreads();
 
   for (int par = 0;; par ^= 1) {
     // ------------------------------------------------------------------ extend
     if (tid == 0) q_packed[par ^ 1] = 0; // next iteration's counters (nobody touches them before the barrier)
+    if (TRACE) {
+      // Closest hits through the SAH BVH, rays handed out dynamically: a lane that finishes its ray
+      // takes the next untraced slot from the CTA-wide counter instead of idling until the longest
+      // traversal of its warp ends. Results go to F_HT / F_HPRIM; the rest of extend() follows below.
+      // Measured (BVH scenes): the hand-out itself is worth 2-4 %; the variant's gain on
+      // oneweek_final (+15 %) comes from running 2 CTAs/SM at 128 registers (no spills around the
+      // media pass). random_scene is faster on the plain 3-CTA form, so only media scenes come here.
+      FbvhTrav tv;
+      int stack[TPT_FBVH_STACK];
+      tv.node = TPT_FBVH_DONE;
+      int ts = -1;
+      Ray tr;
+      tr.o = tr.d = mk(0, 0, 0);
+      tr.time = 0.f;
+      bool dry = false;
+      for (;;) {
+        const bool need = tv.done();
+        if (need && ts >= 0) {
+          SI(F_HPRIM, ts) = tv.best_prim;
+          SF(F_HT, ts) = tv.best;
+          ts = -1;
+        }
+        const unsigned m = __ballot_sync(FULL, need);
+        if (m && !dry) {
+          int base = 0;
+          const int leader = __ffs(m) - 1;
+          if ((int)lane == leader) base = atomicAdd(&trace_next, __popc(m));
+          base = __shfl_sync(FULL, base, leader);
+          if (base >= NSLOT) dry = true;
+          if (need) {
+            const int c = base + __popc(m & lt_mask);
+            if (c < NSLOT && SI(F_ACTIVE, c)) {
+              ts = c;
+              tr.o = mk(SF(F_OX, c), SF(F_OY, c), SF(F_OZ, c));
+              tr.d = mk(SF(F_DX, c), SF(F_DY, c), SF(F_DZ, c));
+              tr.time = SF(F_TIME, c);
+              tv.start(tr, FLT_MAX);
+            }
+          }
+        }
+        if (dry && __ballot_sync(FULL, !tv.done()) == 0u) break;
+        if (!tv.done()) tv.step(S, tr, A.t_min, stack);
+      }
+      __syncthreads();
+    }
     for (int s0 = warp * 32; s0 < NSLOT; s0 += TPT_WAVE_THREADS) {
       const int s = s0 + (int)lane;
       int cls = -2; // -2: nothing to do
@@ -273,7 +336,14 @@ __global__ void __launch_bounds__(TPT_WAVE_THREADS, TPT_WAVE_MIN_BLOCKS) render_
         const int pk = SI(F_PIXEL, s);
         rng.begin(A.seed_lo, A.seed_hi, (uint32_t)((pk >> 16) * A.nx + (pk & 0xffff)), (uint32_t)SI(F_K, s));
         uint32_t ndraw0;
-        cls = extend<PAR, SMALL, MEDIA>(S, ps, A.max_depth, A.t_min, t, prim, rad, rng, ndraw0);
+        if (TRACE) {
+          t = SF(F_HT, s);
+          prim = SI(F_HPRIM, s);
+          if (MEDIA) rng.set_stage((uint32_t)ps.depth + 1u);
+          cls = extend_finish<PAR, MEDIA>(S, ps, A.max_depth, A.t_min, prim >= 0, t, prim, rad, rng, ndraw0);
+        } else {
+          cls = extend<PAR, SMALL, MEDIA>(S, ps, A.max_depth, A.t_min, t, prim, rad, rng, ndraw0);
+        }
         if (cls == TPT_EXT_DONE) {
           // col += de_nan(tmp): main.cpp:126, headers/utils.h:100-109
           if (isnan(rad.x) || isnan(rad.y) || isnan(rad.z)) n_nan++;
@@ -307,6 +377,7 @@ __global__ void __launch_bounds__(TPT_WAVE_THREADS, TPT_WAVE_MIN_BLOCKS) render_
     __syncthreads();
     // -------------------------------------------------------- shade + generate
     {
+      if (TRACE && tid == 0) trace_next = 0;
       const unsigned long long packed = q_packed[par];
       const int c0 = (int)(packed & 0xffffu), c1 = (int)((packed >> 16) & 0xffffu);
       const int c2 = (int)((packed >> 32) & 0xffffu), c3 = (int)((packed >> 48) & 0xffffu);
@@ -543,25 +614,32 @@ cudaError_t TPT_FN(launch_mega_)(const RenderArgs &A, bool smem, bool small, boo
 }
 
 typedef void (*wave_fn)(RenderArgs);
-static wave_fn wave_variant(bool small, bool smem, bool media) {
+// `trace` (FAST only): closest hits through the library's SAH BVH with dynamic ray hand-out; the
+// scene tables are read through L1 there and shared memory holds TPT_TRACE_SLOTS path slots.
+static wave_fn wave_variant(bool small, bool smem, bool media, bool trace) {
+#if !TPT_PAR
+  if (trace) return media ? render_wave_kernel<false, false, false, true, true> : render_wave_kernel<false, false, false, false, true>;
+#endif
+  (void)trace;
   if (media) return smem ? render_wave_kernel<TPT_PAR, false, true, true> : render_wave_kernel<TPT_PAR, false, false, true>;
   if (!smem) return render_wave_kernel<TPT_PAR, false, false, false>;
   return small ? render_wave_kernel<TPT_PAR, true, true, false> : render_wave_kernel<TPT_PAR, false, true, false>;
 }
-static size_t wave_smem_bytes(const RenderArgs &A, bool smem) {
+static size_t wave_smem_bytes(const RenderArgs &A, bool smem, bool trace) {
+  if (trace && !TPT_PAR) return (size_t)TPT_TRACE_SLOTS * (22 * 4 + 2 * TPT_WAVE_NQ * 2);
   return (smem ? (size_t)A.scene.blob_words * 16 : 0) + (size_t)TPT_WAVE_SLOTS * (22 * 4 + 2 * TPT_WAVE_NQ * 2);
 }
 
-cudaError_t TPT_FN(wave_occupancy_)(const RenderArgs &A, bool small, bool smem, bool media, int *blocks_per_sm) {
-  wave_fn k = wave_variant(small, smem, media);
-  size_t bytes = wave_smem_bytes(A, smem);
+cudaError_t TPT_FN(wave_occupancy_)(const RenderArgs &A, bool small, bool smem, bool media, bool trace, int *blocks_per_sm) {
+  wave_fn k = wave_variant(small, smem, media, trace);
+  size_t bytes = wave_smem_bytes(A, smem, trace);
   cudaError_t e = allow_smem(k, bytes);
   if (e != cudaSuccess) return e;
   return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k, TPT_WAVE_THREADS, bytes);
 }
 
-cudaError_t TPT_FN(launch_wave_)(const RenderArgs &A, bool small, bool smem, bool media, int blocks, cudaStream_t st) {
-  wave_variant(small, smem, media)<<<blocks, TPT_WAVE_THREADS, wave_smem_bytes(A, smem), st>>>(A);
+cudaError_t TPT_FN(launch_wave_)(const RenderArgs &A, bool small, bool smem, bool media, bool trace, int blocks, cudaStream_t st) {
+  wave_variant(small, smem, media, trace)<<<blocks, TPT_WAVE_THREADS, wave_smem_bytes(A, smem, trace), st>>>(A);
   return cudaGetLastError();
 }
 

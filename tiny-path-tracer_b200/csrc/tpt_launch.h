@@ -7,6 +7,15 @@
 #ifndef TPT_WAVE_SPLIT_GEN
 #define TPT_WAVE_SPLIT_GEN 1 // 1: generate runs as its own phase after shade (one more barrier, +8 % measured)
 #endif
+#ifndef TPT_TRACE_ENABLE
+#define TPT_TRACE_ENABLE 1
+#endif
+#ifndef TPT_TRACE_SLOTS
+#define TPT_TRACE_SLOTS 768    // path slots per CTA of the BVH ("trace") wavefront variant: 3 rays per lane to hand out
+#endif
+#ifndef TPT_TRACE_MIN_BLOCKS
+#define TPT_TRACE_MIN_BLOCKS 2 // 2 CTAs/SM: 128 registers for the traversal state, 2 x 78 KB of slots (more starves L1 of the BVH)
+#endif
 #ifndef TPT_WAVE_MIN_BLOCKS
 #define TPT_WAVE_MIN_BLOCKS 3 // __launch_bounds__ min blocks per SM: 80 registers, 3 CTAs (measured best)
 #endif
@@ -63,10 +72,11 @@ cudaError_t mega_occupancy_fast(bool smem, bool small, bool media, size_t smem_b
 cudaError_t launch_mega_parity(const RenderArgs &A, bool smem, bool small, bool media, int blocks, cudaStream_t st);
 cudaError_t launch_mega_fast(const RenderArgs &A, bool smem, bool small, bool media, int blocks, cudaStream_t st);
 // persistent wavefront variant (`smem`: scene tables staged in shared memory, else read through L1)
-cudaError_t wave_occupancy_parity(const RenderArgs &A, bool small, bool smem, bool media, int *blocks_per_sm);
-cudaError_t wave_occupancy_fast(const RenderArgs &A, bool small, bool smem, bool media, int *blocks_per_sm);
-cudaError_t launch_wave_parity(const RenderArgs &A, bool small, bool smem, bool media, int blocks, cudaStream_t st);
-cudaError_t launch_wave_fast(const RenderArgs &A, bool small, bool smem, bool media, int blocks, cudaStream_t st);
+// `trace` (FAST only): SAH-BVH scenes, rays handed out dynamically inside the extend phase
+cudaError_t wave_occupancy_parity(const RenderArgs &A, bool small, bool smem, bool media, bool trace, int *blocks_per_sm);
+cudaError_t wave_occupancy_fast(const RenderArgs &A, bool small, bool smem, bool media, bool trace, int *blocks_per_sm);
+cudaError_t launch_wave_parity(const RenderArgs &A, bool small, bool smem, bool media, bool trace, int blocks, cudaStream_t st);
+cudaError_t launch_wave_fast(const RenderArgs &A, bool small, bool smem, bool media, bool trace, int blocks, cudaStream_t st);
 cudaError_t launch_texture_probe_parity(const TextureProbeArgs &A, cudaStream_t st);
 cudaError_t launch_texture_probe_fast(const TextureProbeArgs &A, cudaStream_t st);
 cudaError_t launch_philox_probe(const uint32_t ctr[4], const uint32_t key[2], uint32_t *d_out, cudaStream_t st);
