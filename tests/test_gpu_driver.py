@@ -61,3 +61,43 @@ def test_driver_writes_reference_compatible_pictures(T, gpu, tmp_path):
         rmse = np.sqrt(np.mean((img.astype(np.float64) - ref) ** 2)) / 255.0
         assert rmse < 0.06, rmse  # 256 spp on both sides; the reference's row-correlated noise dominates
         assert abs(img.mean() - ref.mean()) < 0.03 * ref.mean()
+    # output stage without ImageMagick: img.jpg = the five pictures side by side
+    from PIL import Image
+    jpg = np.asarray(Image.open(tmp_path / "img.jpg")).astype(np.float64)
+    assert jpg.shape == (120, 5 * 120, 3) and "built-in JPEG writer" in out.stdout
+    panels = [img] + [read_p3(tmp_path / f"img_{k}.ppm") for k in range(4)]
+    want = np.concatenate(panels, axis=1)
+    assert np.sqrt(np.mean((jpg - want) ** 2)) < 6.0  # quality 92 on a noisy 256-spp render
+
+
+def test_driver_scene_camera_and_light_keys(T, gpu, tmp_path):
+    """scene, camera and light list chosen from config.ini instead of edits to main().
+    `lights = auto` samples the scene's own lamp only; the estimator stays unbiased up to the
+    reference's Q1 pdf convention, so the picture agrees with the reference-list render up to noise
+    (it is in fact the less noisy of the two). A binary PPM is written when [OUTPUT] ppm = p6."""
+    from PIL import Image
+    exe = os.path.join(T.LIB_DIR, "Path_tracer_b200")
+    base = CONFIG.replace("allow_bonus_pic = 1", "allow_bonus_pic = 0").replace("sample = 256", "sample = 512")
+    pics = {}
+    for tag, extra in (("ref", "[OUTPUT]\nppm = p6\n"), ("auto", "[SCENE]\nlights = auto\n[OUTPUT]\nppm = p6\n")):
+        d = tmp_path / tag
+        d.mkdir()
+        (d / "config.ini").write_text(base + extra)
+        out = subprocess.run([exe], cwd=d, capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stdout + out.stderr
+        if tag == "auto":
+            assert "light list: 1 emissive primitive(s) found" in out.stdout
+        assert open(d / "img.ppm", "rb").read(2) == b"P6"
+        pics[tag] = np.asarray(Image.open(d / "img.ppm")).astype(np.float64)
+    assert pics["ref"].shape == (120, 120, 3)
+    assert abs(pics["auto"].mean() - pics["ref"].mean()) < 0.05 * pics["ref"].mean()
+    # camera keys: looking at the box from the other side of the room shows a different picture
+    d = tmp_path / "cam"
+    d.mkdir()
+    (d / "config.ini").write_text(base + "[CAMERA]\nlookfrom = 250,100,700\nlookat = 0,-100,0\nfocus_dist = 700\n")
+    out = subprocess.run([exe], cwd=d, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    moved = read_p3(d / "img.ppm").astype(np.float64)
+    assert moved.shape == (120, 120, 3) and np.abs(moved - pics["ref"]).mean() > 5.0
+    (d / "config.ini").write_text(base + "[CAMERA]\nlookfrom = 1,2\n")
+    assert subprocess.run([exe], cwd=d, capture_output=True, text=True, timeout=60).returncode == 2

@@ -219,3 +219,98 @@ def test_builtin_jpeg_decoder_matches_stb(T, O):
         q = L.ref_load_image(real.encode(), C.byref(w), C.byref(h), C.byref(ch))
         ref = np.ctypeslib.as_array(q, shape=(h.value, w.value, 3)).copy()
         assert ref.shape == (512, 1024, 3) and np.array_equal(mine(real), ref)
+
+
+def _smooth_picture(nx, ny, seed):
+    """a picture with gradients, edges and mild noise (bottom-up, like the library's rgb8)"""
+    rng = np.random.default_rng(seed)
+    y, x = np.mgrid[0:ny, 0:nx].astype(np.float32)
+    img = np.stack([128 + 100 * np.sin(x / 9.0 + seed), 128 + 100 * np.cos(y / 7.0), 255.0 * x / max(nx - 1, 1)], axis=-1)
+    img[ny // 4: ny // 2, nx // 3: nx // 2] = (250, 20, 20)
+    img += rng.normal(0, 2.0, img.shape)
+    return np.clip(img, 0, 255).astype(np.uint8)
+
+
+def _psnr(a, b):
+    mse = np.mean((a.astype(np.float64) - b.astype(np.float64)) ** 2)
+    return 10 * np.log10(255.0 ** 2 / max(mse, 1e-12))
+
+
+def test_contact_sheet_jpeg_without_imagemagick(T, tmp_path):
+    """the `convert a.ppm b.ppm ... +append img.jpg` stage (main.cpp:224-245) done by
+    the front end itself. The file must be a baseline JPEG any decoder reads (PIL here, and the
+    repo's own tpt_jpeg.cc), the pictures left to right with the top row first, at quality-92
+    fidelity; odd sizes exercise the partial edge blocks."""
+    from PIL import Image
+    H = T.host()
+    nx, ny = 53, 37
+    pics = [_smooth_picture(nx, ny, s) for s in (1, 2, 3)]
+    arr = (C.c_void_p * 3)(*[p.ctypes.data for p in pics])
+    H.tpt_host_write_contact_sheet.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+    path = str(tmp_path / "img.jpg")
+    assert H.tpt_host_write_contact_sheet(path.encode(), arr, 3, nx, ny, 92) == 0
+    want = np.concatenate([p[::-1] for p in pics], axis=1)  # top row first, side by side
+    im = Image.open(path)
+    assert im.format == "JPEG" and im.size == (3 * nx, ny) and im.mode == "RGB"
+    got = np.asarray(im)
+    assert _psnr(got, want) > 34.0, _psnr(got, want)
+    # each panel is where `+append` puts it
+    for i, p in enumerate(pics):
+        assert _psnr(got[:, i * nx:(i + 1) * nx], p[::-1]) > 33.0
+    # the repo's own decoder (the one that reads earthmap.jpg) agrees with PIL to rounding
+    H.tpt_host_load_image.restype = C.POINTER(C.c_uint8)
+    H.tpt_host_load_image.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    H.tpt_host_free.argtypes = [C.c_void_p]
+    w, h, ch = C.c_int(), C.c_int(), C.c_int()
+    q = H.tpt_host_load_image(path.encode(), C.byref(w), C.byref(h), C.byref(ch))
+    assert q and (w.value, h.value, ch.value) == (3 * nx, ny, 3)
+    mine = np.ctypeslib.as_array(q, shape=(ny, 3 * nx, 3)).copy()
+    H.tpt_host_free(q)
+    assert np.abs(mine.astype(int) - got.astype(int)).max() <= 2
+    # quality is the IJG scale: lower quality -> smaller file, lower fidelity
+    small = str(tmp_path / "small.jpg")
+    assert H.tpt_host_write_contact_sheet(small.encode(), arr, 3, nx, ny, 40) == 0
+    assert os.path.getsize(small) < os.path.getsize(path)
+    assert 24.0 < _psnr(np.asarray(Image.open(small)), want) < _psnr(got, want)
+    # a flat picture (every AC coefficient zero) and a 1x1 picture are valid files too
+    flat = np.full((8, 8, 3), 77, np.uint8)
+    one = str(tmp_path / "flat.jpg")
+    assert H.tpt_host_write_contact_sheet(one.encode(), (C.c_void_p * 1)(flat.ctypes.data), 1, 8, 8, 92) == 0
+    assert np.abs(np.asarray(Image.open(one)).astype(int) - 77).max() <= 1
+    dot = np.array([[[10, 200, 90]]], np.uint8)
+    assert H.tpt_host_write_contact_sheet(one.encode(), (C.c_void_p * 1)(dot.ctypes.data), 1, 1, 1, 92) == 0
+    assert np.abs(np.asarray(Image.open(one)).astype(int)[0, 0] - dot[0, 0]).max() <= 3
+
+
+def test_binary_ppm_writer(T, tmp_path):
+    from PIL import Image
+    H = T.host()
+    nx, ny = 5, 4
+    img = _smooth_picture(nx, ny, 4)
+    H.tpt_host_write_ppm_binary.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_int]
+    p = str(tmp_path / "a.ppm")
+    assert H.tpt_host_write_ppm_binary(p.encode(), img.ctypes.data, nx, ny) == 0
+    raw = open(p, "rb").read()
+    assert raw.startswith(b"P6\n5 4\n255\n") and len(raw) == 11 + nx * ny * 3
+    assert np.array_equal(np.asarray(Image.open(p)), img[::-1])
+
+
+def test_light_list_derived_from_the_scene(T):
+    """emissive primitives the light-sampling list can represent. cornell_box has one
+    lamp, flip_normal(xz_rect(-100,100,-150,-50,298)) -- the first of the two shapes main.cpp:99-106
+    hard-codes (the second, the r=120 sphere around the glass ball, is not a lamp); light_spheres
+    has two lit spheres and a lit xy_rect (not representable: hitable::random is only overridden for
+    xz_rect and sphere); random_scene has none."""
+    H = T.host()
+    H.tpt_host_derive_lights.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    out = (T.Light * 8)()
+
+    def lights(name):
+        hs = T.HostScene(name)
+        n = H.tpt_host_derive_lights(hs._h, out, 8)
+        return [(out[i].kind, [round(float(v), 3) for v in out[i].p]) for i in range(n)]
+
+    assert lights("cornell_box") == [(0, [-100.0, 100.0, -150.0, -50.0, 298.0])]  # TPT_LIGHT_XZ_RECT
+    ls = lights("light_spheres")
+    assert ls == [(1, [-3.0, 1.0, 2.0, 1.0, 0.0]), (1, [-3.0, 1.0, -2.0, 1.0, 0.0])]  # the two emissive spheres only
+    assert lights("random_scene") == []

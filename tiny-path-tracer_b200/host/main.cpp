@@ -8,8 +8,13 @@
 // Additional, optional keys (absent => reference behaviour):
 //   [SCENE] name = cornell_box | sphere_cornell_box | random_scene | random_scene_list |
 //                  two_perlin_spheres | two_checker_spheres | light_spheres | earth
-//           background = black | sky        image = earthmap.ppm
+//                  | cornell_box_smoke | oneweek_final
+//           background = black | sky        image = earthmap.jpg
+//           lights = reference | auto       (auto: the scene's own diffuse_light xz_rects / spheres
+//                                            instead of the hard-coded list of main.cpp:99-106)
+//   [CAMERA] lookfrom = x,y,z   lookat = x,y,z   vup = x,y,z   focus_dist = <f>
 //   [GPU]   mode = fast | parity    kernel = mega | wavefront   seed = <u64>   gpus = <n>
+//   [OUTPUT] jpeg = native | convert   quality = 92   ppm = p3 | p6
 #include "tpt.h"
 #include "tpt_flatten.h"
 #include "tpt_image_io.h"
@@ -17,6 +22,7 @@
 #include "tpt_scene.h"
 
 #include <chrono>
+#include <cstdio>
 #include <fstream>
 #include <iostream>
 #include <thread>
@@ -35,6 +41,11 @@ int main(int, char **) {
   int allow_bonus_pic = 0, bonus_pic = 10;
   std::string scene_name = "cornell_box", background = "black", image_file = "earthmap.jpg";
   std::string mode = "fast", kernel = "wavefront";
+  std::string lights = "reference";                  // reference: main.cpp:99-106 ; auto: the scene's own lamps
+  std::string jpeg_tool = "native", ppm_format = "p3"; // [OUTPUT]
+  std::string cam_lookfrom, cam_lookat, cam_vup;     // [CAMERA] "x,y,z"; empty: the scene's camera of main.cpp:85-91
+  float cam_focus = 0.0f;
+  int jpeg_quality = 92;
   unsigned long long seed = 0x5EEDULL;
   int gpus = 1;
 
@@ -54,6 +65,18 @@ int main(int, char **) {
     inipp::extract(ini.sections["SCENE"]["name"], scene_name);
     inipp::extract(ini.sections["SCENE"]["background"], background);
     inipp::extract(ini.sections["SCENE"]["image"], image_file);
+    inipp::extract(ini.sections["SCENE"]["lights"], lights);
+  }
+  if (ini.sections.count("CAMERA")) {
+    inipp::extract(ini.sections["CAMERA"]["lookfrom"], cam_lookfrom);
+    inipp::extract(ini.sections["CAMERA"]["lookat"], cam_lookat);
+    inipp::extract(ini.sections["CAMERA"]["vup"], cam_vup);
+    inipp::extract(ini.sections["CAMERA"]["focus_dist"], cam_focus);
+  }
+  if (ini.sections.count("OUTPUT")) {
+    inipp::extract(ini.sections["OUTPUT"]["jpeg"], jpeg_tool);
+    inipp::extract(ini.sections["OUTPUT"]["ppm"], ppm_format);
+    inipp::extract(ini.sections["OUTPUT"]["quality"], jpeg_quality);
   }
   if (ini.sections.count("GPU")) {
     inipp::extract(ini.sections["GPU"]["mode"], mode);
@@ -116,7 +139,21 @@ int main(int, char **) {
       dist_to_focus = (lookfrom - lookat).length();
     }
   }
-  camera cam(lookfrom, lookat, vec3(0, 1, 0), fov, float(nx) / (float)ny, aperture, dist_to_focus,
+  vec3 vup(0, 1, 0);
+  auto parse_vec3 = [](const std::string &text, vec3 &v) {
+    float x, y, z;
+    if (std::sscanf(text.c_str(), " %f , %f , %f", &x, &y, &z) != 3) return false;
+    v = vec3(x, y, z);
+    return true;
+  };
+  if ((!cam_lookfrom.empty() && !parse_vec3(cam_lookfrom, lookfrom)) || (!cam_lookat.empty() && !parse_vec3(cam_lookat, lookat)) ||
+      (!cam_vup.empty() && !parse_vec3(cam_vup, vup))) {
+    std::cerr << "[CAMERA] lookfrom / lookat / vup must be x,y,z" << std::endl;
+    return 2;
+  }
+  if (cam_focus > 0) dist_to_focus = cam_focus;
+  else if (!cam_lookfrom.empty() || !cam_lookat.empty()) dist_to_focus = (lookfrom - lookat).length();
+  camera cam(lookfrom, lookat, vup, fov, float(nx) / (float)ny, aperture, dist_to_focus,
              time0, time1);
 
   xz_rect light_shape(-100, 100, -150, -50, 298, nullptr);
@@ -132,6 +169,12 @@ int main(int, char **) {
   if (!tpt::flatten_scene(world, &hlist, background == "sky" ? TPT_BG_SKY : TPT_BG_BLACK, flat, err)) {
     std::cerr << "flatten: " << err << std::endl;
     return 3;
+  }
+  if (lights == "auto") {
+    std::vector<tpt_light> own = tpt::derive_light_list(flat);
+    std::cout << "light list: " << own.size() << " emissive primitive(s) found"
+              << (own.empty() ? ", keeping the reference list" : "") << std::endl;
+    if (!own.empty()) flat.lights = own;
   }
   tpt_scene_desc desc = flat.desc();
   if (gpus < 1) gpus = 1;
@@ -176,12 +219,18 @@ int main(int, char **) {
             << " Mpaths/s, " << st.rays / (st.render_ms * 1e3) << " Mrays/s" << std::endl;
 
   // ---- output, as main.cpp:176-245 ----
-  tpt::write_ppm_main(filenames[0], rgb8.data(), nx, ny);
+  const bool p6 = ppm_format == "p6"; // binary PPM instead of the reference's text form
+  if (p6) tpt::write_ppm_binary(filenames[0], rgb8.data(), nx, ny);
+  else tpt::write_ppm_main(filenames[0], rgb8.data(), nx, ny);
+  std::vector<const uint8_t *> pictures{rgb8.data()};
   if (allow_bonus_pic) {
     for (int k = 0; k < bonus_pic; k++) {
       std::string file = "img_" + std::to_string(k) + ".ppm";
       filenames.push_back(file);
-      tpt::write_ppm_bonus(file, rgb8_slices.data() + (size_t)k * nx * ny * 3, nx, ny);
+      const uint8_t *slice = rgb8_slices.data() + (size_t)k * nx * ny * 3;
+      pictures.push_back(slice);
+      if (p6) tpt::write_ppm_binary(file, slice, nx, ny);
+      else tpt::write_ppm_bonus(file, slice, nx, ny);
     }
   }
   auto end = std::chrono::high_resolution_clock::now();
@@ -189,8 +238,15 @@ int main(int, char **) {
             << std::chrono::duration_cast<std::chrono::milliseconds>(end - start).count() / 1000.0f
             << " s" << std::endl;
   for (tpt_scene *sc : scenes) tpt_scene_destroy(sc);
+  // main.cpp:224-245 shells out to `convert ... +append img.jpg`; the built-in writer produces the
+  // same side-by-side JPEG from the pixels in memory ([OUTPUT] jpeg=convert keeps the old route)
+  std::string stem = filenames[0].substr(0, filenames[0].find_first_of("."));
+  if (jpeg_tool == "convert" || !tpt::write_contact_sheet(stem + ".jpg", pictures, nx, ny, jpeg_quality)) {
 #ifdef __linux__
-  tpt::merge_with_convert(filenames);
+    tpt::merge_with_convert(filenames);
 #endif
+  } else {
+    std::cout << "Merging pics:" << "\n" << pictures.size() << " picture(s) +append " << stem << ".jpg (built-in JPEG writer)" << std::endl;
+  }
   return 0;
 }

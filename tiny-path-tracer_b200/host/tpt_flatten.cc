@@ -262,6 +262,27 @@ bool flatten_scene(const hitable *world, const hitable *light_shape, int backgro
   return true;
 }
 
+std::vector<tpt_light> derive_light_list(const FlatScene &flat) {
+  std::vector<tpt_light> out;
+  for (const tpt_prim &p : flat.prims) {
+    if (p.material < 0 || p.material >= (int)flat.materials.size()) continue;
+    if (flat.materials[p.material].kind != TPT_MAT_DIFFUSE_LIGHT || p.chain != 0) continue;
+    tpt_light L;
+    std::memset(&L, 0, sizeof(L));
+    if (p.kind == TPT_PRIM_XZ_RECT) {
+      L.kind = TPT_LIGHT_XZ_RECT;
+      for (int i = 0; i < 5; i++) L.p[i] = p.p[i];
+    } else if (p.kind == TPT_PRIM_SPHERE) {
+      L.kind = TPT_LIGHT_SPHERE;
+      for (int i = 0; i < 4; i++) L.p[i] = p.p[i];
+    } else {
+      continue;
+    }
+    out.push_back(L);
+  }
+  return out;
+}
+
 tpt_camera make_camera_desc(const camera_with_blur &cam) {
   tpt_camera c;
   for (int i = 0; i < 3; i++) {

@@ -98,6 +98,13 @@ private:
 bool flatten_scene(const hitable *world, const hitable *light_shape, int background,
                    FlatScene &out, std::string &err);
 
+// Light-sampling list derived from the scene itself instead of the hard-coded shapes of
+// main.cpp:99-106 (the design regret README.md:17 names): every diffuse_light
+// primitive that hitable::random / pdf_value can represent -- an xz_rect or a sphere outside any
+// translate / rotate_y wrapper (src/rect_box.cc:26-43, src/sphere.cc:93-120). Empty when the scene
+// has none (callers keep the reference list then).
+std::vector<tpt_light> derive_light_list(const FlatScene &flat);
+
 // tpt_camera from the host camera's public fields
 tpt_camera make_camera_desc(const camera_with_blur &cam);
 

@@ -159,4 +159,21 @@ int tpt_host_write_ppm(const char *path, const unsigned char *rgb8, int nx, int 
   return ok ? 0 : -1;
 }
 
+// binary PPM and the ImageMagick-free contact sheet: `n` pictures of nx x ny in the
+// library's bottom-up rgb8 layout, side by side, as one baseline JPEG
+int tpt_host_write_ppm_binary(const char *path, const unsigned char *rgb8, int nx, int ny) {
+  return tpt::write_ppm_binary(path, rgb8, nx, ny) ? 0 : -1;
+}
+int tpt_host_write_contact_sheet(const char *path, const unsigned char *const *pictures, int n, int nx, int ny,
+                                 int quality) {
+  std::vector<const uint8_t *> pics(pictures, pictures + n);
+  return tpt::write_contact_sheet(path, pics, nx, ny, quality) ? 0 : -1;
+}
+// emissive primitives of a built scene that the light-sampling list can represent
+int tpt_host_derive_lights(void *h, tpt_light *out, int capacity) {
+  std::vector<tpt_light> lights = tpt::derive_light_list(static_cast<host_scene *>(h)->flat);
+  for (int i = 0; i < (int)lights.size() && i < capacity; i++) out[i] = lights[i];
+  return (int)lights.size();
+}
+
 } // extern "C"

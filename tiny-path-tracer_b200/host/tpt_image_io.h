@@ -13,6 +13,17 @@ bool write_ppm_main(const std::string &path, const uint8_t *rgb8, int nx, int ny
 bool write_ppm_bonus(const std::string &path, const uint8_t *rgb8, int nx, int ny);
 // `convert a.ppm b.ppm ... +append img.jpg` (main.cpp:224-245); returns the system() status.
 int merge_with_convert(const std::vector<std::string> &files);
+// The same output stage without ImageMagick (tpt_jpeg_enc.cc): the pictures side by side, left to
+// right, as one baseline JPEG. Buffers are the library's rgb8 layout ([ny][nx][3], row 0 = bottom).
+bool write_contact_sheet(const std::string &path, const std::vector<const uint8_t *> &rgb8_bottom_up, int nx, int ny,
+                         int quality = 92);
+// baseline JPEG writer, rows top to bottom; quality follows the IJG scale (convert's default is 92)
+bool encode_jpeg(const uint8_t *rgb, int w, int h, int quality, std::vector<uint8_t> &out);
+bool write_jpeg(const std::string &path, const uint8_t *rgb, int w, int h, int quality = 92);
+void append_pictures(const std::vector<const uint8_t *> &pictures, const std::vector<int> &widths,
+                     const std::vector<int> &heights, std::vector<uint8_t> &out, int &w, int &h);
+// binary PPM ("P6"), rows top to bottom; rgb8 is the library's bottom-up layout
+bool write_ppm_binary(const std::string &path, const uint8_t *rgb8, int nx, int ny);
 // baseline JPEG (8-bit, 1 or 3 components, no chroma subsampling): tpt_jpeg.cc
 bool read_jpeg(const std::string &path, std::vector<uint8_t> &rgb, int &w, int &h);
 // PPM (P6/P3) reader used by tests and as a texture source
