@@ -61,29 +61,29 @@ int main(int, char **) {
   inipp::extract(ini.sections["BLUR"]["aperture"], aperture);
   inipp::extract(ini.sections["CAM_MOTION"]["start_time"], time0);
   inipp::extract(ini.sections["CAM_MOTION"]["end_time"], time1);
-  if (ini.sections.count("SCENE")) {
-    inipp::extract(ini.sections["SCENE"]["name"], scene_name);
-    inipp::extract(ini.sections["SCENE"]["background"], background);
-    inipp::extract(ini.sections["SCENE"]["image"], image_file);
-    inipp::extract(ini.sections["SCENE"]["lights"], lights);
-  }
-  if (ini.sections.count("CAMERA")) {
-    inipp::extract(ini.sections["CAMERA"]["lookfrom"], cam_lookfrom);
-    inipp::extract(ini.sections["CAMERA"]["lookat"], cam_lookat);
-    inipp::extract(ini.sections["CAMERA"]["vup"], cam_vup);
-    inipp::extract(ini.sections["CAMERA"]["focus_dist"], cam_focus);
-  }
-  if (ini.sections.count("OUTPUT")) {
-    inipp::extract(ini.sections["OUTPUT"]["jpeg"], jpeg_tool);
-    inipp::extract(ini.sections["OUTPUT"]["ppm"], ppm_format);
-    inipp::extract(ini.sections["OUTPUT"]["quality"], jpeg_quality);
-  }
-  if (ini.sections.count("GPU")) {
-    inipp::extract(ini.sections["GPU"]["mode"], mode);
-    inipp::extract(ini.sections["GPU"]["kernel"], kernel);
-    inipp::extract(ini.sections["GPU"]["seed"], seed);
-    inipp::extract(ini.sections["GPU"]["gpus"], gpus);
-  }
+  // optional keys: read only when present (the string form of extract() would otherwise replace a
+  // default with the empty value operator[] inserts)
+  auto opt = [&ini](const char *section, const char *key, auto &dst) {
+    auto sec = ini.sections.find(section);
+    if (sec == ini.sections.end()) return;
+    auto kv = sec->second.find(key);
+    if (kv != sec->second.end()) inipp::extract(kv->second, dst);
+  };
+  opt("SCENE", "name", scene_name);
+  opt("SCENE", "background", background);
+  opt("SCENE", "image", image_file);
+  opt("SCENE", "lights", lights);
+  opt("CAMERA", "lookfrom", cam_lookfrom);
+  opt("CAMERA", "lookat", cam_lookat);
+  opt("CAMERA", "vup", cam_vup);
+  opt("CAMERA", "focus_dist", cam_focus);
+  opt("GPU", "mode", mode);
+  opt("GPU", "kernel", kernel);
+  opt("GPU", "seed", seed);
+  opt("GPU", "gpus", gpus);
+  opt("OUTPUT", "jpeg", jpeg_tool);
+  opt("OUTPUT", "ppm", ppm_format);
+  opt("OUTPUT", "quality", jpeg_quality);
   ini.generate(std::cout);
 
   std::cout << "<===========>" << std::endl;
