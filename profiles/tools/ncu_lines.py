@@ -44,7 +44,7 @@ for fn in os.listdir(src_dir):
         L = open(os.path.join(src_dir, fn)).read().split("\n")
         marks = []
         for i, l in enumerate(L):
-            m = re.match(r"(?:template\s*<[^>]*>\s*)?(?:static\s+)?(?:TPT_DEV|__global__|__device__)[^(]*?([A-Za-z_0-9]+)\s*\(", l)
+            m = re.match(r"\s*(?:template\s*<[^>]*>\s*)?(?:static\s+)?(?:TPT_DEV|__global__|__device__)[^(]*?([A-Za-z_0-9]+)\s*\(", l)
             if m and not l.startswith("TPT_DEV V3 operator") and not l.startswith("TPT_DEV float dot") and "{ return" not in l:
                 marks.append((i + 1, m.group(1)))
         defs[fn] = marks
