@@ -488,7 +488,14 @@ TPT_DEV bool walk_range(const SceneView &S, const Ray &r, int first, int end_all
     fr[0].best_t = 0.f;
     fr[0].best_prim = -1;
     fr[0].end_list = n | (int)0x80000000;
+    // The walk is kept in lock step across the lanes of a warp: `i` only moves by decisions every
+    // converged lane shares. A lane whose box test fails does not jump ahead on its own (that put
+    // the lanes of a warp at different nodes: 10 of 32 active in this loop on the Cornell tree);
+    // it marks itself dead until the end of that sub-tree and idles through it, and the sub-tree
+    // is skipped only when no lane wants it. A dead lane records nothing, so the frames it opens
+    // close empty and the result is the one the private walk would produce.
     int i = first;
+    int dead_until = first; // this lane takes part in node i iff i >= dead_until
     for (;;) {
       // close finished groups, handing their result to the parent
       while (sp > 1 && i == (fr[sp - 1].end_list & 0x7fffffff)) {
@@ -503,6 +510,7 @@ TPT_DEV bool walk_range(const SceneView &S, const Ray &r, int first, int end_all
         }
       }
       if (i >= n) break;
+      const bool alive = i >= dead_until;
       Frame &P = fr[sp - 1];
       float ctx = (P.end_list < 0 && P.best_prim >= 0) ? P.best_t : P.tmax_in;
       float4 n0 = N[2 * i], n1 = N[2 * i + 1];
@@ -513,7 +521,7 @@ TPT_DEV bool walk_range(const SceneView &S, const Ray &r, int first, int end_all
       if (k == TPT_NODE_LEAF) {
         float t;
         int prim = __float_as_int(n1.w);
-        if (any_prim_test<PAR, MED>(S, prim, x, r, tmin, ctx, t, g)) {
+        if (alive && any_prim_test<PAR, MED>(S, prim, x, r, tmin, ctx, t, g)) {
           bool take = (P.end_list < 0) || (P.best_prim < 0) || !(P.best_t < t);
           if (take) {
             P.best_t = t;
@@ -523,7 +531,9 @@ TPT_DEV bool walk_range(const SceneView &S, const Ray &r, int first, int end_all
         i++;
       } else {
         int end = __float_as_int(n1.w);
-        if (k == TPT_NODE_BVH && !aabb_hit<PAR>(x, n0, n1, tmin, ctx)) {
+        const bool enter = alive && !(k == TPT_NODE_BVH && !aabb_hit<PAR>(x, n0, n1, tmin, ctx));
+        if (alive && !enter) dead_until = end;
+        if (!__any_sync(__activemask(), enter)) {
           i = end;
         } else {
           Frame &F = fr[sp++];
