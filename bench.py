@@ -48,6 +48,10 @@ def parse():
     ap.add_argument("--kernel", default="wavefront", choices=["wavefront", "mega"])
     ap.add_argument("--spp", type=int, default=NS, help="override samples per pixel (default: the headline 2048)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--bundle-cull", action="store_true",
+                    help="headline with the library's default pixel-bundle bounds test on (pixels that cannot see the "
+                         "scene are finished untraced, exact); by default the bench traces every path and reports the "
+                         "culled variant beside it")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the bounded baseline sample")
     return ap.parse_args()
 
@@ -223,7 +227,7 @@ def run_ours(args, rank, local_rank, world):
     cam = T.cornell_camera(NX, NY, fov=v["fov"])
     kernel = T.KERNEL_WAVEFRONT if args.kernel == "wavefront" else T.KERNEL_MEGA
     params = T.make_params(NX, NY, args.spp, v["depth"], mode=mode, seed=0x5EED, part_index=rank, part_count=world,
-                           device=local_rank, kernel=kernel)
+                           device=local_rank, kernel=kernel, bundle_cull=args.bundle_cull)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     sampler = ClockSampler(local_rank)
@@ -309,7 +313,7 @@ def run_ours(args, rank, local_rank, world):
     parity = None
     if args.mode == "fast":
         pp = T.make_params(NX, NY, min(256, args.spp), v["depth"], mode=T.MODE_PARITY, seed=0x5EED, part_index=rank,
-                           part_count=world, device=local_rank, kernel=kernel)
+                           part_count=world, device=local_rank, kernel=kernel, bundle_cull=args.bundle_cull)
         scene.render_device(cam, pp)
         barrier()
         stp = scene.render_device(cam, pp)
@@ -317,6 +321,31 @@ def run_ours(args, rank, local_rank, world):
         p_paths = sum_over_ranks(float(stp["paths"]))
         parity = {"value": p_paths / (p_ms * 1e-3) / 1e6, "unit": "Mpaths/s", "spp": min(256, args.spp),
                   "note": "TPT_MODE_PARITY: fp64 where the reference promotes, no FMA contraction, reference BVH walk"}
+
+    # ---- the same job with the library's default pixel-bundle bounds test (exact: tests/
+    # test_gpu_properties.py::test_pixel_bundle_test_is_exact), reported beside the headline --------
+    culled = None
+    if not args.bundle_cull:
+        pc = T.make_params(NX, NY, args.spp, v["depth"], mode=mode, seed=0x5EED, part_index=rank, part_count=world,
+                           device=local_rank, kernel=kernel, bundle_cull=True)
+        scene.render_device(cam, pc)
+        barrier()
+        c_ms, c_paths, c_culled, c_rays = 0.0, 0, 0, 0
+        for _ in range(args.steps):
+            flush.zero_()
+            torch.cuda.synchronize()
+            stc = scene.render_device(cam, pc)
+            c_ms += stc["render_ms"] + stc["resolve_ms"]
+            c_paths += stc["paths"]
+            c_culled += stc["culled_paths"]
+            c_rays += stc["rays"]
+        barrier()
+        c_ms = max_over_ranks(c_ms)
+        c_paths, c_culled, c_rays = sum_over_ranks(float(c_paths)), sum_over_ranks(float(c_culled)), sum_over_ranks(float(c_rays))
+        culled = {"value": c_paths / (c_ms * 1e-3) / 1e6, "unit": "Mpaths/s", "ms_per_step": c_ms / args.steps,
+                  "culled_path_fraction": c_culled / c_paths, "rays_per_path": c_rays / c_paths,
+                  "note": "library default (tpt_render_params.reserved[2] = 0): pixels none of whose rays can reach the "
+                          "scene's bounds are finished untraced; bit-identical image"}
 
     if rank != 0:
         return
@@ -378,6 +407,10 @@ def run_ours(args, rank, local_rank, world):
         line["cpu_baseline"] = cpu
     if parity:
         line["parity_mode"] = parity
+    if culled:
+        line["bundle_cull"] = culled
+    line["config"]["paths_traced"] = ("every (pixel, sample) traced (bundle test off)" if not args.bundle_cull
+                                      else "pixel-bundle bounds test on (library default)")
     print(json.dumps(line))
 
 

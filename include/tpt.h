@@ -213,7 +213,10 @@ typedef struct tpt_render_params {
    * (tile_index % part_count) == part_index ; tiles are TPT_TILE x TPT_TILE pixels, row-major */
   int32_t part_index, part_count;
   int32_t device;   /* CUDA device ordinal for single-device calls */
-  int32_t reserved[4];
+  int32_t reserved[4]; /* zero for defaults. [1] > 0: sample sub-ranges per slice (work granularity);
+                          [2] = 1: trace every path, also those of pixels none of whose rays can reach the
+                          scene's bounds (by default such (pixel, sample) pairs are finished untraced with
+                          their exact result, 0 on the black background -- tpt_stats.culled_paths) */
 } tpt_render_params;
 
 #define TPT_TILE 16
@@ -240,6 +243,9 @@ typedef struct tpt_stats {
   int32_t blocks, threads_per_block;
   int32_t reserved[4];     /* [0] = sample ranges per pixel of the last single-device render
                               (tpt_render_multi: batches taken by GPUs 0..3) */
+  uint64_t culled_paths;   /* of `paths`: those of pixels whose whole ray bundle misses the scene's bounds;
+                              world->hit is false for every ray they can generate, so they are finished
+                              without tracing (0 rays counted for them). See tpt_render_params.reserved[2]. */
 } tpt_stats;
 
 typedef struct tpt_scene tpt_scene; /* opaque: owns the device copies */

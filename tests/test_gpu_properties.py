@@ -144,11 +144,38 @@ def test_statistics_headline_frame(T, cornell):
     zero-throughput paths that turn NaN later; both contribute 0 after de_nan)."""
     nx = ny = 1200
     cam = T.cornell_camera(nx, ny)
-    st = cornell.render_device(cam, T.make_params(nx, ny, 4, 15, seed=1))
-    assert st["paths"] == nx * ny * 4
+    st = cornell.render_device(cam, T.make_params(nx, ny, 4, 15, seed=1, bundle_cull=False))
+    assert st["paths"] == nx * ny * 4 and st["culled_paths"] == 0
     assert 1.9 < st["rays"] / st["paths"] < 2.41
     assert 0.005 < st["nan_samples"] / st["paths"] < 0.022
     assert st["kernel_launches"] == 2
+
+
+@pytest.mark.parametrize("mode", ["parity", "fast"])
+@pytest.mark.parametrize("kernel", ["mega", "wavefront"])
+def test_pixel_bundle_test_is_exact(T, cornell, mode, kernel):
+    """Pixels none of whose rays (any lens point, any jitter) can reach the scene's bounds are
+    finished without tracing (tpt_stats.culled_paths). That is exact, not an approximation: the
+    image is bit-identical to the one with every path traced, each untraced path is exactly one
+    world->hit query that would have returned false (rays differ by culled_paths), and at fov 90
+    the shipped camera looks past the box in ~64 % of the frame."""
+    m = T.MODE_PARITY if mode == "parity" else T.MODE_FAST
+    k = T.KERNEL_WAVEFRONT if kernel == "wavefront" else T.KERNEL_MEGA
+    nx, ny, ns = 300, 300, 8
+    cam = T.cornell_camera(nx, ny)
+    a = cornell.render(cam, T.make_params(nx, ny, ns, 15, mode=m, seed=77, kernel=k, slices=2), want_slices=True)
+    b = cornell.render(cam, T.make_params(nx, ny, ns, 15, mode=m, seed=77, kernel=k, slices=2, bundle_cull=False), want_slices=True)
+    assert np.array_equal(a.sum_rgb, b.sum_rgb) and np.array_equal(a.rgb8, b.rgb8) and np.array_equal(a.rgb8_slices, b.rgb8_slices)
+    sa, sb = a.stats, b.stats
+    assert sa["paths"] == sb["paths"] == nx * ny * ns and sb["culled_paths"] == 0
+    assert 0.55 < sa["culled_paths"] / sa["paths"] < 0.66
+    assert sa["rays"] + sa["culled_paths"] == sb["rays"] and sa["nan_samples"] == sb["nan_samples"]
+    # every culled pixel is black in the traced render; no pixel that received light was culled
+    culled_px = sa["culled_paths"] // ns
+    assert (b.sum_rgb[-1].sum(axis=-1) == 0).sum() >= culled_px
+    # a frame-filling camera, the sky background and an interior camera cull nothing
+    inside = cornell.render(T.cornell_camera(64, 64, fov=61.93), T.make_params(64, 64, 4, 15, mode=m, kernel=k))
+    assert inside.stats["culled_paths"] == 0
 
 
 def test_fast_and_parity_converge_to_the_same_image(T, cornell):

@@ -127,7 +127,8 @@ class Stats(C.Structure):
                 ("render_ms", C.c_double), ("resolve_ms", C.c_double), ("h2d_ms", C.c_double),
                 ("d2h_ms", C.c_double), ("wall_ms", C.c_double), ("h2d_bytes", C.c_uint64),
                 ("d2h_bytes", C.c_uint64), ("kernel_launches", C.c_int32), ("sm_count", C.c_int32),
-                ("blocks", C.c_int32), ("threads_per_block", C.c_int32), ("reserved", C.c_int32 * 4)]
+                ("blocks", C.c_int32), ("threads_per_block", C.c_int32), ("reserved", C.c_int32 * 4),
+                ("culled_paths", C.c_uint64)]
 
 
 RAY_DTYPE = np.dtype([("o", np.float32, 3), ("d", np.float32, 3), ("time", np.float32)])
@@ -277,7 +278,7 @@ class RenderResult:
 
 
 def make_params(nx, ny, ns, max_depth, mode=MODE_FAST, slices=1, seed=0x5EED, t_min=0.001, part_index=0,
-                part_count=1, device=0, kernel=KERNEL_MEGA, subs=0) -> RenderParams:
+                part_count=1, device=0, kernel=KERNEL_MEGA, subs=0, bundle_cull=True) -> RenderParams:
     p = RenderParams()
     p.nx, p.ny, p.ns, p.max_depth = nx, ny, ns, max_depth
     p.slices, p.mode, p.kernel = slices, mode, kernel
@@ -285,6 +286,7 @@ def make_params(nx, ny, ns, max_depth, mode=MODE_FAST, slices=1, seed=0x5EED, t_
     p.t_min = t_min
     p.part_index, p.part_count, p.device = part_index, part_count, device
     p.reserved[1] = subs
+    p.reserved[2] = 0 if bundle_cull else 1  # 1: trace every path, also those whose pixel cannot see the scene
     return p
 
 

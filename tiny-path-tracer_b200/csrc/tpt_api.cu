@@ -129,6 +129,12 @@ struct tpt_scene {
   int n_mediums = 0;
   bool fbvh_has_moving = false; // the fast BVH boxes moving spheres over [fbvh_t0, fbvh_t1] only
   float fbvh_t0 = 0, fbvh_t1 = 0;
+  // world bounds for the pixel-bundle test: the root node's box when it is stated in world space
+  bool root_box_ok = false;
+  float root_lo[3] = {0, 0, 0}, root_hi[3] = {0, 0, 0};
+  bool any_moving = false; // node boxes of moving spheres hold for [moving_t0, moving_t1] only
+  float moving_t0 = 0, moving_t1 = 0;
+  int background = 0;
   // render products (device)
   float *d_acc = nullptr;
   size_t acc_bytes = 0;
@@ -635,6 +641,82 @@ int make_plan(tpt_scene *s, const tpt_camera *cam, const tpt_render_params *p, P
   A.t_min = p->t_min;
   A.seed_lo = p->seed_lo;
   A.seed_hi = p->seed_hi;
+  // Pixel-bundle bounds test (RenderArgs::cull): black background, world-space root box, shutter
+  // inside the interval the moving spheres' boxes were built for. reserved[2] = 1 turns it off.
+  A.cull = 0;
+  if (p->reserved[2] == 0 && s->background == TPT_BG_BLACK && s->root_box_ok &&
+      (!s->any_moving || (std::min(cam->time0, cam->time1) >= s->moving_t0 && std::max(cam->time0, cam->time1) <= s->moving_t1))) {
+    auto dotd = [](const double *a, const float *b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; };
+    double q[3];
+    for (int k = 0; k < 3; k++) q[k] = (double)cam->lower_left_corner[k] - cam->origin[k];
+    const double fd = -dotd(q, cam->w);
+    const double hlen[3] = {cam->horizontal[0], cam->horizontal[1], cam->horizontal[2]};
+    const double vlen[3] = {cam->vertical[0], cam->vertical[1], cam->vertical[2]};
+    // the frame must be the one camera_with_blur builds (src/camera.cc:2-21): horizontal along u,
+    // vertical along v, focus plane perpendicular to w at distance fd > 0
+    const double h_off = std::fabs(dotd(hlen, cam->v)) + std::fabs(dotd(hlen, cam->w));
+    const double v_off = std::fabs(dotd(vlen, cam->u)) + std::fabs(dotd(vlen, cam->w));
+    const double span = std::fabs(dotd(hlen, cam->u)) + std::fabs(dotd(vlen, cam->v));
+    if (fd > 0 && std::isfinite(fd) && span > 0 && h_off <= 1e-4 * span && v_off <= 1e-4 * span) {
+      // Camera coordinates: x along u, y along v, z forward (-w). The rays of pixel column px run
+      // from a lens point (|x| <= R at z = 0) through the column's footprint [fx0, fx1] on the
+      // focus plane z = fd, so at depth z = l * fd they satisfy
+      //     x >= l*fx0 - |1-l|*R >= l*(fx0 - R) - R        (likewise x <= l*(fx1 + R) + R):
+      // two planes bound them all. The column cannot see the box when its eight corners are all on
+      // the wrong side of one of the planes; rows alike; nothing is visible when the box is behind
+      // the lens plane. The visible set is therefore a pixel rectangle. Conservative: the box is
+      // padded as in may_hit_world, the footprint widened by `slack`.
+      const double inv_fd = 1.0 / fd;
+      const double xl = dotd(q, cam->u), yb = dotd(q, cam->v);
+      const double hl = dotd(hlen, cam->u), vl = dotd(vlen, cam->v);
+      const double slack = 1e-4 * span + std::fabs((double)cam->lens_radius) * 1.001;
+      double X[8], Y[8], Z[8];
+      bool finite = true, behind = true;
+      for (int c = 0; c < 8; c++) {
+        double pw[3];
+        for (int k = 0; k < 3; k++) {
+          const double lo = s->root_lo[k], hi = s->root_hi[k];
+          const double pad = 1e-3 * std::max(std::fabs(lo), std::fabs(hi)) + 1e-3;
+          pw[k] = ((c >> k) & 1 ? hi + pad : lo - pad) - cam->origin[k];
+        }
+        X[c] = dotd(pw, cam->u);
+        Y[c] = dotd(pw, cam->v);
+        Z[c] = -dotd(pw, cam->w);
+        finite = finite && std::isfinite(X[c]) && std::isfinite(Y[c]) && std::isfinite(Z[c]);
+        behind = behind && Z[c] < 0;
+      }
+      auto visible_span = [&](int n, double first, double len, const double *C, int &i0, int &i1) {
+        i0 = n;
+        i1 = -1;
+        for (int i = 0; i < n; i++) {
+          const double a = first + (double)i / n * len, b = first + (double)(i + 1) / n * len;
+          const double lo = std::min(a, b) - slack, hi = std::max(a, b) + slack;
+          bool out_lo = true, out_hi = true;
+          for (int c = 0; c < 8; c++) {
+            const double l = Z[c] * inv_fd;
+            out_lo = out_lo && (C[c] < l * lo - slack);
+            out_hi = out_hi && (C[c] > l * hi + slack);
+          }
+          if (!(out_lo || out_hi)) {
+            i0 = std::min(i0, i);
+            i1 = std::max(i1, i);
+          }
+        }
+      };
+      if (finite) {
+        A.cull = 1;
+        if (behind) {
+          A.cull_x0 = A.cull_y0 = 1;
+          A.cull_x1 = A.cull_y1 = 0; // empty rectangle
+        } else {
+          visible_span(p->nx, xl, hl, X, A.cull_x0, A.cull_x1);
+          visible_span(p->ny, yb, vl, Y, A.cull_y0, A.cull_y1);
+        }
+        // nothing to cull (frame-filling or interior camera): run the kernel build without the test
+        if (A.cull_x0 <= 0 && A.cull_y0 <= 0 && A.cull_x1 >= p->nx - 1 && A.cull_y1 >= p->ny - 1) A.cull = 0;
+      }
+    }
+  }
   // sample ranges: each slice is cut into `subs` sub-ranges (finer bins => shorter kernel tail);
   // samples beyond slices*per_slice (ns not divisible) form one tail range.
   // Automatic choice (fast mode): enough bins that every resident path slot works through >= 32 of
@@ -724,8 +806,8 @@ int run_plan(tpt_scene *s, Plan &plan, bool want_sum, bool want_rgb8, bool want_
   if (plan.wavefront)
     CK(plan.parity ? wave_occupancy_parity(A, small, s->use_smem, media, trace, &bps) : wave_occupancy_fast(A, small, s->use_smem, media, trace, &bps));
   else
-    CK(plan.parity ? mega_occupancy_parity(s->use_smem, small, media, smem, &bps)
-                   : mega_occupancy_fast(s->use_smem, small, media, smem, &bps));
+    CK(plan.parity ? mega_occupancy_parity(A, s->use_smem, small, media, smem, &bps)
+                   : mega_occupancy_fast(A, s->use_smem, small, media, smem, &bps));
   if (bps < 1) return fail(TPT_ERR_CUDA, "render kernel does not fit on an SM");
   plan.blocks_per_sm = bps;
   plan.blocks = bps * s->prop.multiProcessorCount;
@@ -743,7 +825,7 @@ int run_plan(tpt_scene *s, Plan &plan, bool want_sum, bool want_rgb8, bool want_
   CK(cudaGetLastError());
   CK(cudaEventRecord(s->ev[2], s->stream));
   CK(cudaStreamSynchronize(s->stream));
-  unsigned long long c[4];
+  unsigned long long c[5];
   CK(cudaMemcpy(c, s->d_counters, sizeof(c), cudaMemcpyDeviceToHost));
   float ms_render = 0, ms_resolve = 0;
   CK(cudaEventElapsedTime(&ms_render, s->ev[0], s->ev[1]));
@@ -753,6 +835,7 @@ int run_plan(tpt_scene *s, Plan &plan, bool want_sum, bool want_rgb8, bool want_
   st.paths = c[3];
   st.rays = c[1];
   st.nan_samples = c[2];
+  st.culled_paths = c[4];
   st.render_ms = ms_render;
   st.resolve_ms = ms_resolve;
   st.kernel_launches = 2;
@@ -858,8 +941,8 @@ int launch_batch(tpt_scene *s, const tpt_camera *cam, const tpt_render_params *p
   if (plan.wavefront)
     CK(plan.parity ? wave_occupancy_parity(A, small, s->use_smem, media, trace, &bps) : wave_occupancy_fast(A, small, s->use_smem, media, trace, &bps));
   else
-    CK(plan.parity ? mega_occupancy_parity(s->use_smem, small, media, smem, &bps)
-                   : mega_occupancy_fast(s->use_smem, small, media, smem, &bps));
+    CK(plan.parity ? mega_occupancy_parity(A, s->use_smem, small, media, smem, &bps)
+                   : mega_occupancy_fast(A, s->use_smem, small, media, smem, &bps));
   if (bps < 1) return fail(TPT_ERR_CUDA, "render kernel does not fit on an SM");
   int blocks = bps * s->prop.multiProcessorCount;
   if (plan.wavefront)
@@ -1020,6 +1103,7 @@ int render_multi(tpt_scene *const *scenes, int n, const tpt_camera *cam, const t
       st.paths += c[(size_t)b * 8 + 3];
       st.rays += c[(size_t)b * 8 + 1];
       st.nan_samples += c[(size_t)b * 8 + 2];
+      st.culled_paths += c[(size_t)b * 8 + 4];
     }
     st.render_ms = std::max(st.render_ms, W[g].busy_ms);
     st.kernel_launches += W[g].batches + 1;
@@ -1159,6 +1243,25 @@ int tpt_scene_create(const tpt_scene_desc *d, int device, tpt_scene **out) {
     append(blob, rec.data(), rec.size());
   }
   L.n_fbvh = (int)(fb.nodes.size() / 16);
+  {
+    // world bounds = the root node's box, when the root sits outside any transform wrapper
+    const tpt_node &root = d->nodes[0];
+    s->root_box_ok = (root.kind >> 16) == 0;
+    for (int k = 0; k < 3; k++) {
+      s->root_lo[k] = root.bmin[k];
+      s->root_hi[k] = root.bmax[k];
+      if (!std::isfinite(root.bmin[k]) || !std::isfinite(root.bmax[k]) || !(root.bmin[k] <= root.bmax[k])) s->root_box_ok = false;
+    }
+    s->moving_t0 = FLT_MAX;
+    s->moving_t1 = -FLT_MAX;
+    for (int i = 0; i < d->n_prims; i++)
+      if (d->prims[i].kind == TPT_PRIM_MOVING_SPHERE) {
+        s->any_moving = true;
+        s->moving_t0 = std::min(s->moving_t0, std::min(d->prims[i].p[7], d->prims[i].p[8]));
+        s->moving_t1 = std::max(s->moving_t1, std::max(d->prims[i].p[7], d->prims[i].p[8]));
+      }
+    s->background = d->background;
+  }
   L.fbvh_time_ok = 1;
   s->fbvh_has_moving = fb.has_moving;
   s->fbvh_t0 = fb.moving_t0;

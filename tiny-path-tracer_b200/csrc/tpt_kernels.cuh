@@ -76,7 +76,14 @@ struct LaneBin {
   unsigned acc_index;
   V3 acc;
 };
-TPT_DEV void lane_bin_refill(const RenderArgs &A, LaneBin &B, bool need, unsigned lane, unsigned bins_per_tile) {
+// no ray of pixel (px, py) can reach the scene's bounds (RenderArgs::cull_*, computed in make_plan)
+TPT_DEV bool pixel_bundle_misses(const RenderArgs &A, int px, int py) {
+  return px < A.cull_x0 || px > A.cull_x1 || py < A.cull_y0 || py > A.cull_y1;
+}
+
+template <bool CULL>
+TPT_DEV void lane_bin_refill(const RenderArgs &A, LaneBin &B, bool need, unsigned lane, unsigned bins_per_tile,
+                             unsigned long long &n_paths, unsigned long long &n_culled) {
   const unsigned FULL = 0xffffffffu;
   if (need && B.have_bin) { // bin finished: one store per (pixel, range)
     float *o = A.acc + (size_t)B.acc_index * 3;
@@ -85,8 +92,9 @@ TPT_DEV void lane_bin_refill(const RenderArgs &A, LaneBin &B, bool need, unsigne
     o[2] = B.acc.z;
     B.have_bin = false;
   }
-  unsigned m = __ballot_sync(FULL, need);
-  if (m) {
+  for (;;) { // until every lane that needs a bin holds one it has to trace, or the counter is dry
+    unsigned m = __ballot_sync(FULL, need);
+    if (!m) break;
     unsigned long long base = 0;
     int leader = __ffs(m) - 1;
     if ((int)lane == leader) base = atomicAdd(A.counters + 0, (unsigned long long)__popc(m));
@@ -95,6 +103,7 @@ TPT_DEV void lane_bin_refill(const RenderArgs &A, LaneBin &B, bool need, unsigne
       unsigned long long b = base + __popc(m & ((1u << lane) - 1u));
       if (b >= A.n_bins) {
         B.exhausted = true;
+        need = false;
       } else {
         unsigned bb = (unsigned)b;
         unsigned tile_local = bb / bins_per_tile;
@@ -106,11 +115,21 @@ TPT_DEV void lane_bin_refill(const RenderArgs &A, LaneBin &B, bool need, unsigne
         B.px = (int)(tx * TPT_TILE + (pit & (TPT_TILE - 1)));
         B.py = (int)(ty * TPT_TILE + (pit / TPT_TILE));
         if (B.px < A.nx && B.py < A.ny) {
-          B.have_bin = true;
           B.k = A.range_bounds[range];
           B.k_end = A.range_bounds[range + 1];
-          B.acc = mk(0, 0, 0);
           B.acc_index = range * (unsigned)(A.nx * A.ny) + (unsigned)(B.py * A.nx + B.px);
+          if (CULL && pixel_bundle_misses(A, B.px, B.py)) {
+            float *o = A.acc + (size_t)B.acc_index * 3; // the bin's sum is exactly 0: finished
+            o[0] = 0.f;
+            o[1] = 0.f;
+            o[2] = 0.f;
+            n_paths += (unsigned long long)(B.k_end - B.k);
+            n_culled += (unsigned long long)(B.k_end - B.k);
+          } else {
+            B.have_bin = true;
+            B.acc = mk(0, 0, 0);
+            need = false;
+          }
         }
       }
     }
@@ -129,7 +148,7 @@ TPT_DEV void lane_bin_refill(const RenderArgs &A, LaneBin &B, bool need, unsigne
 // Bins are ordered tile-major with the pixel index fastest: the 32 lanes of a warp work on 32
 // neighbouring pixels of one tile.
 // ------------------------------------------------------------------------------------------
-template <bool PAR, bool SMEM, bool SMALL, bool MEDIA>
+template <bool PAR, bool SMEM, bool SMALL, bool MEDIA, bool CULL>
 __global__ void __launch_bounds__(TPT_MEGA_THREADS) render_mega_kernel(const __grid_constant__ RenderArgs A) {
   extern __shared__ float4 sblob[];
   SceneView S;
@@ -148,11 +167,11 @@ __global__ void __launch_bounds__(TPT_MEGA_THREADS) render_mega_kernel(const __g
   B.acc = mk(0, 0, 0);
   PathState ps;
   Rng rng;
-  unsigned long long n_rays = 0, n_nan = 0, n_paths = 0;
+  unsigned long long n_rays = 0, n_nan = 0, n_paths = 0, n_culled = 0;
   const unsigned bins_per_tile = (unsigned)(TPT_TILE * TPT_TILE) * (unsigned)A.n_ranges;
 
   for (;;) {
-    lane_bin_refill(A, B, !active && !B.exhausted && (!B.have_bin || B.k >= B.k_end), lane, bins_per_tile);
+    lane_bin_refill<CULL>(A, B, !active && !B.exhausted && (!B.have_bin || B.k >= B.k_end), lane, bins_per_tile, n_paths, n_culled);
     if (!active && B.have_bin && B.k < B.k_end) { // next sample of this lane's pixel
       rng.begin(A.seed_lo, A.seed_hi, (uint32_t)(B.py * A.nx + B.px), (uint32_t)B.k);
       ps.ray = camera_sample<PAR>(A.cam, B.px, B.py, A.nx, A.ny, rng);
@@ -184,11 +203,13 @@ __global__ void __launch_bounds__(TPT_MEGA_THREADS) render_mega_kernel(const __g
     n_rays += __shfl_xor_sync(FULL, n_rays, o);
     n_nan += __shfl_xor_sync(FULL, n_nan, o);
     n_paths += __shfl_xor_sync(FULL, n_paths, o);
+    n_culled += __shfl_xor_sync(FULL, n_culled, o);
   }
   if (lane == 0) {
     atomicAdd(A.counters + 1, n_rays);
     atomicAdd(A.counters + 2, n_nan);
     atomicAdd(A.counters + 3, n_paths);
+    if (n_culled) atomicAdd(A.counters + 4, n_culled);
   }
 }
 
@@ -219,7 +240,7 @@ __global__ void __launch_bounds__(TPT_MEGA_THREADS) render_mega_kernel(const __g
 // ------------------------------------------------------------------------------------------
 #define TPT_WAVE_NQ 4 // queues: 0 lambertian, 1 metal, 2 dielectric (= TPT_MAT_*), 3 generate
 
-template <bool PAR, bool SMALL, bool SMEM, bool MEDIA, bool TRACE = false>
+template <bool PAR, bool SMALL, bool SMEM, bool MEDIA, bool CULL, bool TRACE = false>
 __global__ void __launch_bounds__(TPT_WAVE_THREADS, TRACE ? TPT_TRACE_MIN_BLOCKS : TPT_WAVE_MIN_BLOCKS)
 render_wave_kernel(const __grid_constant__ RenderArgs A) {
   extern __shared__ float4 sblob[];
@@ -254,7 +275,7 @@ render_wave_kernel(const __grid_constant__ RenderArgs A) {
   const unsigned lt_mask = (1u << lane) - 1u;
   const int warp = tid >> 5;
   const unsigned bins_per_tile = (unsigned)(TPT_TILE * TPT_TILE) * (unsigned)A.n_ranges;
-  unsigned long long n_rays = 0, n_nan = 0, n_paths = 0;
+  unsigned long long n_rays = 0, n_nan = 0, n_paths = 0, n_culled = 0;
 
   for (int s = tid; s < NSLOT; s += TPT_WAVE_THREADS) {
     SI(F_ACTIVE, s) = 0;
@@ -474,17 +495,29 @@ render_wave_kernel(const __grid_constant__ RenderArgs A) {
                 int px = (int)(tx * TPT_TILE + (pit & (TPT_TILE - 1)));
                 int py = (int)(ty * TPT_TILE + (pit / TPT_TILE));
                 if (px < A.nx && py < A.ny) {
-                  need = false;
-                  have_bin = true;
-                  pixel = px | (py << 16); // packed: no division when the camera ray is generated
-                  k = A.range_bounds[range];
-                  k_end = A.range_bounds[range + 1];
-                  SI(F_PIXEL, s) = pixel;
-                  SI(F_KEND, s) = k_end;
-                  SI(F_ACCIDX, s) = (int)(range * (unsigned)(A.nx * A.ny) + (unsigned)(py * A.nx + px));
-                  SF(F_AX, s) = 0.f;
-                  SF(F_AY, s) = 0.f;
-                  SF(F_AZ, s) = 0.f;
+                  const unsigned acc_index = range * (unsigned)(A.nx * A.ny) + (unsigned)(py * A.nx + px);
+                  if (CULL && pixel_bundle_misses(A, px, py)) {
+                    // no ray of this pixel reaches the scene: the bin's sum is exactly 0, take another
+                    float *o = A.acc + (size_t)acc_index * 3;
+                    o[0] = 0.f;
+                    o[1] = 0.f;
+                    o[2] = 0.f;
+                    const int cnt = A.range_bounds[range + 1] - A.range_bounds[range];
+                    n_paths += (unsigned long long)cnt;
+                    n_culled += (unsigned long long)cnt;
+                  } else {
+                    need = false;
+                    have_bin = true;
+                    pixel = px | (py << 16); // packed: no division when the camera ray is generated
+                    k = A.range_bounds[range];
+                    k_end = A.range_bounds[range + 1];
+                    SI(F_PIXEL, s) = pixel;
+                    SI(F_KEND, s) = k_end;
+                    SI(F_ACCIDX, s) = (int)acc_index;
+                    SF(F_AX, s) = 0.f;
+                    SF(F_AY, s) = 0.f;
+                    SF(F_AZ, s) = 0.f;
+                  }
                 }
               }
             }
@@ -542,11 +575,13 @@ render_wave_kernel(const __grid_constant__ RenderArgs A) {
     n_rays += __shfl_xor_sync(FULL, n_rays, o);
     n_nan += __shfl_xor_sync(FULL, n_nan, o);
     n_paths += __shfl_xor_sync(FULL, n_paths, o);
+    n_culled += __shfl_xor_sync(FULL, n_culled, o);
   }
   if (lane == 0) {
     atomicAdd(A.counters + 1, n_rays);
     atomicAdd(A.counters + 2, n_nan);
     atomicAdd(A.counters + 3, n_paths);
+    if (n_culled) atomicAdd(A.counters + 4, n_culled);
   }
 }
 
@@ -592,16 +627,20 @@ cudaError_t TPT_FN(launch_intersect_)(const IntersectArgs &A, bool smem, bool sm
   return cudaGetLastError();
 }
 
-// kernel variant table: [smem][small], or the media build (generic walk, scene staged when it fits)
+// kernel variant tables: [smem][small] or the media build (generic walk, scene staged when it
+// fits), each with and without the pixel-bundle bounds test compiled in (RenderArgs::cull)
 typedef void (*mega_fn)(RenderArgs);
-static mega_fn mega_variant(bool smem, bool small, bool media) {
-  if (media) return smem ? render_mega_kernel<TPT_PAR, true, false, true> : render_mega_kernel<TPT_PAR, false, false, true>;
-  if (smem) return small ? render_mega_kernel<TPT_PAR, true, true, false> : render_mega_kernel<TPT_PAR, true, false, false>;
-  return render_mega_kernel<TPT_PAR, false, false, false>;
+template <bool CULL> static mega_fn mega_variant_c(bool smem, bool small, bool media) {
+  if (media) return smem ? render_mega_kernel<TPT_PAR, true, false, true, CULL> : render_mega_kernel<TPT_PAR, false, false, true, CULL>;
+  if (smem) return small ? render_mega_kernel<TPT_PAR, true, true, false, CULL> : render_mega_kernel<TPT_PAR, true, false, false, CULL>;
+  return render_mega_kernel<TPT_PAR, false, false, false, CULL>;
+}
+static mega_fn mega_variant(const RenderArgs &A, bool smem, bool small, bool media) {
+  return A.cull ? mega_variant_c<true>(smem, small, media) : mega_variant_c<false>(smem, small, media);
 }
 
-cudaError_t TPT_FN(mega_occupancy_)(bool smem, bool small, bool media, size_t smem_bytes, int *blocks_per_sm) {
-  mega_fn k = mega_variant(smem, small, media);
+cudaError_t TPT_FN(mega_occupancy_)(const RenderArgs &A, bool smem, bool small, bool media, size_t smem_bytes, int *blocks_per_sm) {
+  mega_fn k = mega_variant(A, smem, small, media);
   cudaError_t e;
   if (smem && (e = allow_smem(k, smem_bytes)) != cudaSuccess) return e;
   return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k, TPT_MEGA_THREADS, smem ? smem_bytes : 0);
@@ -609,21 +648,24 @@ cudaError_t TPT_FN(mega_occupancy_)(bool smem, bool small, bool media, size_t sm
 
 cudaError_t TPT_FN(launch_mega_)(const RenderArgs &A, bool smem, bool small, bool media, int blocks, cudaStream_t st) {
   size_t bytes = smem ? (size_t)A.scene.blob_words * 16 : 0;
-  mega_variant(smem, small, media)<<<blocks, TPT_MEGA_THREADS, bytes, st>>>(A);
+  mega_variant(A, smem, small, media)<<<blocks, TPT_MEGA_THREADS, bytes, st>>>(A);
   return cudaGetLastError();
 }
 
 typedef void (*wave_fn)(RenderArgs);
 // `trace` (FAST only): closest hits through the library's SAH BVH with dynamic ray hand-out; the
 // scene tables are read through L1 there and shared memory holds TPT_TRACE_SLOTS path slots.
-static wave_fn wave_variant(bool small, bool smem, bool media, bool trace) {
+template <bool CULL> static wave_fn wave_variant_c(bool small, bool smem, bool media, bool trace) {
 #if !TPT_PAR
-  if (trace) return media ? render_wave_kernel<false, false, false, true, true> : render_wave_kernel<false, false, false, false, true>;
+  if (trace) return media ? render_wave_kernel<false, false, false, true, CULL, true> : render_wave_kernel<false, false, false, false, CULL, true>;
 #endif
   (void)trace;
-  if (media) return smem ? render_wave_kernel<TPT_PAR, false, true, true> : render_wave_kernel<TPT_PAR, false, false, true>;
-  if (!smem) return render_wave_kernel<TPT_PAR, false, false, false>;
-  return small ? render_wave_kernel<TPT_PAR, true, true, false> : render_wave_kernel<TPT_PAR, false, true, false>;
+  if (media) return smem ? render_wave_kernel<TPT_PAR, false, true, true, CULL> : render_wave_kernel<TPT_PAR, false, false, true, CULL>;
+  if (!smem) return render_wave_kernel<TPT_PAR, false, false, false, CULL>;
+  return small ? render_wave_kernel<TPT_PAR, true, true, false, CULL> : render_wave_kernel<TPT_PAR, false, true, false, CULL>;
+}
+static wave_fn wave_variant(const RenderArgs &A, bool small, bool smem, bool media, bool trace) {
+  return A.cull ? wave_variant_c<true>(small, smem, media, trace) : wave_variant_c<false>(small, smem, media, trace);
 }
 static size_t wave_smem_bytes(const RenderArgs &A, bool smem, bool trace) {
   if (trace && !TPT_PAR) return (size_t)TPT_TRACE_SLOTS * (22 * 4 + 2 * TPT_WAVE_NQ * 2);
@@ -631,7 +673,7 @@ static size_t wave_smem_bytes(const RenderArgs &A, bool smem, bool trace) {
 }
 
 cudaError_t TPT_FN(wave_occupancy_)(const RenderArgs &A, bool small, bool smem, bool media, bool trace, int *blocks_per_sm) {
-  wave_fn k = wave_variant(small, smem, media, trace);
+  wave_fn k = wave_variant(A, small, smem, media, trace);
   size_t bytes = wave_smem_bytes(A, smem, trace);
   cudaError_t e = allow_smem(k, bytes);
   if (e != cudaSuccess) return e;
@@ -639,7 +681,7 @@ cudaError_t TPT_FN(wave_occupancy_)(const RenderArgs &A, bool small, bool smem, 
 }
 
 cudaError_t TPT_FN(launch_wave_)(const RenderArgs &A, bool small, bool smem, bool media, bool trace, int blocks, cudaStream_t st) {
-  wave_variant(small, smem, media, trace)<<<blocks, TPT_WAVE_THREADS, wave_smem_bytes(A, smem, trace), st>>>(A);
+  wave_variant(A, small, smem, media, trace)<<<blocks, TPT_WAVE_THREADS, wave_smem_bytes(A, smem, trace), st>>>(A);
   return cudaGetLastError();
 }
 

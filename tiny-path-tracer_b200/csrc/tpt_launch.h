@@ -52,7 +52,14 @@ struct RenderArgs {
   int tiles_x, tiles_y, part_index, part_count;
   unsigned long long n_bins;             // local tiles x TILE^2 x n_ranges
   float *acc;                            // [n_ranges][ny*nx][3] per-range radiance sums
-  unsigned long long *counters;          // [0] next bin, [1] rays, [2] NaN samples, [3] paths
+  unsigned long long *counters;          // [0] next bin, [1] rays, [2] NaN samples, [3] paths, [4] paths resolved by the bundle test
+  // Pixel-bundle bounds test (black background only): the rectangle of pixels [cull_x0, cull_x1] x
+  // [cull_y0, cull_y1] outside of which no ray the camera can generate -- any lens point, any
+  // jitter -- reaches the scene's padded root box (computed on the host, make_plan). A (pixel,
+  // sample range) bin outside it is finished when it is taken: world->hit is false for all its
+  // rays, so the bin's sum is exactly 0.
+  int cull;
+  int cull_x0, cull_x1, cull_y0, cull_y1;
 };
 
 struct TextureProbeArgs {
@@ -67,8 +74,8 @@ cudaError_t launch_intersect_parity(const IntersectArgs &A, bool smem, bool smal
 cudaError_t launch_intersect_fast(const IntersectArgs &A, bool smem, bool small, cudaStream_t st);
 // `media`: scene has constant_medium primitives (the stream is threaded through world->hit)
 // `small`: scene has few enough primitives for the warp-uniform brute-force closest hit
-cudaError_t mega_occupancy_parity(bool smem, bool small, bool media, size_t smem_bytes, int *blocks_per_sm);
-cudaError_t mega_occupancy_fast(bool smem, bool small, bool media, size_t smem_bytes, int *blocks_per_sm);
+cudaError_t mega_occupancy_parity(const RenderArgs &A, bool smem, bool small, bool media, size_t smem_bytes, int *blocks_per_sm);
+cudaError_t mega_occupancy_fast(const RenderArgs &A, bool smem, bool small, bool media, size_t smem_bytes, int *blocks_per_sm);
 cudaError_t launch_mega_parity(const RenderArgs &A, bool smem, bool small, bool media, int blocks, cudaStream_t st);
 cudaError_t launch_mega_fast(const RenderArgs &A, bool smem, bool small, bool media, int blocks, cudaStream_t st);
 // persistent wavefront variant (`smem`: scene tables staged in shared memory, else read through L1)
