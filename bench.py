@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--variant", default="A", choices=["A", "B"])
     ap.add_argument("--kernel", default="wavefront", choices=["wavefront", "mega"])
     ap.add_argument("--spp", type=int, default=NS, help="override samples per pixel (default: the headline 2048)")
+    ap.add_argument("--size", type=int, default=NX, help="frame edge in pixels (default 1200; BASELINE configs[4] is 4096 with --spp 4096)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--bundle-cull", action="store_true",
                     help="headline with the library's default pixel-bundle bounds test on (pixels that cannot see the "
@@ -142,7 +143,7 @@ def cpu_reference_sample(variant, target_seconds, threads=0):
     spp = int(max(1, min(64, round(target_seconds / max(per_spp, 1e-3)))))
     _, _, st = rs.render(cam, NX, NY, spp, v["depth"], deterministic=False, threads=threads, count_rays=False)
     return {"value": st["paths"] / st["seconds"] / 1e6, "unit": "Mpaths/s", "cores": st["threads"], "kind": "reference",
-            "sample": f"Cornell variant {variant} full 1200x1200 frame at {spp} spp ({st['paths']} paths, {st['seconds']:.1f} s): "
+            "sample": f"Cornell variant {variant} full {NX}x{NY} frame at {spp} spp ({st['paths']} paths, {st['seconds']:.1f} s): "
                       f"reference color()/hit/scatter (oracle/_ref/libtptref.so, mt19937 drand_r) on {st['threads']} threads",
             "seconds": st["seconds"], "spp": spp}
 
@@ -171,11 +172,11 @@ def run_reference_arm(args, rank, world):
     t = sum(secs)
     value = paths * len(secs) / t / 1e6
     line = {
-        "impl": "reference", "metric": "Cornell 1200x1200 path-tracing throughput", "value": value, "unit": "Mpaths/s",
+        "impl": "reference", "metric": f"Cornell {NX}x{NY} path-tracing throughput", "value": value, "unit": "Mpaths/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / len(secs),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": value / PUBLISHED_MPATHS, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": f"Cornell box metal+glass 1200x1200, variant {args.variant} (fov {v['fov']}, depth {v['depth']}), "
+        "config": {"workload": f"Cornell box metal+glass {NX}x{NY}, variant {args.variant} (fov {v['fov']}, depth {v['depth']}), "
                                f"bounded sample {spp} spp per step of the 2048-spp job", "spp_per_step": spp},
         "cpu_baseline": {"value": value, "unit": "Mpaths/s", "cores": first["cores"], "kind": "reference",
                          "sample": first["sample"]},
@@ -281,6 +282,7 @@ def run_ours(args, rank, local_rank, world):
         barrier()
         t0 = time.perf_counter()
         s = T.Scene(hs, device=local_rank)  # flattened scene -> HBM
+        t_created = time.perf_counter()
         if dist is None:
             T._check(T.lib().tpt_render(s._s, C.byref(cam), C.byref(params), C.byref(img)))
         else:
@@ -297,12 +299,13 @@ def run_ours(args, rank, local_rank, world):
                 T._check(T.lib().tpt_render_fetch(s._s, C.byref(img)))
         st2 = s.stats()
         loss = float(sum_host[0, NY // 2, NX // 2, 1])  # the step's result is read on the host
+        t_rendered = time.perf_counter()
         s.close()
         barrier()
         if i >= E2E_WARM:
             e2e_s.append(time.perf_counter() - t0)
         if os.environ.get("TPT_BENCH_DEBUG") and rank == 0:
-            sys.stderr.write(f"e2e iter {i}: {time.perf_counter() - t0:.4f} s  render_ms {st2['render_ms']:.1f} wall_ms {st2['wall_ms']:.1f} d2h_ms {st2['d2h_ms']:.1f}\n")
+            sys.stderr.write(f"e2e iter {i}: {time.perf_counter() - t0:.4f} s (create {t_created - t0:.4f}, render+fetch {t_rendered - t_created:.4f}, destroy {time.perf_counter() - t_rendered:.4f})  render_ms {st2['render_ms']:.1f} wall_ms {st2['wall_ms']:.1f} d2h_ms {st2['d2h_ms']:.1f}\n")
         h2d = int(st2["h2d_bytes"])  # flattened scene blob + camera/params launch arguments
         d2h = int(st2["d2h_bytes"]) if rank == 0 else 0
     e2e_step = max_over_ranks(statistics.mean(e2e_s))
@@ -388,11 +391,11 @@ def run_ours(args, rank, local_rank, world):
         except Exception as e:  # the checker must never take the bench down
             cpu = {"value": None, "unit": "Mpaths/s", "cores": 0, "kind": "reference", "sample": f"failed: {e}"}
     line = {
-        "metric": "Cornell 1200x1200 path-tracing throughput", "value": value, "unit": "Mpaths/s", "n_gpus": world,
+        "metric": f"Cornell {NX}x{NY} path-tracing throughput", "value": value, "unit": "Mpaths/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": value / PUBLISHED_MPATHS, "dtype": "f32" if args.mode == "fast" else "f32+f64",
         "data": "synthetic",
-        "config": {"workload": f"Cornell box metal+glass 1200x1200 @ {args.spp} spp, variant {args.variant} "
+        "config": {"workload": f"Cornell box metal+glass {NX}x{NY} @ {args.spp} spp, variant {args.variant} "
                                f"(fov {v['fov']}, depth {v['depth']}, aperture 0.1), {args.mode} mode, {args.kernel} kernel",
                    "paths_per_step": total_paths / args.steps, "partition": f"static interleaved 16x16 tiles over {world} rank(s)",
                    "l2": "256 MiB memset between steps (flush); scene working set is shared-memory resident",
@@ -415,7 +418,9 @@ def run_ours(args, rank, local_rank, world):
 
 
 def main():
+    global NX, NY
     args = parse()
+    NX = NY = args.size
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -15,6 +15,7 @@
 #include <atomic>
 #include <string>
 #include <thread>
+#include <mutex>
 #include <vector>
 
 using namespace tptd;
@@ -1153,19 +1154,37 @@ int tpt_scene_create(const tpt_scene_desc *d, int device, tpt_scene **out) {
   CK(cudaSetDevice(device));
   tpt_scene *s = new tpt_scene();
   s->device = device;
-  CK(cudaGetDeviceProperties(&s->prop, device));
+  {
+    // cudaGetDeviceProperties is a slow driver query (3 ms typical, 100+ ms now and then): once
+    // per device and process; the same for the memory pool's release threshold
+    static std::mutex mu;
+    static std::vector<std::pair<int, cudaDeviceProp>> cache;
+    std::lock_guard<std::mutex> lock(mu);
+    const cudaDeviceProp *hit = nullptr;
+    for (auto &c : cache)
+      if (c.first == device) hit = &c.second;
+    if (!hit) {
+      cudaDeviceProp prop;
+      cudaError_t pe = cudaGetDeviceProperties(&prop, device);
+      if (pe != cudaSuccess) {
+        delete s;
+        return fail(TPT_ERR_CUDA, cudaGetErrorString(pe));
+      }
+      cudaMemPool_t pool;
+      if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        unsigned long long keep = ~0ULL;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+      }
+      cache.emplace_back(device, prop);
+      hit = &cache.back().second;
+    }
+    s->prop = *hit;
+  }
   if (s->prop.major < 10) {
     delete s;
     return fail(TPT_ERR_NO_DEVICE, "device is not sm_100-class; kernels are built for sm_100a only");
   }
   CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
-  {
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-      unsigned long long keep = ~0ULL;
-      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-    }
-  }
   for (auto &ev : s->ev) CK(cudaEventCreate(&ev));
 
   // ---- blob: the C structs back to back, each table padded to 16 bytes ----

@@ -133,6 +133,7 @@ TPT_DEV void lane_bin_refill(const RenderArgs &A, LaneBin &B, bool need, unsigne
         }
       }
     }
+    if (!CULL) break; // without the bundle test a lane asks once per outer iteration (out-of-frame pixels of a partial tile: it asks again next time)
   }
 }
 

@@ -10,3 +10,6 @@ python bench.py --steps 2 --warmup 3 --mode parity --spp 256 --no-cpu-baseline >
 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:render_wave -s 1 -c 1 -f -o gpurun_out/prof_wave python bench.py --steps 1 --warmup 1 --spp 256 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
 ls -la gpurun_out | head -30
+# BVH / texture scenes: throughput + one full capture each (L1/L2 hit rates, DRAM traffic)
+python tools/gpu_bvh_perf.py 32 > gpurun_out/bvh_perf.txt 2>&1; cat gpurun_out/bvh_perf.txt
+KERN=1 bash tools/gpu_prof_scenes.sh > gpurun_out/scenes_perf.txt 2>&1; cat gpurun_out/scenes_perf.txt
