@@ -119,6 +119,11 @@ struct tpt_scene {
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaDeviceProp prop{};
+  // Pool of the image products (sums, 8-bit pictures): the one tpt_render_multi opens to GPU 0 for
+  // the NVLink gather. The big per-range accumulators stay in the device's default pool, which is
+  // never peer-mapped (a peer-mapped pool refused allocations above ~2 GB: "out of memory").
+  cudaMemPool_t products = nullptr;
+  bool products_private = false; // some product had to come from the default pool: gather through staged copies
   SceneLayout layout{};
   float4 *d_blob = nullptr;
   size_t blob_bytes = 0;
@@ -580,13 +585,25 @@ void build_small_scene(const tpt_scene_desc *d, int n_root, bool smem_ok, SmallS
 // keeps freed blocks (release threshold = max, set in tpt_scene_create), so creating a scene,
 // rendering and destroying it again -- the end-to-end pattern of a short-lived caller -- does not
 // pay cudaMalloc / cudaFree device synchronisations and page (un)mapping every time.
-int ensure(cudaStream_t st, void **p, size_t &have, size_t want) {
+// `pool`: the device's products pool (see products_pool) or nullptr for the default pool
+int ensure(cudaStream_t st, void **p, size_t &have, size_t want, cudaMemPool_t pool = nullptr, bool *fell_back = nullptr) {
   if (have >= want && *p) return TPT_OK;
   if (*p) cudaFreeAsync(*p, st);
   *p = nullptr;
   have = 0;
-  cudaError_t e = cudaMallocAsync(p, want, st);
-  if (e != cudaSuccess) return cuda_fail(e, "cudaMallocAsync");
+  cudaError_t e = pool ? cudaMallocFromPoolAsync(p, want, pool, st) : cudaMallocAsync(p, want, st);
+  if (e != cudaSuccess && pool) { // e.g. a product too large to be peer-mapped: private memory, staged gather
+    cudaGetLastError();
+    e = cudaMallocAsync(p, want, st);
+    if (fell_back) *fell_back = true;
+  }
+  if (e != cudaSuccess) {
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    char what[160];
+    std::snprintf(what, sizeof(what), "cudaMallocAsync(%zu bytes; device reports %zu of %zu free)", want, free_b, total_b);
+    return cuda_fail(e, what);
+  }
   have = want;
   return TPT_OK;
 }
@@ -787,9 +804,9 @@ int run_plan(tpt_scene *s, Plan &plan, bool want_sum, bool want_rgb8, bool want_
   size_t acc_want = (size_t)A.n_ranges * plan.npix * 3 * sizeof(float);
   if ((rc = ensure(s->stream, (void **)&s->d_acc, s->acc_bytes, acc_want)) != TPT_OK) return rc;
   size_t sum_want = (size_t)R.slices * plan.npix * 3 * sizeof(float);
-  if ((rc = ensure(s->stream, (void **)&s->d_sum, s->sum_bytes, sum_want)) != TPT_OK) return rc;
-  if ((rc = ensure(s->stream, (void **)&s->d_rgb8, s->rgb8_bytes, plan.npix * 3)) != TPT_OK) return rc;
-  if ((rc = ensure(s->stream, (void **)&s->d_rgb8_slices, s->rgb8_slices_bytes, (size_t)R.slices * plan.npix * 3)) != TPT_OK) return rc;
+  if ((rc = ensure(s->stream, (void **)&s->d_sum, s->sum_bytes, sum_want, s->products, &s->products_private)) != TPT_OK) return rc;
+  if ((rc = ensure(s->stream, (void **)&s->d_rgb8, s->rgb8_bytes, plan.npix * 3, s->products, &s->products_private)) != TPT_OK) return rc;
+  if ((rc = ensure(s->stream, (void **)&s->d_rgb8_slices, s->rgb8_slices_bytes, (size_t)R.slices * plan.npix * 3, s->products, &s->products_private)) != TPT_OK) return rc;
   A.acc = s->d_acc;
   A.counters = s->d_counters;
   R.acc = s->d_acc;
@@ -913,9 +930,9 @@ int prepare_buffers(tpt_scene *s, Plan &plan, bool want_slices) {
   int rc;
   size_t acc_want = (size_t)A.n_ranges * plan.npix * 3 * sizeof(float);
   if ((rc = ensure(s->stream, (void **)&s->d_acc, s->acc_bytes, acc_want)) != TPT_OK) return rc;
-  if ((rc = ensure(s->stream, (void **)&s->d_sum, s->sum_bytes, (size_t)R.slices * plan.npix * 3 * sizeof(float))) != TPT_OK) return rc;
-  if ((rc = ensure(s->stream, (void **)&s->d_rgb8, s->rgb8_bytes, plan.npix * 3)) != TPT_OK) return rc;
-  if ((rc = ensure(s->stream, (void **)&s->d_rgb8_slices, s->rgb8_slices_bytes, (size_t)R.slices * plan.npix * 3)) != TPT_OK) return rc;
+  if ((rc = ensure(s->stream, (void **)&s->d_sum, s->sum_bytes, (size_t)R.slices * plan.npix * 3 * sizeof(float), s->products, &s->products_private)) != TPT_OK) return rc;
+  if ((rc = ensure(s->stream, (void **)&s->d_rgb8, s->rgb8_bytes, plan.npix * 3, s->products, &s->products_private)) != TPT_OK) return rc;
+  if ((rc = ensure(s->stream, (void **)&s->d_rgb8_slices, s->rgb8_slices_bytes, (size_t)R.slices * plan.npix * 3, s->products, &s->products_private)) != TPT_OK) return rc;
   R.acc = s->d_acc;
   R.sum_rgb = s->d_sum;
   R.rgb8 = s->d_rgb8;
@@ -1053,13 +1070,12 @@ int render_multi(tpt_scene *const *scenes, int n, const tpt_camera *cam, const t
       if (can) {
         // the products live in GPU g's stream-ordered pool: pools are private to their device
         // until access is granted explicitly (cudaDeviceEnablePeerAccess does not cover them)
-        cudaMemPool_t pool;
         cudaMemAccessDesc acc_desc{};
         acc_desc.location.type = cudaMemLocationTypeDevice;
         acc_desc.location.id = s0->device;
         acc_desc.flags = cudaMemAccessFlagsProtReadWrite;
-        if (cudaDeviceGetDefaultMemPool(&pool, scenes[g]->device) != cudaSuccess ||
-            cudaMemPoolSetAccess(pool, &acc_desc, 1) != cudaSuccess) {
+        if (!scenes[g]->products || scenes[g]->products_private ||
+            cudaMemPoolSetAccess(scenes[g]->products, &acc_desc, 1) != cudaSuccess) {
           cudaGetLastError();
           can = 0;
         }
@@ -1158,11 +1174,12 @@ int tpt_scene_create(const tpt_scene_desc *d, int device, tpt_scene **out) {
     // cudaGetDeviceProperties is a slow driver query (3 ms typical, 100+ ms now and then): once
     // per device and process; the same for the memory pool's release threshold
     static std::mutex mu;
-    static std::vector<std::pair<int, cudaDeviceProp>> cache;
+    struct DeviceOnce { int device; cudaDeviceProp prop; cudaMemPool_t products; };
+    static std::vector<DeviceOnce> cache;
     std::lock_guard<std::mutex> lock(mu);
-    const cudaDeviceProp *hit = nullptr;
+    const DeviceOnce *hit = nullptr;
     for (auto &c : cache)
-      if (c.first == device) hit = &c.second;
+      if (c.device == device) hit = &c;
     if (!hit) {
       cudaDeviceProp prop;
       cudaError_t pe = cudaGetDeviceProperties(&prop, device);
@@ -1175,10 +1192,24 @@ int tpt_scene_create(const tpt_scene_desc *d, int device, tpt_scene **out) {
         unsigned long long keep = ~0ULL;
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
       }
-      cache.emplace_back(device, prop);
-      hit = &cache.back().second;
+      cudaMemPool_t products = nullptr;
+      cudaMemPoolProps pp{};
+      pp.allocType = cudaMemAllocationTypePinned;
+      pp.handleTypes = cudaMemHandleTypeNone;
+      pp.location.type = cudaMemLocationTypeDevice;
+      pp.location.id = device;
+      if (cudaMemPoolCreate(&products, &pp) == cudaSuccess) {
+        unsigned long long keep = ~0ULL;
+        cudaMemPoolSetAttribute(products, cudaMemPoolAttrReleaseThreshold, &keep);
+      } else {
+        cudaGetLastError();
+        products = nullptr; // products fall back to the default pool, the gather to staged copies
+      }
+      cache.push_back(DeviceOnce{device, prop, products});
+      hit = &cache.back();
     }
-    s->prop = *hit;
+    s->prop = hit->prop;
+    s->products = hit->products;
   }
   if (s->prop.major < 10) {
     delete s;
