@@ -15,7 +15,8 @@ WANT = {
     "smsp__thread_inst_executed_per_inst_executed.ratio": "active_threads_per_inst",
     "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active": "fma_pipe_pct",
     "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active": "alu_pipe_pct",
-    "sm__issue_active.avg.pct_of_peak_sustained_active": "issue_active_pct",
+    "sm__inst_issued.avg.pct_of_peak_sustained_active": "issue_active_pct",
+    "sm__inst_executed.avg.per_cycle_active": "ipc_active",
     "sm__warps_active.avg.pct_of_peak_sustained_active": "achieved_occupancy_pct",
     "l1tex__t_sector_hit_rate.pct": "l1_hit_pct",
     "lts__t_sector_hit_rate.pct": "l2_hit_pct",
