@@ -13,8 +13,9 @@ for scene, camf in (("cornell_box", T.cornell_camera), ("random_scene", T.book_c
     cam = camf(40, 24)
     for mode in (T.MODE_PARITY, T.MODE_FAST):
         for kern in (T.KERNEL_MEGA, T.KERNEL_WAVEFRONT):
-            r = sc.render(cam, T.make_params(40, 24, 4, 8, mode=mode, seed=1, kernel=kern, slices=2), want_slices=True)
-            print(scene, mode, kern, r.stats["paths"], float(r.sum_rgb.mean()))
+            for cull in (True, False):  # kernel builds with and without the pixel-bundle bounds test
+                r = sc.render(cam, T.make_params(40, 24, 4, 8, mode=mode, seed=1, kernel=kern, slices=2, bundle_cull=cull), want_slices=True)
+                print(scene, mode, kern, cull, r.stats["paths"], r.stats["culled_paths"], float(r.sum_rgb.mean()))
         if scene not in ("cornell_box_smoke", "oneweek_final"):  # tpt_intersect_batch refuses media scenes
             sc.intersect(raygen.primary_batch(scene, 200, 200, seed=1), mode=mode)
     sc.close()
