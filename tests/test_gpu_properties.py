@@ -231,3 +231,34 @@ def test_config5_frame_size(T, cornell):
     assert paths == nx * ny
     r = cornell.fetch(T.make_params(nx, ny, 1, 15), want_sum=False)
     assert r.rgb8.shape == (ny, nx, 3)
+
+
+def test_pixel_bundle_test_random_cameras(T, gpu):
+    """the bundle test against brute force over many cameras: positions inside, beside and behind
+    the scene, large and zero apertures, tilted up-vectors, non-square frames, list-rooted and
+    BVH-rooted scenes, moving spheres. Images and NaN counts must be identical with the test on and
+    off, traced rays must differ by exactly the untraced paths."""
+    rng = np.random.default_rng(2024)
+    scenes = {name: T.Scene(common.host_scene(T, name)) for name in ("cornell_box", "light_spheres", "random_scene")}
+    extent = {"cornell_box": 300.0, "light_spheres": 6.0, "random_scene": 12.0}
+    culled_some = 0
+    for trial in range(60):
+        name = ("cornell_box", "light_spheres", "random_scene")[trial % 3]
+        sc, e = scenes[name], extent[name]
+        lookfrom = rng.uniform(-3.5 * e, 3.5 * e, 3)
+        lookat = rng.uniform(-1.5 * e, 1.5 * e, 3) if trial % 5 else lookfrom + rng.uniform(-1, 1, 3)
+        vup = np.array([0.0, 1.0, 0.0]) + (rng.uniform(-0.4, 0.4, 3) if trial % 2 else 0.0)
+        nx, ny = [(48, 48), (64, 40), (37, 53)][trial % 3]
+        fov = float(rng.uniform(10.0, 120.0))
+        aperture = float([0.0, 0.1, 0.5 * e, 2.5 * e][trial % 4])
+        focus = float(rng.uniform(0.2 * e, 4.0 * e))
+        t1 = 1.0 if name == "random_scene" and trial % 2 else 0.0
+        cam = T.make_camera(tuple(lookfrom), tuple(lookat), tuple(vup), fov, nx / ny, aperture, focus, 0.0, t1)
+        for mode in (T.MODE_PARITY, T.MODE_FAST):
+            a = sc.render(cam, T.make_params(nx, ny, 4, 8, mode=mode, seed=trial, kernel=T.KERNEL_WAVEFRONT))
+            b = sc.render(cam, T.make_params(nx, ny, 4, 8, mode=mode, seed=trial, kernel=T.KERNEL_WAVEFRONT, bundle_cull=False))
+            assert np.array_equal(a.sum_rgb, b.sum_rgb), (trial, name, mode)
+            assert a.stats["rays"] + a.stats["culled_paths"] == b.stats["rays"], (trial, name, mode)
+            assert a.stats["nan_samples"] == b.stats["nan_samples"]
+        culled_some += a.stats["culled_paths"] > 0
+    assert culled_some >= 8  # fires in most Cornell trials; the other two scenes sit on a radius-1000 ground sphere
