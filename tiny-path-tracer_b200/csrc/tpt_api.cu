@@ -657,8 +657,10 @@ int make_plan(tpt_scene *s, const tpt_camera *cam, const tpt_render_params *p, P
   A.ns = p->ns;
   A.max_depth = p->max_depth;
   A.t_min = p->t_min;
-  A.seed_lo = p->seed_lo;
-  A.seed_hi = p->seed_hi;
+  for (uint32_t r = 0; r < 10; r++) { // Philox key schedule, uniform over the launch
+    A.rk[2 * r] = p->seed_lo + r * 0x9E3779B9u;
+    A.rk[2 * r + 1] = p->seed_hi + r * 0xBB67AE85u;
+  }
   // Pixel-bundle bounds test (RenderArgs::cull): black background, world-space root box, shutter
   // inside the interval the moving spheres' boxes were built for. reserved[2] = 1 turns it off.
   A.cull = 0;

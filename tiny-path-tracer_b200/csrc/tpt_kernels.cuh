@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(TPT_MEGA_THREADS) render_mega_kernel(const __g
   for (;;) {
     lane_bin_refill<CULL>(A, B, !active && !B.exhausted && (!B.have_bin || B.k >= B.k_end), lane, bins_per_tile, n_paths, n_culled);
     if (!active && B.have_bin && B.k < B.k_end) { // next sample of this lane's pixel
-      rng.begin(A.seed_lo, A.seed_hi, (uint32_t)(B.py * A.nx + B.px), (uint32_t)B.k);
+      rng.begin(A.rk, (uint32_t)(B.py * A.nx + B.px), (uint32_t)B.k);
       ps.ray = camera_sample<PAR>(A.cam, B.px, B.py, A.nx, A.ny, rng);
       ps.T = mk(1.f, 1.f, 1.f);
       ps.depth = 0;
@@ -356,7 +356,7 @@ render_wave_kernel(const __grid_constant__ RenderArgs A) {
         n_rays++;
         Rng rng; // only participating media draw during extend
         const int pk = SI(F_PIXEL, s);
-        rng.begin(A.seed_lo, A.seed_hi, (uint32_t)((pk >> 16) * A.nx + (pk & 0xffff)), (uint32_t)SI(F_K, s));
+        rng.begin(A.rk, (uint32_t)((pk >> 16) * A.nx + (pk & 0xffff)), (uint32_t)SI(F_K, s));
         uint32_t ndraw0;
         if (TRACE) {
           t = SF(F_HT, s);
@@ -433,7 +433,7 @@ render_wave_kernel(const __grid_constant__ RenderArgs A) {
             ps.depth = SI(F_DEPTH, s);
             Rng rng;
             const int pk = SI(F_PIXEL, s);
-            rng.begin(A.seed_lo, A.seed_hi, (uint32_t)((pk >> 16) * A.nx + (pk & 0xffff)), (uint32_t)SI(F_K, s));
+            rng.begin(A.rk, (uint32_t)((pk >> 16) * A.nx + (pk & 0xffff)), (uint32_t)SI(F_K, s));
             bool alive = shade<PAR>(S, ps, rng, SI(F_HPRIM, s), SF(F_HT, s), MEDIA ? (uint32_t)SI(F_NDRAW, s) : 0u);
             if (alive) {
               SF(F_OX, s) = ps.ray.o.x; SF(F_OY, s) = ps.ray.o.y; SF(F_OZ, s) = ps.ray.o.z;
@@ -527,7 +527,7 @@ render_wave_kernel(const __grid_constant__ RenderArgs A) {
             if (have_bin) {
               Rng rng;
               const int py = pixel >> 16, px = pixel & 0xffff;
-              rng.begin(A.seed_lo, A.seed_hi, (uint32_t)(py * A.nx + px), (uint32_t)k);
+              rng.begin(A.rk, (uint32_t)(py * A.nx + px), (uint32_t)k);
               Ray r = camera_sample<PAR>(A.cam, px, py, A.nx, A.ny, rng);
               // A camera ray that cannot hit the scene's bounds (64 % of the headline frame looks past
               // the box) ends its path right here -- world->hit is false for it -- and the lane draws
@@ -542,7 +542,7 @@ render_wave_kernel(const __grid_constant__ RenderArgs A) {
                   n_paths++;
                   n_rays++;
                   k++;
-                  rng.begin(A.seed_lo, A.seed_hi, (uint32_t)(py * A.nx + px), (uint32_t)k);
+                  rng.begin(A.rk, (uint32_t)(py * A.nx + px), (uint32_t)k);
                   r = camera_sample<PAR>(A.cam, px, py, A.nx, A.ny, rng);
                 }
               }

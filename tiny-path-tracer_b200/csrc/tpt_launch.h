@@ -46,7 +46,7 @@ struct RenderArgs {
   CamView cam;
   int nx, ny, ns, max_depth;
   float t_min;
-  uint32_t seed_lo, seed_hi;
+  uint32_t rk[20]; // Philox round keys: rk[2r] = seed_lo + r * 0x9E3779B9, rk[2r+1] = seed_hi + r * 0xBB67AE85
   int n_ranges;                          // sample ranges per pixel (slices x sub-ranges)
   int range_bounds[TPT_MAX_RANGES + 1];  // range r covers samples [bounds[r], bounds[r+1])
   int tiles_x, tiles_y, part_index, part_count;
