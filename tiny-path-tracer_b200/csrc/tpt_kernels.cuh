@@ -223,8 +223,8 @@ __global__ void __launch_bounds__(TPT_MEGA_THREADS) render_mega_kernel(const __g
 //   extend          each thread intersects its slots (warp-uniform brute force on small scenes).
 //                   Paths that end here (miss, lamp, absorber, depth limit) add their radiance to
 //                   the slot's accumulator and go to the GENERATE queue, the others to the queue of
-//                   their material. Queues are compacted with __ballot_sync/__popc and ONE packed
-//                   64-bit shared-memory atomic per warp.
+//                   their material. Queues are compacted with __ballot_sync/__popc and one or two
+//                   packed 32-bit shared-memory atomics per warp.
 //   shade+generate  warps pull 32-item chunks from the queues: a warp shades 32 lambertian (or 32
 //                   dielectric, or 32 metal) hits together instead of diverging over the material
 //                   switch, or finishes 32 samples together (k++, store the bin when its range is
@@ -257,13 +257,17 @@ render_wave_kernel(const __grid_constant__ RenderArgs A) {
   static_assert((STATE_BYTES + QUEUE_BYTES) % 16 == 0, "scene blob must stay 16-byte aligned");
   float *sf = reinterpret_cast<float *>(sblob);
   int *si = reinterpret_cast<int *>(sblob);
-  // queue[parity][q][NSLOT] slot ids; counters packed 4 x 16 bit in one 64-bit word per parity
+  // queue[parity][q][NSLOT] slot ids; counters packed 2 x 16 bit in two 32-bit words per parity
+  // (q_cnt): word 0 = lambertian | generate << 16 (almost every warp feeds both), word 1 = metal |
+  // dielectric << 16 (touched only by warps that saw one). 32-bit shared atomics are native
+  // (ATOMS.ADD); the 64-bit add this replaces compiled to a compare-and-swap spin loop
+  // (ATOMS.CAST.SPIN.64) that eight warps contended for.
   unsigned short *queue = reinterpret_cast<unsigned short *>(reinterpret_cast<char *>(sblob) + STATE_BYTES);
   SceneView S;
   S.blob = stage_scene<SMEM>(A.scene, sblob + (STATE_BYTES + QUEUE_BYTES) / 16); // > 64 KB: stays in global memory
   S.L = &A.scene;
   S.small = &A.small;
-  __shared__ unsigned long long q_packed[2];
+  __shared__ unsigned q_cnt[2][2];
   __shared__ int n_idle;
   __shared__ int trace_next; // TRACE: next slot whose ray nobody has taken yet
 #define SF(f, s) sf[(f) * NSLOT + (s)]
@@ -285,8 +289,10 @@ render_wave_kernel(const __grid_constant__ RenderArgs A) {
     QUEUE(0, 3)[s] = (unsigned short)s;
   }
   if (tid == 0) {
-    q_packed[0] = (unsigned long long)NSLOT << 48; // everything starts in GENERATE
-    q_packed[1] = 0;
+    q_cnt[0][0] = (unsigned)NSLOT << 16; // everything starts in GENERATE
+    q_cnt[0][1] = 0;
+    q_cnt[1][0] = 0;
+    q_cnt[1][1] = 0;
     n_idle = 0;
     trace_next = 0;
   }
@@ -294,7 +300,10 @@ render_wave_kernel(const __grid_constant__ RenderArgs A) {
 
   for (int par = 0;; par ^= 1) {
     // ------------------------------------------------------------------ extend
-    if (tid == 0) q_packed[par ^ 1] = 0; // next iteration's counters (nobody touches them before the barrier)
+    if (tid == 0) { // next iteration's counters (nobody touches them before the barrier)
+      q_cnt[par ^ 1][0] = 0;
+      q_cnt[par ^ 1][1] = 0;
+    }
     if (TRACE) {
       // Closest hits through the SAH BVH, rays handed out dynamically: a lane that finishes its ray
       // takes the next untraced slot from the CTA-wide counter instead of idling until the longest
@@ -384,14 +393,19 @@ render_wave_kernel(const __grid_constant__ RenderArgs A) {
       const unsigned m0 = __ballot_sync(FULL, q == 0), m1 = __ballot_sync(FULL, q == 1);
       const unsigned m2 = __ballot_sync(FULL, q == 2), m3 = __ballot_sync(FULL, q == 3);
       if (m0 | m1 | m2 | m3) {
-        unsigned long long add = (unsigned long long)__popc(m0) | ((unsigned long long)__popc(m1) << 16) |
-                                 ((unsigned long long)__popc(m2) << 32) | ((unsigned long long)__popc(m3) << 48);
-        unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(&q_packed[par], add);
-        base = __shfl_sync(FULL, base, 0);
+        const unsigned add_a = (unsigned)__popc(m0) | ((unsigned)__popc(m3) << 16);
+        const unsigned add_b = (unsigned)__popc(m1) | ((unsigned)__popc(m2) << 16);
+        unsigned base_a = 0, base_b = 0;
+        if (lane == 0) {
+          if (add_a) base_a = atomicAdd(&q_cnt[par][0], add_a);
+          if (add_b) base_b = atomicAdd(&q_cnt[par][1], add_b);
+        }
+        base_a = __shfl_sync(FULL, base_a, 0);
+        base_b = __shfl_sync(FULL, base_b, 0);
         if (q >= 0) {
           const unsigned mine = q == 0 ? m0 : q == 1 ? m1 : q == 2 ? m2 : m3;
-          const int at = (int)((base >> (16 * q)) & 0xffffu) + __popc(mine & lt_mask);
+          const unsigned base = (q == 0 || q == 3) ? base_a : base_b;
+          const int at = (int)((base >> ((q >= 2) ? 16 : 0)) & 0xffffu) + __popc(mine & lt_mask);
           QUEUE(par, q)[at] = (unsigned short)s;
         }
       }
@@ -400,9 +414,9 @@ render_wave_kernel(const __grid_constant__ RenderArgs A) {
     // -------------------------------------------------------- shade + generate
     {
       if (TRACE && tid == 0) trace_next = 0;
-      const unsigned long long packed = q_packed[par];
-      const int c0 = (int)(packed & 0xffffu), c1 = (int)((packed >> 16) & 0xffffu);
-      const int c2 = (int)((packed >> 32) & 0xffffu), c3 = (int)((packed >> 48) & 0xffffu);
+      const unsigned word_a = q_cnt[par][0], word_b = q_cnt[par][1];
+      const int c0 = (int)(word_a & 0xffffu), c3 = (int)(word_a >> 16);
+      const int c1 = (int)(word_b & 0xffffu), c2 = (int)(word_b >> 16);
       const int t0 = (c0 + 31) >> 5, t1 = (c1 + 31) >> 5, t2 = (c2 + 31) >> 5, t3 = (c3 + 31) >> 5;
       // GENERATE chunks first (they are the most numerous and the most uniform), then the materials
 #if TPT_WAVE_SPLIT_GEN
@@ -449,10 +463,10 @@ render_wave_kernel(const __grid_constant__ RenderArgs A) {
           // dead paths regenerate in the NEXT iteration: push into the other parity's GENERATE queue
           const unsigned md = __ballot_sync(FULL, died);
           if (md) {
-            unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(&q_packed[par ^ 1], (unsigned long long)__popc(md) << 48);
+            unsigned base = 0;
+            if (lane == 0) base = atomicAdd(&q_cnt[par ^ 1][0], (unsigned)__popc(md) << 16);
             base = __shfl_sync(FULL, base, 0);
-            if (died) QUEUE(par ^ 1, 3)[(int)(base >> 48) + __popc(md & lt_mask)] = (unsigned short)s;
+            if (died) QUEUE(par ^ 1, 3)[(int)(base >> 16) + __popc(md & lt_mask)] = (unsigned short)s;
           }
         } else {
           // ---------------------------------------------------------- generate
