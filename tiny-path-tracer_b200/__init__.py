@@ -41,7 +41,7 @@ C_ABI_SYMBOLS = [
     "tpt_api_version", "tpt_device_count", "tpt_last_error", "tpt_scene_create", "tpt_scene_destroy",
     "tpt_intersect_batch", "tpt_render", "tpt_render_device", "tpt_render_fetch", "tpt_get_stats",
     "tpt_device_buffers", "tpt_render_multi",
-    "tpt_debug_philox", "tpt_debug_texture",
+    "tpt_debug_philox", "tpt_debug_texture", "tpt_debug_small_scene",
 ]
 
 
@@ -175,6 +175,7 @@ def lib() -> C.CDLL:
                                          C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
         L.tpt_debug_philox.argtypes = [C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
         L.tpt_debug_texture.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]
+        L.tpt_debug_small_scene.argtypes = [C.POINTER(SceneDesc), C.POINTER(C.c_int32)]
         _lib = L
     return _lib
 
@@ -376,6 +377,17 @@ def render_multi(scenes, cam: Camera, params: RenderParams, want_sum=True, want_
     arr = (C.c_void_p * len(scenes))(*[sc._s for sc in scenes])
     _check(lib().tpt_render_multi(arr, len(scenes), C.byref(cam), C.byref(params), C.byref(img)))
     return RenderResult(s, r, rs, scenes[0].stats())
+
+
+def small_scene_summary(desc) -> dict:
+    """tpt_debug_small_scene: the small-scene table tpt_scene_create would build (host only)."""
+    d = desc.desc if isinstance(desc, HostScene) else desc
+    out = (C.c_int32 * 64)()
+    _check(lib().tpt_debug_small_scene(d, out))
+    blocks = [{"faces": [int(out[8 + 8 * b + f]) for f in range(6)], "chain": int(out[8 + 8 * b + 6]),
+               "open": bool(out[8 + 8 * b + 7])} for b in range(int(out[4]))]
+    return {"enabled": bool(out[0]), "groups": int(out[1]), "rects": int(out[2]), "spheres": int(out[3]),
+            "blocks": blocks}
 
 
 def philox(ctr, key, device: int = 0):

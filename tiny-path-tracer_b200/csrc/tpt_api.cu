@@ -11,6 +11,7 @@
 #include <climits>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <atomic>
 #include <string>
@@ -512,6 +513,86 @@ void build_small_scene(const tpt_scene_desc *d, int n_root, bool smem_ok, SmallS
     }
     B.face[6] = g.kind >> 16; // chain, consumed below
     nb++;
+  }
+  // ---- loose rects of one chain that are whole faces of a common axis-aligned block (the five
+  // walls of a Cornell room): two perpendicular faces fix the block, every rect of the chain that
+  // is exactly one of its faces joins; >= 4 faces make it worth one slab test instead of that many
+  // rectangle tests. Absent faces stay -1 (closest_hit_uniform skips a crossing without a face).
+  // TPT_SMALL_OPEN_BLOCKS=0 in the environment keeps the rects separate (A/B measurements). ----
+  const char *open_env = std::getenv("TPT_SMALL_OPEN_BLOCKS");
+  const bool open_blocks = !(open_env && open_env[0] == '0');
+  auto rect_axes = [](int kind, int &axis, int &a, int &b) {
+    if (kind == TPT_PRIM_XY_RECT) { axis = 2; a = 0; b = 1; }
+    else if (kind == TPT_PRIM_XZ_RECT) { axis = 1; a = 0; b = 2; }
+    else { axis = 0; a = 1; b = 2; }
+  };
+  auto extent = [&](const tpt_prim &p, int along, float &lo, float &hi) { // in-plane extent along an axis
+    int axis, a, b;
+    rect_axes(p.kind, axis, a, b);
+    if (along == a) { lo = p.p[0]; hi = p.p[1]; }
+    else { lo = p.p[2]; hi = p.p[3]; }
+  };
+  auto match_faces = [&](const std::vector<int> &cand, const float lo[3], const float hi[3], int face[6]) {
+    int count = 0;
+    for (int f = 0; f < 6; f++) face[f] = -1;
+    for (int id : cand) {
+      const tpt_prim &p = d->prims[id];
+      int axis, a, b;
+      rect_axes(p.kind, axis, a, b);
+      if (!(p.p[0] == lo[a] && p.p[1] == hi[a] && p.p[2] == lo[b] && p.p[3] == hi[b])) continue;
+      if (p.p[4] != lo[axis] && p.p[4] != hi[axis]) continue;
+      const int slot = 2 * axis + (p.p[4] == lo[axis] ? 0 : 1);
+      if (face[slot] >= 0) continue; // a second rect on the same face stays a rect
+      face[slot] = id;
+      count++;
+    }
+    return count;
+  };
+  for (int c = 0; open_blocks && c < d->n_chains; c++) {
+    while (nb < TPT_SMALL_MAX_BOXES) {
+      std::vector<int> cand;
+      for (int id : surface) {
+        const tpt_prim &p = d->prims[id];
+        if (p.chain == c && in_box[id] < 0 && p.kind >= TPT_PRIM_XY_RECT && p.kind <= TPT_PRIM_YZ_RECT) cand.push_back(id);
+      }
+      int best_count = 0, best_face[6];
+      float best_lo[3], best_hi[3];
+      for (int i : cand)
+        for (int j : cand) {
+          const tpt_prim &pi = d->prims[i], &pj = d->prims[j];
+          int ai, aa, ab, aj, ja, jb;
+          rect_axes(pi.kind, ai, aa, ab);
+          rect_axes(pj.kind, aj, ja, jb);
+          if (ai == aj) continue;
+          const int ac = 3 - ai - aj; // the axis both rects extend along
+          float lo[3], hi[3], l2, h2;
+          extent(pi, ac, lo[ac], hi[ac]);
+          extent(pj, ac, l2, h2);
+          if (l2 != lo[ac] || h2 != hi[ac]) continue;
+          extent(pi, aj, lo[aj], hi[aj]);
+          extent(pj, ai, lo[ai], hi[ai]);
+          if ((pj.p[4] != lo[aj] && pj.p[4] != hi[aj]) || (pi.p[4] != lo[ai] && pi.p[4] != hi[ai])) continue;
+          if (!(lo[0] < hi[0] && lo[1] < hi[1] && lo[2] < hi[2])) continue;
+          int face[6];
+          const int count = match_faces(cand, lo, hi, face);
+          if (count > best_count) {
+            best_count = count;
+            for (int f = 0; f < 6; f++) best_face[f] = face[f];
+            for (int k = 0; k < 3; k++) { best_lo[k] = lo[k]; best_hi[k] = hi[k]; }
+          }
+        }
+      if (best_count < 4) break;
+      SmallBox &B = Q.boxes[nb];
+      B.lo = make_float4(best_lo[0], best_lo[1], best_lo[2], 0.f);
+      B.hi = make_float4(best_hi[0], best_hi[1], best_hi[2], 0.f);
+      for (int f = 0; f < 6; f++) {
+        B.face[f] = best_face[f];
+        if (best_face[f] >= 0) in_box[best_face[f]] = nb;
+      }
+      B.face[6] = c;
+      B.face[7] = best_count < 6 ? 1 : 0;
+      nb++;
+    }
   }
   int n = 0, ng = 0, nbox_sorted = 0;
   SmallBox sorted[TPT_SMALL_MAX_BOXES];
@@ -1480,6 +1561,32 @@ int tpt_debug_philox(int device, const uint32_t ctr[4], const uint32_t key[2], u
   if (e == cudaSuccess) e = cudaMemcpy(out, d, 16, cudaMemcpyDeviceToHost);
   cudaFree(d);
   if (e != cudaSuccess) return cuda_fail(e, "philox probe");
+  return TPT_OK;
+}
+
+int tpt_debug_small_scene(const tpt_scene_desc *d, int32_t out[64]) {
+  int depth = 0;
+  int rc = validate_desc(d, depth);
+  if (rc != TPT_OK) return rc;
+  if (!out) return fail(TPT_ERR_INVALID, "null argument");
+  const int n_root = d->n_root_nodes > 0 ? d->n_root_nodes : d->n_nodes;
+  SmallScene Q;
+  build_small_scene(d, n_root, true, Q);
+  std::memset(out, 0, 64 * sizeof(int32_t));
+  out[0] = Q.enabled;
+  out[1] = Q.n_groups;
+  int nbox = 0, nrect = 0, nsph = 0;
+  for (int g = 0; g < Q.n_groups; g++) {
+    const SmallGroup &G = Q.groups[g];
+    nrect += G.yz_end - G.begin;
+    nsph += G.sph_end - G.yz_end;
+    nbox = std::max(nbox, G.box_end);
+  }
+  out[2] = nrect;
+  out[3] = nsph;
+  out[4] = nbox;
+  for (int b = 0; b < nbox && b < TPT_SMALL_MAX_BOXES; b++)
+    for (int f = 0; f < 8; f++) out[8 + 8 * b + f] = Q.boxes[b].face[f];
   return TPT_OK;
 }
 

@@ -65,9 +65,11 @@ struct SmallGroup {
 };
 // `box` (src/rect_box.cc:93-115) recognised at scene upload: six rect faces of one axis-aligned
 // block. One slab test finds the entry / exit face instead of six rectangle tests.
+// Loose rects of one chain that are whole faces of a common block (the walls of a Cornell room) are
+// gathered the same way; faces nobody provides stay -1 and face[7] marks the block as open.
 struct SmallBox {
   float4 lo, hi;  // pmin, pmax
-  int face[8];    // prim ids of the faces: [-x, +x, -y, +y, -z, +z]
+  int face[8];    // prim ids of the faces: [-x, +x, -y, +y, -z, +z], -1 = absent; [6] chain (host), [7] open
 };
 struct SmallScene {
   int n_groups, enabled, pad0, pad1;
@@ -674,6 +676,37 @@ TPT_DEV bool closest_hit_uniform(const SceneView &S, const Ray &r, float tmin, f
       const float nz = fminf(z0, z1), fz = fmaxf(z0, z1);
       const float tn = fmaxf(fmaxf(nx, ny), nz), tf = fminf(fminf(fx, fy), fz);
       // the closest face hit with t >= t_min is the entry point, or the exit when the origin is inside
+      if (B.face[7]) {
+        // open block (some faces absent, e.g. the five walls of a Cornell room): the only places a
+        // ray can meet the faces are its entry and exit points of the block, in that order; a
+        // crossing whose face is absent is skipped
+        if ((tn <= tf) & (tf >= tmin)) {
+          bool settled = false;
+          if (tn >= tmin) {
+            settled = tn > best; // both crossings lie behind the closest hit so far
+            if (!settled) {
+              const int axis = tn == nx ? 0 : (tn == ny ? 1 : 2);
+              const float t_lo = axis == 0 ? x0 : (axis == 1 ? y0 : z0);
+              const int f = B.face[2 * axis + (tn == t_lo ? 0 : 1)];
+              if (f >= 0) {
+                best = tn;
+                best_prim = f;
+                settled = true;
+              }
+            }
+          }
+          if (!settled && tf <= best) {
+            const int axis = tf == fx ? 0 : (tf == fy ? 1 : 2);
+            const float t_lo = axis == 0 ? x0 : (axis == 1 ? y0 : z0);
+            const int f = B.face[2 * axis + (tf == t_lo ? 0 : 1)];
+            if (f >= 0) {
+              best = tf;
+              best_prim = f;
+            }
+          }
+        }
+        continue;
+      }
       const bool entry = tn >= tmin;
       const float t = entry ? tn : tf;
       const bool ok = (tn <= tf) & (t >= tmin) & (t <= best);
