@@ -365,19 +365,42 @@ def run_ours(args, rank, local_rank, world):
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    traffic = None
+    traffic, prof_k = None, {}
     try:
         prof = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json")))
-        traffic = prof.get("render_wave_kernel" if args.kernel == "wavefront" else "render_mega_kernel", {}).get("dram_bytes_per_launch")
+        prof_k = prof.get("render_wave_kernel" if args.kernel == "wavefront" else "render_mega_kernel", {})
+        traffic = prof_k.get("dram_bytes_per_launch")
     except Exception:
         pass
+    # FP32 FMA throughput measured on this device right now (independent FMA chains at full occupancy,
+    # csrc/tpt_render_fast.cu fp32_peak_kernel): the denominator next to the data-sheet product
+    fma_peak = None
+    try:
+        fma_peak = T.fp32_peak(local_rank)["tflops"]
+    except Exception as e:
+        sys.stderr.write(f"fp32 peak probe failed: {e}\n")
+    # issue slots: what actually bounds this kernel (compares, selects, integer RNG and address work
+    # issue like FMAs but count no FLOP). warp instructions per path from the committed ncu capture of
+    # the same kernel and variant x the paths/s measured here, against 4 warp instructions per clock and SM
+    issue = None
+    if prof_k.get("warp_inst_per_path") and args.variant == "A" and args.mode == "fast" and not args.bundle_cull:
+        sm_mhz = clocks.get("sm_mhz") or sm_max
+        ginst = prof_k["warp_inst_per_path"] * paths_per_launch / (ms_per_launch * 1e-3) / 1e9
+        issue = {"warp_inst_per_path": prof_k["warp_inst_per_path"], "achieved_ginst_per_s": ginst,
+                 "peak_ginst_per_s": sm_count * 4 * sm_mhz * 1e6 / 1e9, "frac": ginst / (sm_count * 4 * sm_mhz * 1e6 / 1e9),
+                 "active_threads_per_inst": prof_k.get("avg_active_threads_per_inst"),
+                 "source": "profiles/ncu_summary.json (ncu smsp__inst_executed.sum of the same kernel) x live paths/s; "
+                           "peak = SMs x 4 schedulers x sm_mhz under load"}
     acc_bytes = npix / world * 12 * max(1, st["reserved"][0])  # R accumulator planes x 12 B per owned pixel
     roofline = {
         "bound": "fp32", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops,
         "traffic": traffic, "kernel": "render_wave_kernel" if args.kernel == "wavefront" else "render_mega_kernel",
         "peak_source": f"{sm_count} SMs x {SM_FP32_LANES} FP32 lanes x 2 FLOP x {sm_max:.0f} MHz (clocks.max.sm); no tensor/HBM "
-                       "bound applies (SURVEY 8d): MEASURED_PEAKS.json has no FP32-issue figure, so this is the nominal one",
+                       "bound applies (SURVEY 8d): MEASURED_PEAKS.json has no FP32-issue figure, so this is the nominal one; "
+                       "peak_measured_fma is the FMA rate the library's own probe kernel reaches on this device",
         "flop_per_path": F_PATH[args.variant],
+        "peak_measured_fma": fma_peak, "frac_of_measured_fma": (achieved / fma_peak) if fma_peak else None,
+        "issue": issue,
         "frac_at_measured_clock": (achieved / (sm_count * SM_FP32_LANES * 2 * clocks["sm_mhz"] * 1e6 / 1e12)) if clocks.get("sm_mhz") else None,
         "hbm": {"algorithmic_bytes_per_launch": acc_bytes, "achieved_gbs": acc_bytes / (ms_per_launch * 1e-3) / 1e9,
                 "peak_gbs": peaks.get("hbm_gbs", 6650.0), "peak_source": "measured" if peaks else "fallback"},

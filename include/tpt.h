@@ -289,6 +289,10 @@ int tpt_get_stats(const tpt_scene *scene, tpt_stats *out);
 int tpt_debug_philox(int device, const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 int tpt_debug_texture(const tpt_scene *scene, int texture, const float *uvp /* n x 5: u,v,px,py,pz */,
                       size_t n, int mode, float *out_rgb);
+/* measured FP32 FMA throughput of `device` (TFLOP/s, 2 FLOP per FMA; best of three ~35 ms launches of
+ * independent FMA chains at full occupancy): the denominator bench.py's FP32 roofline is quoted on */
+int tpt_debug_fp32_peak(int device, double *tflops, double *ms);
+
 /* host only, no device needed: what tpt_scene_create's small-scene table (the constant-bank copy the
  * warp-uniform closest hit reads) would hold for this scene. out[0] enabled, [1] groups, [2] loose
  * rects, [3] spheres, [4] blocks; then 8 ints per block: six face primitive ids in the order

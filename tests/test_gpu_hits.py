@@ -125,3 +125,25 @@ def test_tmin_tmax_window(T, O, gpu):
 def test_empty_batch(T, gpu):
     sc = T.Scene(common.host_scene(T, "cornell_box"))
     assert len(sc.intersect(np.zeros((0, 7), np.float32))) == 0
+
+
+def test_open_block_equals_separate_rects(T, gpu, monkeypatch):
+    """fast mode folds the five Cornell walls into one open block (one slab test); with
+    TPT_SMALL_OPEN_BLOCKS=0 they stay five rectangle tests. Same closest object on every ray (a
+    tie at a shared edge aside), t within an ulp ((k - o) / d against (k - o) * (1 / d))."""
+    hs = common.host_scene(T, "cornell_box")
+    extent, eye, lookat = raygen.SCENE_INFO["cornell_box"]
+    rng = np.random.default_rng(77)  # camera + interior rays; no hand-made ties (fast mode does not promise those)
+    rays = np.concatenate([raygen.camera_rays(60000, eye, lookat, 90.0, rng), raygen.interior_rays(60000, extent, rng)])
+    folded = T.Scene(hs)
+    a = folded.intersect(rays, mode=T.MODE_FAST)
+    sec = raygen.secondary_rays(a, np.random.default_rng(9))
+    rays = np.concatenate([rays, sec])
+    a = folded.intersect(rays, mode=T.MODE_FAST)
+    monkeypatch.setenv("TPT_SMALL_OPEN_BLOCKS", "0")
+    b = T.Scene(hs).intersect(rays, mode=T.MODE_FAST)
+    assert (a["hit"] == 1).sum() > len(rays) // 3
+    differ = (a["hit"] != b["hit"]) | ((a["hit"] == 1) & (a["prim"] != b["prim"]))
+    assert differ.sum() <= max(2, len(rays) // 20000), int(differ.sum())
+    same = ~differ & (a["hit"] == 1)
+    assert np.allclose(a["t"][same], b["t"][same], rtol=4e-7, atol=0)

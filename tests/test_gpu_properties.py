@@ -262,3 +262,11 @@ def test_pixel_bundle_test_random_cameras(T, gpu):
             assert a.stats["nan_samples"] == b.stats["nan_samples"]
         culled_some += a.stats["culled_paths"] > 0
     assert culled_some >= 8  # fires in most Cornell trials; the other two scenes sit on a radius-1000 ground sphere
+
+
+def test_fp32_peak_probe_is_plausible(T, gpu):
+    """the roofline denominator bench.py measures: independent FMA chains must land between half of
+    and just above the data-sheet product of this device (148 SMs x 128 lanes x 2 x 1.965 GHz)"""
+    r = T.fp32_peak(0)
+    assert 30.0 < r["tflops"] < 80.0, r
+    assert 20.0 < r["ms"] < 120.0, r

@@ -41,7 +41,7 @@ C_ABI_SYMBOLS = [
     "tpt_api_version", "tpt_device_count", "tpt_last_error", "tpt_scene_create", "tpt_scene_destroy",
     "tpt_intersect_batch", "tpt_render", "tpt_render_device", "tpt_render_fetch", "tpt_get_stats",
     "tpt_device_buffers", "tpt_render_multi",
-    "tpt_debug_philox", "tpt_debug_texture", "tpt_debug_small_scene",
+    "tpt_debug_philox", "tpt_debug_texture", "tpt_debug_small_scene", "tpt_debug_fp32_peak",
 ]
 
 
@@ -175,6 +175,7 @@ def lib() -> C.CDLL:
                                          C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
         L.tpt_debug_philox.argtypes = [C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
         L.tpt_debug_texture.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]
+        L.tpt_debug_fp32_peak.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.tpt_debug_small_scene.argtypes = [C.POINTER(SceneDesc), C.POINTER(C.c_int32)]
         _lib = L
     return _lib
@@ -388,6 +389,13 @@ def small_scene_summary(desc) -> dict:
                "open": bool(out[8 + 8 * b + 7])} for b in range(int(out[4]))]
     return {"enabled": bool(out[0]), "groups": int(out[1]), "rects": int(out[2]), "spheres": int(out[3]),
             "blocks": blocks}
+
+
+def fp32_peak(device: int = 0) -> dict:
+    """tpt_debug_fp32_peak: measured FP32 FMA throughput of the device (TFLOP/s)."""
+    tf, ms = C.c_double(), C.c_double()
+    _check(lib().tpt_debug_fp32_peak(device, C.byref(tf), C.byref(ms)))
+    return {"tflops": tf.value, "ms": ms.value}
 
 
 def philox(ctr, key, device: int = 0):

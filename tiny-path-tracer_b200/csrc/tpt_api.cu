@@ -1564,6 +1564,43 @@ int tpt_debug_philox(int device, const uint32_t ctr[4], const uint32_t key[2], u
   return TPT_OK;
 }
 
+int tpt_debug_fp32_peak(int device, double *tflops, double *ms) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(TPT_ERR_NO_DEVICE, "no CUDA device available");
+  }
+  if (!tflops) return fail(TPT_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(device));
+  int sms = 0;
+  CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  const int blocks = sms * 8, iters = 1 << 16;
+  float *sink = nullptr;
+  cudaEvent_t e0, e1;
+  CK(cudaMalloc((void **)&sink, 4));
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  float best = 0.f;
+  cudaError_t e = cudaSuccess;
+  for (int rep = 0; rep < 4 && e == cudaSuccess; rep++) { // first pass warms the clocks up
+    cudaEventRecord(e0, 0);
+    e = launch_fp32_peak_probe(blocks, iters, sink, 0);
+    cudaEventRecord(e1, 0);
+    if (e == cudaSuccess) e = cudaEventSynchronize(e1);
+    float t = 0.f;
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&t, e0, e1);
+    if (rep > 0 && (best == 0.f || t < best)) best = t;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(sink);
+  if (e != cudaSuccess) return cuda_fail(e, "fp32 peak probe");
+  const double flop = (double)blocks * 256.0 * (double)iters * 64.0 * 2.0;
+  *tflops = flop / ((double)best * 1e-3) / 1e12;
+  if (ms) *ms = best;
+  return TPT_OK;
+}
+
 int tpt_debug_small_scene(const tpt_scene_desc *d, int32_t out[64]) {
   int depth = 0;
   int rc = validate_desc(d, depth);

@@ -86,6 +86,8 @@ cudaError_t launch_wave_parity(const RenderArgs &A, bool small, bool smem, bool 
 cudaError_t launch_wave_fast(const RenderArgs &A, bool small, bool smem, bool media, bool trace, int blocks, cudaStream_t st);
 cudaError_t launch_texture_probe_parity(const TextureProbeArgs &A, cudaStream_t st);
 cudaError_t launch_texture_probe_fast(const TextureProbeArgs &A, cudaStream_t st);
+// iters x 64 FMAs per thread, 256 threads per block (tpt_debug_fp32_peak)
+cudaError_t launch_fp32_peak_probe(int blocks, int iters, float *sink, cudaStream_t st);
 cudaError_t launch_philox_probe(const uint32_t ctr[4], const uint32_t key[2], uint32_t *d_out, cudaStream_t st);
 
 } // namespace tptd

@@ -9,8 +9,16 @@
 namespace tptd {
 __global__ void philox_probe_kernel(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
                                     uint32_t k1, uint32_t *out) {
-  uint32_t o[4];
-  philox4x32_10(c0, c1, c2, c3, k0, k1, o);
+  // the render kernels use the form with a precomputed key schedule (RenderArgs::rk, built the same
+  // way in make_plan); the refill path uses the key-add form: both must give the known answers
+  uint32_t rk[20], o[4], o2[4];
+  for (uint32_t r = 0; r < 10; r++) {
+    rk[2 * r] = k0 + r * 0x9E3779B9u;
+    rk[2 * r + 1] = k1 + r * 0xBB67AE85u;
+  }
+  philox4x32_10_rk(c0, c1, c2, c3, rk, o);
+  philox4x32_10(c0, c1, c2, c3, k0, k1, o2);
+  if (o[0] != o2[0] || o[1] != o2[1] || o[2] != o2[2] || o[3] != o2[3]) o[0] = o[1] = o[2] = o[3] = 0xDEADBEEFu;
   out[0] = o[0];
   out[1] = o[1];
   out[2] = o[2];
