@@ -175,8 +175,9 @@ def lib() -> C.CDLL:
                                          C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
         L.tpt_debug_philox.argtypes = [C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
         L.tpt_debug_texture.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]
-        L.tpt_debug_fp32_peak.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
-        L.tpt_debug_small_scene.argtypes = [C.POINTER(SceneDesc), C.POINTER(C.c_int32)]
+        if "TPT_LIBTPT" not in os.environ or hasattr(L, "tpt_debug_fp32_peak"):  # tuning builds of older sources lack the probes
+            L.tpt_debug_fp32_peak.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+            L.tpt_debug_small_scene.argtypes = [C.POINTER(SceneDesc), C.POINTER(C.c_int32)]
         _lib = L
     return _lib
 
