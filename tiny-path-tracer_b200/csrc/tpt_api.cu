@@ -133,6 +133,7 @@ struct tpt_scene {
   std::vector<cudaArray_t> arrays;
   std::vector<cudaTextureObject_t> textures;
   bool has_lights = false;
+  bool constant_textures_only = false; // no checker / Perlin / image texture anywhere: lean kernel builds apply
   int n_mediums = 0;
   bool fbvh_has_moving = false; // the fast BVH boxes moving spheres over [fbvh_t0, fbvh_t1] only
   float fbvh_t0 = 0, fbvh_t1 = 0;
@@ -745,6 +746,7 @@ int make_plan(tpt_scene *s, const tpt_camera *cam, const tpt_render_params *p, P
   // Pixel-bundle bounds test (RenderArgs::cull): black background, world-space root box, shutter
   // inside the interval the moving spheres' boxes were built for. reserved[2] = 1 turns it off.
   A.cull = 0;
+  A.lean = s->constant_textures_only ? 1 : 0;
   if (p->reserved[2] == 0 && s->background == TPT_BG_BLACK && s->root_box_ok &&
       (!s->any_moving || (std::min(cam->time0, cam->time1) >= s->moving_t0 && std::max(cam->time0, cam->time1) <= s->moving_t1))) {
     auto dotd = [](const double *a, const float *b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; };
@@ -1405,6 +1407,11 @@ int tpt_scene_create(const tpt_scene_desc *d, int device, tpt_scene **out) {
   L.n_lights = d->n_lights;
   L.background = d->background;
   s->has_lights = d->n_lights > 0;
+  s->constant_textures_only = true; // TPT_NO_LEAN=1 in the environment keeps the full kernels (A/B measurements)
+  for (int i = 0; i < d->n_textures; i++)
+    if (d->textures[i].kind != TPT_TEX_CONSTANT) s->constant_textures_only = false;
+  if (const char *e = std::getenv("TPT_NO_LEAN"))
+    if (e[0] == '1') s->constant_textures_only = false;
   s->blob_bytes = blob.size();
   CK(cudaMallocAsync((void **)&s->d_blob, blob.size(), s->stream));
   CK(cudaMemcpyAsync(s->d_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice, s->stream));

@@ -244,6 +244,10 @@ template <bool PAR> TPT_DEV void to_chain(const SceneView &S, const Ray &r, int 
   if (chain != 0) {
     float4 c = S.blob[S.L->off_chains + chain];
     int first = __float_as_int(c.x), n = __float_as_int(c.y);
+    // chains hold 1-2 wrappers: unrolled copies only spread the FAST kernels' hot code over more
+    // I-cache lines (there the chain is entered once per shaded hit); the PARITY walk enters it at every
+    // node of the reference's tree and keeps the compiler's unrolling
+#pragma unroll(PAR ? 4 : 1)
     for (int i = 0; i < n; i++) {
       float4 op = S.blob[S.L->off_ops + first + i];
       if (__float_as_int(op.x) == TPT_XF_TRANSLATE) {
@@ -273,6 +277,7 @@ TPT_DEV void from_chain(const SceneView &S, int chain, V3 &p, V3 &n) {
   if (chain == 0) return;
   float4 c = S.blob[S.L->off_chains + chain];
   int first = __float_as_int(c.x), cnt = __float_as_int(c.y);
+#pragma unroll 1
   for (int i = cnt - 1; i >= 0; i--) {
     float4 op = S.blob[S.L->off_ops + first + i];
     if (__float_as_int(op.x) == TPT_XF_TRANSLATE) {
@@ -393,6 +398,27 @@ TPT_DEV bool sphere_test(V3 center, float radius, const XRay &x, float tmin, flo
     }
   }
   return false;
+}
+
+// FAST mode, huge "wall" spheres only: the exact-root variant as an out-of-line call. It is rare
+// (no such sphere in most scenes) and its IEEE sqrt / divide sequences are long; inlined at every
+// sphere site they sat between the hot instructions. The render kernels' hot loop is about as large
+// as the SM's 32 KB instruction cache (ncu: 93 % hit rate, GPC instruction fetch at 79 % of its
+// peak before this), so rarely executed code is kept out of line throughout this file.
+static __device__ __noinline__ float2 sphere_test_exact_slow(float cx, float cy, float cz, float radius, float ox, float oy,
+                                                         float oz, float dx, float dy, float dz, float tmin, float tmax) {
+  XRay x;
+  x.o = mk(ox, oy, oz);
+  x.d = mk(dx, dy, dz);
+  x.chain = 0;
+  float t = 0.f;
+  const bool hit = sphere_test<false, true>(mk(cx, cy, cz), radius, x, tmin, tmax, t);
+  return make_float2(hit ? 1.0f : 0.0f, t);
+}
+TPT_DEV bool sphere_test_exact_fast(V3 c, float radius, const XRay &x, float tmin, float tmax, float &t) {
+  const float2 r = sphere_test_exact_slow(c.x, c.y, c.z, radius, x.o.x, x.o.y, x.o.z, x.d.x, x.d.y, x.d.z, tmin, tmax);
+  t = r.y;
+  return r.x != 0.0f;
 }
 
 // axis: 0 = xy_rect (plane z=k), 1 = xz_rect (y=k), 2 = yz_rect (x=k); p = a0,a1,b0,b1,k
@@ -725,7 +751,7 @@ TPT_DEV bool closest_hit_uniform(const SceneView &S, const Ray &r, float tmin, f
         const float4 g = Q.geo[i];
         const float2 w = Q.aux[i]; // w.x != 0: huge sphere, exact roots
         float t;
-        const bool hit = (w.x != 0.0f) ? sphere_test<false, true>(mk(g.x, g.y, g.z), g.w, x, tmin, best, t)
+        const bool hit = (w.x != 0.0f) ? sphere_test_exact_fast(mk(g.x, g.y, g.z), g.w, x, tmin, best, t)
                                        : sphere_test<false, false>(mk(g.x, g.y, g.z), g.w, x, tmin, best, t);
         if (hit) {
           best = t;
@@ -833,7 +859,7 @@ struct FbvhTrav {
             const float4 m = Q[2];
             cen = moving_center(g, make_float4(m.x, m.y, m.z, h.w), make_float4(m.w, 0.f, 0.f, 0.f), r.time);
           }
-          hit = (kf & 0x100) ? sphere_test<false, true>(cen, g.w, x, tmin, best, t)
+          hit = (kf & 0x100) ? sphere_test_exact_fast(cen, g.w, x, tmin, best, t)
                              : sphere_test_quick(cen, g.w, x, tmin, best, t);
         } else {
           hit = rect_test<false>(kind - TPT_PRIM_XY_RECT, g, h.w, x, tmin, best, t);
@@ -891,7 +917,9 @@ template <bool PAR> TPT_DEV void get_uv_map(V3 p, float &u, float &v) {
   v += 0.5f;
 }
 
-template <bool PAR>
+// LEAN (FAST kernels of small scenes whose textures are all constant_texture, e.g. the Cornell box):
+// nobody reads (u, v), so the atan2f / asinf sequence is not even compiled in
+template <bool PAR, bool LEAN = false>
 TPT_DEV void fill_hit(const SceneView &S, const Ray &r, int prim, float t, bool want_uv, HitRec &h) {
   const float4 *P = S.blob + S.L->off_prims + 4 * prim;
   float4 hd = P[0], a = P[1];
@@ -912,7 +940,7 @@ TPT_DEV void fill_hit(const SceneView &S, const Ray &r, int prim, float t, bool 
     V3 cn = c;
     if (kind == TPT_PRIM_MOVING_SPHERE) cn = moving_center(a, P[2], P[3], r.time);
     h.n = (h.p - cn) / a.w;                                 // src/sphere.cc:28,59
-    if (want_uv) get_uv_map<PAR>((h.p - c) / a.w, h.u, h.v); // src/sphere.cc:27,60 (center0_)
+    if (!LEAN && want_uv) get_uv_map<PAR>((h.p - c) / a.w, h.u, h.v); // src/sphere.cc:27,60 (center0_)
   } else {
     float k = P[2].x;
     (void)k;
@@ -994,7 +1022,17 @@ template <bool PAR> TPT_DEV float perlin_turb(const SceneView &S, V3 p) {
   return fabsf(accum);
 }
 
-template <bool PAR> TPT_DEV V3 texture_value(const SceneView &S, int tex, float u, float v, V3 p) {
+// LEAN: the scene's textures are all constant_texture (checked at upload): the checker / Perlin /
+// image code -- a third of the kernel's instructions, never executed on such a scene -- is left out.
+// The hot loop of the render kernels is about as large as the SM's 32 KB instruction cache (ncu on
+// the Cornell frame: 92.8 % hit rate and the GPC's instruction fetch at 79 % of its peak with
+// everything compiled in; 97.5 % and 43 % without the dead code), so what a scene cannot reach is
+// kept out of its kernel.
+template <bool PAR, bool LEAN = false> TPT_DEV V3 texture_value(const SceneView &S, int tex, float u, float v, V3 p) {
+  if (LEAN) {
+    const float4 t0 = S.blob[S.L->off_texs + 2 * tex];
+    return mk(t0.y, t0.z, t0.w);
+  }
   for (int guard = 0; guard < 8; guard++) {
     float4 t0 = S.blob[S.L->off_texs + 2 * tex], t1 = S.blob[S.L->off_texs + 2 * tex + 1];
     int kind = __float_as_int(t0.x);
@@ -1161,8 +1199,10 @@ template <bool PAR> TPT_DEV float light_pdf(const SceneView &S, V3 origin, V3 di
       float t;
       V3 c = mk(l0.y, l0.z, l0.w);
       float radius = l1.x;
-      const bool sph_hit = (PAR || radius >= 500.0f) ? sphere_test<PAR, true>(c, radius, x, 0.001f, FLT_MAX, t)
-                                                     : sphere_test<PAR, false>(c, radius, x, 0.001f, FLT_MAX, t);
+      bool sph_hit;
+      if (PAR) sph_hit = sphere_test<PAR, true>(c, radius, x, 0.001f, FLT_MAX, t);
+      else if (radius >= 500.0f) sph_hit = sphere_test_exact_fast(c, radius, x, 0.001f, FLT_MAX, t);
+      else sph_hit = sphere_test<PAR, false>(c, radius, x, 0.001f, FLT_MAX, t);
       if (sph_hit) {
         float tmp = (radius * radius) / sqlen(c - origin);
         float cmax = sqrtf(1 - tmp);
@@ -1307,7 +1347,7 @@ template <bool PAR> TPT_DEV V3 background_radiance(const SceneView &S, const Ray
 // carry the stream through world->hit (taking the Rng's address costs registers everywhere else).
 // Everything extend() does once the closest surface hit (any_hit, t, prim) is known: the media
 // pass of FAST mode, the miss / lamp / absorber / depth-limit endings, else the material kind.
-template <bool PAR, bool MEDIA>
+template <bool PAR, bool MEDIA, bool LEAN = false>
 TPT_DEV int extend_finish(const SceneView &S, const PathState &ps, int max_depth, float t_min, bool any_hit, float &t,
                           int &prim, V3 &radiance, Rng &g, uint32_t &ndraw_out) {
   if (!PAR && MEDIA) {
@@ -1332,15 +1372,15 @@ TPT_DEV int extend_finish(const SceneView &S, const PathState &ps, int max_depth
     // src/material.cc:79-86: one-sided; base scatter() is false -> return emitted
     const int mtex = __float_as_int(m0.y);
     HitRec h;
-    fill_hit<PAR>(S, ps.ray, prim, t, texture_needs_uv(S, mtex), h);
-    if (dot(h.n, ps.ray.d) < 0) radiance = ps.T * texture_value<PAR>(S, mtex, h.u, h.v, h.p);
+    fill_hit<PAR, LEAN>(S, ps.ray, prim, t, !LEAN && texture_needs_uv(S, mtex), h);
+    if (dot(h.n, ps.ray.d) < 0) radiance = ps.T * texture_value<PAR, LEAN>(S, mtex, h.u, h.v, h.p);
     return TPT_EXT_DONE;
   }
   if (mkind == TPT_MAT_ABSORBER || mkind == TPT_MAT_ISOTROPIC || ps.depth >= max_depth) return TPT_EXT_DONE; // emitted == 0
   return mkind;
 }
 
-template <bool PAR, bool SMALL, bool MEDIA>
+template <bool PAR, bool SMALL, bool MEDIA, bool LEAN = false>
 TPT_DEV int extend(const SceneView &S, const PathState &ps, int max_depth, float t_min, float &t, int &prim,
                    V3 &radiance, Rng &g, uint32_t &ndraw_out) {
   // scenes with participating media draw inside world->hit: the stage's stream starts here
@@ -1357,12 +1397,13 @@ TPT_DEV int extend(const SceneView &S, const PathState &ps, int max_depth, float
     else if (S.L->n_fbvh > 0 && S.L->fbvh_time_ok) any_hit = closest_hit_fbvh(S, ps.ray, t_min, FLT_MAX, t, prim);
     else any_hit = walk_range<false, false>(S, ps.ray, 0, S.L->n_nodes, t_min, FLT_MAX, t, prim, nullptr);
   }
-  return extend_finish<PAR, MEDIA>(S, ps, max_depth, t_min, any_hit, t, prim, radiance, g, ndraw_out);
+  return extend_finish<PAR, MEDIA, LEAN>(S, ps, max_depth, t_min, any_hit, t, prim, radiance, g, ndraw_out);
 }
 
 // shade(): material::scatter + the mixture-pdf step of color() for the hit (prim, t).
 // Returns true while the path continues (ps holds the next ray, throughput, depth).
-template <bool PAR> TPT_DEV bool shade(const SceneView &S, PathState &ps, Rng &g, int prim, float t, uint32_t ndraw0) {
+template <bool PAR, bool LEAN = false>
+TPT_DEV bool shade(const SceneView &S, PathState &ps, Rng &g, int prim, float t, uint32_t ndraw0) {
   // stage d+1 = the draws color() makes at depth d; ndraw0 of them were already taken inside
   // world->hit by participating media (0 in scenes without any)
   if (ndraw0 == 0u) g.set_stage((uint32_t)ps.depth + 1u);
@@ -1372,9 +1413,9 @@ template <bool PAR> TPT_DEV bool shade(const SceneView &S, PathState &ps, Rng &g
   const float4 m1 = S.blob[S.L->off_mats + 2 * mat + 1];
   const int mkind = __float_as_int(m0.x);
   const int mtex = __float_as_int(m0.y);
-  bool want_uv = mkind == TPT_MAT_LAMBERTIAN && texture_needs_uv(S, mtex);
+  bool want_uv = !LEAN && mkind == TPT_MAT_LAMBERTIAN && texture_needs_uv(S, mtex);
   HitRec h;
-  fill_hit<PAR>(S, ps.ray, prim, t, want_uv, h);
+  fill_hit<PAR, LEAN>(S, ps.ray, prim, t, want_uv, h);
   if (mkind == TPT_MAT_METAL) { // src/material.cc:88-98
     V3 reflected = reflect(unit<PAR>(ps.ray.d), h.n);
     V3 dir = reflected + m1.y * random_in_unit_sphere(g); // fuzz_
@@ -1410,7 +1451,7 @@ template <bool PAR> TPT_DEV bool shade(const SceneView &S, PathState &ps, Rng &g
     ps.ray.d = (xi < reflect_prob) ? reflected : refracted; // attenuation (1,1,1)
   } else {
     // lambertian: src/material.cc:3-17 + mixture sampling src/utils.cc:73-81
-    V3 atten = texture_value<PAR>(S, mtex, h.u, h.v, h.p);
+    V3 atten = texture_value<PAR, LEAN>(S, mtex, h.u, h.v, h.p);
     Onb uvw = onb_from_w<PAR>(h.n);
     V3 dir;
     if (g.next() < 0.5f) {
@@ -1440,14 +1481,14 @@ template <bool PAR> TPT_DEV bool shade(const SceneView &S, PathState &ps, Rng &g
 }
 
 // one bounce = extend + shade (megakernel form)
-template <bool PAR, bool SMALL, bool MEDIA>
+template <bool PAR, bool SMALL, bool MEDIA, bool LEAN = false>
 TPT_DEV bool bounce(const SceneView &S, PathState &ps, Rng &g, int max_depth, float t_min, V3 &radiance) {
   float t;
   int prim;
   uint32_t ndraw0;
-  int cls = extend<PAR, SMALL, MEDIA>(S, ps, max_depth, t_min, t, prim, radiance, g, ndraw0);
+  int cls = extend<PAR, SMALL, MEDIA, LEAN>(S, ps, max_depth, t_min, t, prim, radiance, g, ndraw0);
   if (cls == TPT_EXT_DONE) return false;
-  return shade<PAR>(S, ps, g, prim, t, ndraw0);
+  return shade<PAR, LEAN>(S, ps, g, prim, t, ndraw0);
 }
 
 } // namespace tptd

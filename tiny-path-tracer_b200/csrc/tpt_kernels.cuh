@@ -149,7 +149,7 @@ TPT_DEV void lane_bin_refill(const RenderArgs &A, LaneBin &B, bool need, unsigne
 // Bins are ordered tile-major with the pixel index fastest: the 32 lanes of a warp work on 32
 // neighbouring pixels of one tile.
 // ------------------------------------------------------------------------------------------
-template <bool PAR, bool SMEM, bool SMALL, bool MEDIA, bool CULL>
+template <bool PAR, bool SMEM, bool SMALL, bool MEDIA, bool CULL, bool LEAN = false>
 __global__ void __launch_bounds__(TPT_MEGA_THREADS) render_mega_kernel(const __grid_constant__ RenderArgs A) {
   extern __shared__ float4 sblob[];
   SceneView S;
@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(TPT_MEGA_THREADS) render_mega_kernel(const __g
     if (active) {
       V3 rad;
       n_rays++;
-      if (!bounce<PAR, SMALL, MEDIA>(S, ps, rng, A.max_depth, A.t_min, rad)) {
+      if (!bounce<PAR, SMALL, MEDIA, LEAN>(S, ps, rng, A.max_depth, A.t_min, rad)) {
         // col += de_nan(tmp): main.cpp:126, headers/utils.h:100-109
         bool nan_any = isnan(rad.x) || isnan(rad.y) || isnan(rad.z) || isnan(ps.T.x) ||
                        isnan(ps.T.y) || isnan(ps.T.z);
@@ -240,16 +240,27 @@ __global__ void __launch_bounds__(TPT_MEGA_THREADS) render_mega_kernel(const __g
 // from 1.6 to 7.2 cycles per issued instruction; it ran 35 % slower than this lock-step form.
 // ------------------------------------------------------------------------------------------
 #define TPT_WAVE_NQ 4 // queues: 0 lambertian, 1 metal, 2 dielectric (= TPT_MAT_*), 3 generate
+__host__ __device__ constexpr int wave_state_words(bool media) { return media ? 21 : 20; } // 32-bit words of path state per slot
 
-template <bool PAR, bool SMALL, bool SMEM, bool MEDIA, bool CULL, bool TRACE = false>
+template <bool PAR, bool SMALL, bool SMEM, bool MEDIA, bool CULL, bool TRACE = false, bool LEAN = false>
 __global__ void __launch_bounds__(TPT_WAVE_THREADS, TRACE ? TPT_TRACE_MIN_BLOCKS : TPT_WAVE_MIN_BLOCKS)
 render_wave_kernel(const __grid_constant__ RenderArgs A) {
+  // shade and generate as ONE phase (a warp takes material chunks and generate chunks from one list:
+  // better balance, one barrier fewer) or as two (each phase's code stays hot in the instruction
+  // cache). Measured on the Cornell frame: the split form won by 8 % while the kernel carried the
+  // texture code it never runs; with the lean build the merged form wins by 6 % (fast mode). The
+  // parity kernels are several times larger and keep the split (merged: -6 %).
+  constexpr bool SPLIT_GEN = TPT_WAVE_SPLIT_GEN == 1 || (TPT_WAVE_SPLIT_GEN == 2 && PAR);
   extern __shared__ float4 sblob[];
   constexpr int NSLOT = TRACE ? TPT_TRACE_SLOTS : TPT_WAVE_SLOTS;
   constexpr int NWARP = TPT_WAVE_THREADS / 32;
   // structure-of-arrays slot state: field f of slot s at sf[f * NSLOT + s]
+  // F_DEPTH < 0 marks a slot without a live path; F_NDRAW (draws a medium took inside world->hit)
+  // exists only in the media builds. 20 words per slot: with the queues 96 B, so that four 512-slot
+  // CTAs fit one SM's shared memory.
   enum { F_OX, F_OY, F_OZ, F_DX, F_DY, F_DZ, F_TIME, F_TX, F_TY, F_TZ, F_AX, F_AY, F_AZ,
-         F_PIXEL, F_K, F_KEND, F_ACCIDX, F_DEPTH, F_HPRIM, F_HT, F_ACTIVE, F_NDRAW, F_COUNT };
+         F_PIXEL, F_K, F_KEND, F_ACCIDX, F_DEPTH, F_HPRIM, F_HT, F_NDRAW };
+  constexpr int F_COUNT = wave_state_words(MEDIA);
   // dynamic shared memory: [slot state | queues | scene blob]. State and queues sit at
   // compile-time offsets (plain LDS/STS with immediate offsets); the blob, whose size is only known
   // at run time, comes last.
@@ -283,7 +294,7 @@ render_wave_kernel(const __grid_constant__ RenderArgs A) {
   unsigned long long n_rays = 0, n_nan = 0, n_paths = 0, n_culled = 0;
 
   for (int s = tid; s < NSLOT; s += TPT_WAVE_THREADS) {
-    SI(F_ACTIVE, s) = 0;
+    SI(F_DEPTH, s) = -1;
     SI(F_K, s) = 0;
     SI(F_KEND, s) = -1; // no bin yet
     QUEUE(0, 3)[s] = (unsigned short)s;
@@ -335,7 +346,7 @@ render_wave_kernel(const __grid_constant__ RenderArgs A) {
           if (base >= NSLOT) dry = true;
           if (need) {
             const int c = base + __popc(m & lt_mask);
-            if (c < NSLOT && SI(F_ACTIVE, c)) {
+            if (c < NSLOT && SI(F_DEPTH, c) >= 0) {
               ts = c;
               tr.o = mk(SF(F_OX, c), SF(F_OY, c), SF(F_OZ, c));
               tr.d = mk(SF(F_DX, c), SF(F_DY, c), SF(F_DZ, c));
@@ -352,13 +363,14 @@ render_wave_kernel(const __grid_constant__ RenderArgs A) {
     for (int s0 = warp * 32; s0 < NSLOT; s0 += TPT_WAVE_THREADS) {
       const int s = s0 + (int)lane;
       int cls = -2; // -2: nothing to do
-      if (SI(F_ACTIVE, s)) {
+      const int depth_s = SI(F_DEPTH, s);
+      if (depth_s >= 0) {
         PathState ps;
         ps.ray.o = mk(SF(F_OX, s), SF(F_OY, s), SF(F_OZ, s));
         ps.ray.d = mk(SF(F_DX, s), SF(F_DY, s), SF(F_DZ, s));
         ps.ray.time = SF(F_TIME, s);
         ps.T = mk(SF(F_TX, s), SF(F_TY, s), SF(F_TZ, s));
-        ps.depth = SI(F_DEPTH, s);
+        ps.depth = depth_s;
         float t;
         int prim;
         V3 rad;
@@ -371,9 +383,9 @@ render_wave_kernel(const __grid_constant__ RenderArgs A) {
           t = SF(F_HT, s);
           prim = SI(F_HPRIM, s);
           if (MEDIA) rng.set_stage((uint32_t)ps.depth + 1u);
-          cls = extend_finish<PAR, MEDIA>(S, ps, A.max_depth, A.t_min, prim >= 0, t, prim, rad, rng, ndraw0);
+          cls = extend_finish<PAR, MEDIA, LEAN>(S, ps, A.max_depth, A.t_min, prim >= 0, t, prim, rad, rng, ndraw0);
         } else {
-          cls = extend<PAR, SMALL, MEDIA>(S, ps, A.max_depth, A.t_min, t, prim, rad, rng, ndraw0);
+          cls = extend<PAR, SMALL, MEDIA, LEAN>(S, ps, A.max_depth, A.t_min, t, prim, rad, rng, ndraw0);
         }
         if (cls == TPT_EXT_DONE) {
           // col += de_nan(tmp): main.cpp:126, headers/utils.h:100-109
@@ -381,7 +393,7 @@ render_wave_kernel(const __grid_constant__ RenderArgs A) {
           SF(F_AX, s) += isnan(rad.x) ? 0.f : rad.x;
           SF(F_AY, s) += isnan(rad.y) ? 0.f : rad.y;
           SF(F_AZ, s) += isnan(rad.z) ? 0.f : rad.z;
-          SI(F_ACTIVE, s) = 0;
+          SI(F_DEPTH, s) = -1;
         } else {
           SI(F_HPRIM, s) = prim;
           SF(F_HT, s) = t;
@@ -419,14 +431,10 @@ render_wave_kernel(const __grid_constant__ RenderArgs A) {
       const int c1 = (int)(word_b & 0xffffu), c2 = (int)(word_b >> 16);
       const int t0 = (c0 + 31) >> 5, t1 = (c1 + 31) >> 5, t2 = (c2 + 31) >> 5, t3 = (c3 + 31) >> 5;
       // GENERATE chunks first (they are the most numerous and the most uniform), then the materials
-#if TPT_WAVE_SPLIT_GEN
-      for (int pass = 0; pass < 2; pass++) {
-      if (pass == 1) __syncthreads();
-      const int lo_t = pass == 0 ? t3 : 0, hi_t = pass == 0 ? t0 + t1 + t2 + t3 : t3;
+      for (int pass = 0; pass < (SPLIT_GEN ? 2 : 1); pass++) {
+      if (SPLIT_GEN && pass == 1) __syncthreads();
+      const int lo_t = !SPLIT_GEN ? 0 : (pass == 0 ? t3 : 0), hi_t = !SPLIT_GEN ? t0 + t1 + t2 + t3 : (pass == 0 ? t0 + t1 + t2 + t3 : t3);
       for (int wt = lo_t + warp; wt < hi_t; wt += NWARP) {
-#else
-      for (int wt = warp; wt < t0 + t1 + t2 + t3; wt += NWARP) {
-#endif
         int q, chunk, cnt;
         if (wt < t3) { q = 3; chunk = wt; cnt = c3; }
         else if (wt < t3 + t0) { q = 0; chunk = wt - t3; cnt = c0; }
@@ -448,7 +456,7 @@ render_wave_kernel(const __grid_constant__ RenderArgs A) {
             Rng rng;
             const int pk = SI(F_PIXEL, s);
             rng.begin(A.rk, (uint32_t)((pk >> 16) * A.nx + (pk & 0xffff)), (uint32_t)SI(F_K, s));
-            bool alive = shade<PAR>(S, ps, rng, SI(F_HPRIM, s), SF(F_HT, s), MEDIA ? (uint32_t)SI(F_NDRAW, s) : 0u);
+            bool alive = shade<PAR, LEAN>(S, ps, rng, SI(F_HPRIM, s), SF(F_HT, s), MEDIA ? (uint32_t)SI(F_NDRAW, s) : 0u);
             if (alive) {
               SF(F_OX, s) = ps.ray.o.x; SF(F_OY, s) = ps.ray.o.y; SF(F_OZ, s) = ps.ray.o.z;
               SF(F_DX, s) = ps.ray.d.x; SF(F_DY, s) = ps.ray.d.y; SF(F_DZ, s) = ps.ray.d.z;
@@ -456,7 +464,7 @@ render_wave_kernel(const __grid_constant__ RenderArgs A) {
               SI(F_DEPTH, s) = ps.depth;
             } else {
               died = true; // contributes 0 (metal absorbed, or throughput 0 / NaN in every channel)
-              SI(F_ACTIVE, s) = 0;
+              SI(F_DEPTH, s) = -1;
               if (isnan(ps.T.x) || isnan(ps.T.y) || isnan(ps.T.z)) n_nan++;
             }
           }
@@ -564,9 +572,8 @@ render_wave_kernel(const __grid_constant__ RenderArgs A) {
               SF(F_DX, s) = r.d.x; SF(F_DY, s) = r.d.y; SF(F_DZ, s) = r.d.z;
               SF(F_TIME, s) = r.time;
               SF(F_TX, s) = 1.f; SF(F_TY, s) = 1.f; SF(F_TZ, s) = 1.f;
-              SI(F_DEPTH, s) = 0;
+              SI(F_DEPTH, s) = 0; // live
               SI(F_K, s) = k;
-              SI(F_ACTIVE, s) = 1;
               n_paths++;
             } else if (exhausted) {
               SI(F_KEND, s) = -1;
@@ -575,9 +582,7 @@ render_wave_kernel(const __grid_constant__ RenderArgs A) {
           }
         }
       }
-#if TPT_WAVE_SPLIT_GEN
       }
-#endif
     }
     __syncthreads();
     if (n_idle >= NSLOT) break; // every slot idle: the work counter is dry and all paths ended
@@ -625,7 +630,7 @@ template <bool PAR> __global__ void texture_probe_kernel(const __grid_constant__
 #define TPT_FN(name) TPT_CAT(name, TPT_SUFFIX)
 
 template <typename K> static cudaError_t allow_smem(K kernel, size_t bytes) {
-  if (bytes <= 48 * 1024) return cudaSuccess;
+  if (bytes + 1024 <= 48 * 1024) return cudaSuccess; // the 48 KB default covers static + dynamic shared memory together
   return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
@@ -645,13 +650,17 @@ cudaError_t TPT_FN(launch_intersect_)(const IntersectArgs &A, bool smem, bool sm
 // kernel variant tables: [smem][small] or the media build (generic walk, scene staged when it
 // fits), each with and without the pixel-bundle bounds test compiled in (RenderArgs::cull)
 typedef void (*mega_fn)(RenderArgs);
-template <bool CULL> static mega_fn mega_variant_c(bool smem, bool small, bool media) {
+template <bool CULL> static mega_fn mega_variant_c(bool smem, bool small, bool media, bool lean) {
+#if !TPT_PAR
+  if (lean && small && smem && !media) return render_mega_kernel<false, true, true, false, CULL, true>;
+#endif
+  (void)lean;
   if (media) return smem ? render_mega_kernel<TPT_PAR, true, false, true, CULL> : render_mega_kernel<TPT_PAR, false, false, true, CULL>;
   if (smem) return small ? render_mega_kernel<TPT_PAR, true, true, false, CULL> : render_mega_kernel<TPT_PAR, true, false, false, CULL>;
   return render_mega_kernel<TPT_PAR, false, false, false, CULL>;
 }
 static mega_fn mega_variant(const RenderArgs &A, bool smem, bool small, bool media) {
-  return A.cull ? mega_variant_c<true>(smem, small, media) : mega_variant_c<false>(smem, small, media);
+  return A.cull ? mega_variant_c<true>(smem, small, media, A.lean != 0) : mega_variant_c<false>(smem, small, media, A.lean != 0);
 }
 
 cudaError_t TPT_FN(mega_occupancy_)(const RenderArgs &A, bool smem, bool small, bool media, size_t smem_bytes, int *blocks_per_sm) {
@@ -670,33 +679,36 @@ cudaError_t TPT_FN(launch_mega_)(const RenderArgs &A, bool smem, bool small, boo
 typedef void (*wave_fn)(RenderArgs);
 // `trace` (FAST only): closest hits through the library's SAH BVH with dynamic ray hand-out; the
 // scene tables are read through L1 there and shared memory holds TPT_TRACE_SLOTS path slots.
-template <bool CULL> static wave_fn wave_variant_c(bool small, bool smem, bool media, bool trace) {
+template <bool CULL> static wave_fn wave_variant_c(bool small, bool smem, bool media, bool trace, bool lean) {
 #if !TPT_PAR
+  if (lean && small && smem && !media && !trace) return render_wave_kernel<false, true, true, false, CULL, false, true>;
   if (trace) return media ? render_wave_kernel<false, false, false, true, CULL, true> : render_wave_kernel<false, false, false, false, CULL, true>;
 #endif
   (void)trace;
+  (void)lean;
   if (media) return smem ? render_wave_kernel<TPT_PAR, false, true, true, CULL> : render_wave_kernel<TPT_PAR, false, false, true, CULL>;
   if (!smem) return render_wave_kernel<TPT_PAR, false, false, false, CULL>;
   return small ? render_wave_kernel<TPT_PAR, true, true, false, CULL> : render_wave_kernel<TPT_PAR, false, true, false, CULL>;
 }
 static wave_fn wave_variant(const RenderArgs &A, bool small, bool smem, bool media, bool trace) {
-  return A.cull ? wave_variant_c<true>(small, smem, media, trace) : wave_variant_c<false>(small, smem, media, trace);
+  return A.cull ? wave_variant_c<true>(small, smem, media, trace, A.lean != 0) : wave_variant_c<false>(small, smem, media, trace, A.lean != 0);
 }
-static size_t wave_smem_bytes(const RenderArgs &A, bool smem, bool trace) {
-  if (trace && !TPT_PAR) return (size_t)TPT_TRACE_SLOTS * (22 * 4 + 2 * TPT_WAVE_NQ * 2);
-  return (smem ? (size_t)A.scene.blob_words * 16 : 0) + (size_t)TPT_WAVE_SLOTS * (22 * 4 + 2 * TPT_WAVE_NQ * 2);
+static size_t wave_smem_bytes(const RenderArgs &A, bool smem, bool media, bool trace) {
+  const size_t per_slot = (size_t)wave_state_words(media) * 4 + 2 * TPT_WAVE_NQ * 2;
+  if (trace && !TPT_PAR) return (size_t)TPT_TRACE_SLOTS * per_slot;
+  return (smem ? (size_t)A.scene.blob_words * 16 : 0) + (size_t)TPT_WAVE_SLOTS * per_slot;
 }
 
 cudaError_t TPT_FN(wave_occupancy_)(const RenderArgs &A, bool small, bool smem, bool media, bool trace, int *blocks_per_sm) {
   wave_fn k = wave_variant(A, small, smem, media, trace);
-  size_t bytes = wave_smem_bytes(A, smem, trace);
+  size_t bytes = wave_smem_bytes(A, smem, media, trace);
   cudaError_t e = allow_smem(k, bytes);
   if (e != cudaSuccess) return e;
   return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k, TPT_WAVE_THREADS, bytes);
 }
 
 cudaError_t TPT_FN(launch_wave_)(const RenderArgs &A, bool small, bool smem, bool media, bool trace, int blocks, cudaStream_t st) {
-  wave_variant(A, small, smem, media, trace)<<<blocks, TPT_WAVE_THREADS, wave_smem_bytes(A, smem, trace), st>>>(A);
+  wave_variant(A, small, smem, media, trace)<<<blocks, TPT_WAVE_THREADS, wave_smem_bytes(A, smem, media, trace), st>>>(A);
   return cudaGetLastError();
 }
 

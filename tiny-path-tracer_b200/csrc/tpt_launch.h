@@ -5,7 +5,7 @@
 
 #define TPT_MEGA_THREADS 256
 #ifndef TPT_WAVE_SPLIT_GEN
-#define TPT_WAVE_SPLIT_GEN 1 // 1: generate runs as its own phase after shade (one more barrier, +8 % measured)
+#define TPT_WAVE_SPLIT_GEN 2 // generate as its own phase after shade: 0 never, 1 always, 2 in the parity kernels only (see render_wave_kernel)
 #endif
 #ifndef TPT_TRACE_ENABLE
 #define TPT_TRACE_ENABLE 1
@@ -60,6 +60,7 @@ struct RenderArgs {
   // rays, so the bin's sum is exactly 0.
   int cull;
   int cull_x0, cull_x1, cull_y0, cull_y1;
+  int lean; // every texture of the scene is a constant_texture: FAST small-scene kernels without the texture code
 };
 
 struct TextureProbeArgs {

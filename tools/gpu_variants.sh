@@ -22,7 +22,7 @@ print(" ".join(out), "Mpaths/s (A fast, B fast, A parity) blocks", st["blocks"])
 PY
 for d in gpurun_variants/*/; do
   [ -f $d/libtpt.so ] || continue
-  echo -n "$(basename $d): "
+  echo -n "$(basename $d) [$(cat $d/flags.txt 2>/dev/null)]: "
   TPT_LIBTPT=$d/libtpt.so python /tmp/run_one.py 2>&1 | tail -1
 done
 echo -n "in-tree, walls as five rects: "; TPT_SMALL_OPEN_BLOCKS=0 python /tmp/run_one.py 2>&1 | tail -1
