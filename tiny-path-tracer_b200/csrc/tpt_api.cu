@@ -745,9 +745,15 @@ int make_plan(tpt_scene *s, const tpt_camera *cam, const tpt_render_params *p, P
   }
   // Pixel-bundle bounds test (RenderArgs::cull): black background, world-space root box, shutter
   // inside the interval the moving spheres' boxes were built for. reserved[2] = 1 turns it off.
+  // The same rectangle also tells whether ANY pixel of the frame can look past the scene: only then
+  // does the wavefront kernel's generate step test fresh camera rays against the scene's bounds and
+  // redraw the ones that miss (RenderArgs::camera_tries); a frame-filling or interior camera skips
+  // the test altogether.
   A.cull = 0;
+  A.camera_tries = 1;
   A.lean = s->constant_textures_only ? 1 : 0;
-  if (p->reserved[2] == 0 && s->background == TPT_BG_BLACK && s->root_box_ok &&
+  const bool want_cull = p->reserved[2] == 0 && s->background == TPT_BG_BLACK;
+  if (s->root_box_ok &&
       (!s->any_moving || (std::min(cam->time0, cam->time1) >= s->moving_t0 && std::max(cam->time0, cam->time1) <= s->moving_t1))) {
     auto dotd = [](const double *a, const float *b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; };
     double q[3];
@@ -817,6 +823,8 @@ int make_plan(tpt_scene *s, const tpt_camera *cam, const tpt_render_params *p, P
         }
         // nothing to cull (frame-filling or interior camera): run the kernel build without the test
         if (A.cull_x0 <= 0 && A.cull_y0 <= 0 && A.cull_x1 >= p->nx - 1 && A.cull_y1 >= p->ny - 1) A.cull = 0;
+        else A.camera_tries = TPT_WAVE_CAMERA_TRIES;
+        if (!want_cull) A.cull = 0;
       }
     }
   }

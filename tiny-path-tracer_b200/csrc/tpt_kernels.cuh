@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(TPT_MEGA_THREADS) render_mega_kernel(const __g
 __host__ __device__ constexpr int wave_state_words(bool media) { return media ? 21 : 20; } // 32-bit words of path state per slot
 
 template <bool PAR, bool SMALL, bool SMEM, bool MEDIA, bool CULL, bool TRACE = false, bool LEAN = false>
-__global__ void __launch_bounds__(TPT_WAVE_THREADS, TRACE ? TPT_TRACE_MIN_BLOCKS : TPT_WAVE_MIN_BLOCKS)
+__global__ void __launch_bounds__(TPT_WAVE_THREADS, TRACE ? TPT_TRACE_MIN_BLOCKS : (LEAN ? TPT_WAVE_LEAN_MIN_BLOCKS : TPT_WAVE_MIN_BLOCKS))
 render_wave_kernel(const __grid_constant__ RenderArgs A) {
   // shade and generate as ONE phase (a warp takes material chunks and generate chunks from one list:
   // better balance, one barrier fewer) or as two (each phase's code stays hot in the instruction
@@ -281,6 +281,11 @@ render_wave_kernel(const __grid_constant__ RenderArgs A) {
   __shared__ unsigned q_cnt[2][2];
   __shared__ int n_idle;
   __shared__ int trace_next; // TRACE: next slot whose ray nobody has taken yet
+  __shared__ int next_chunk; // merged shade+generate phase: next 32-item chunk nobody has taken yet
+  // Merged phase: warps take chunks from one list through a shared counter, the expensive ones
+  // first (lambertian, dielectric, metal, then the many short generate chunks as fillers) -- longest
+  // processing time first -- instead of a fixed round-robin share.
+  constexpr bool DYNAMIC = !SPLIT_GEN && TPT_WAVE_DYNAMIC;
 #define SF(f, s) sf[(f) * NSLOT + (s)]
 #define SI(f, s) si[(f) * NSLOT + (s)]
 #define QUEUE(par, q) (queue + ((par) * TPT_WAVE_NQ + (q)) * NSLOT)
@@ -306,6 +311,7 @@ render_wave_kernel(const __grid_constant__ RenderArgs A) {
     q_cnt[1][1] = 0;
     n_idle = 0;
     trace_next = 0;
+    next_chunk = 0;
   }
   __syncthreads();
 
@@ -314,6 +320,7 @@ render_wave_kernel(const __grid_constant__ RenderArgs A) {
     if (tid == 0) { // next iteration's counters (nobody touches them before the barrier)
       q_cnt[par ^ 1][0] = 0;
       q_cnt[par ^ 1][1] = 0;
+      next_chunk = 0;
     }
     if (TRACE) {
       // Closest hits through the SAH BVH, rays handed out dynamically: a lane that finishes its ray
@@ -434,9 +441,19 @@ render_wave_kernel(const __grid_constant__ RenderArgs A) {
       for (int pass = 0; pass < (SPLIT_GEN ? 2 : 1); pass++) {
       if (SPLIT_GEN && pass == 1) __syncthreads();
       const int lo_t = !SPLIT_GEN ? 0 : (pass == 0 ? t3 : 0), hi_t = !SPLIT_GEN ? t0 + t1 + t2 + t3 : (pass == 0 ? t0 + t1 + t2 + t3 : t3);
-      for (int wt = lo_t + warp; wt < hi_t; wt += NWARP) {
+      auto take_chunk = [&]() {
+        int v = 0;
+        if (lane == 0) v = atomicAdd(&next_chunk, 1);
+        return __shfl_sync(FULL, v, 0);
+      };
+      for (int wt = DYNAMIC ? take_chunk() : lo_t + warp; wt < hi_t; wt = DYNAMIC ? take_chunk() : wt + NWARP) {
         int q, chunk, cnt;
-        if (wt < t3) { q = 3; chunk = wt; cnt = c3; }
+        if (DYNAMIC) {
+          if (wt < t0) { q = 0; chunk = wt; cnt = c0; }
+          else if (wt < t0 + t2) { q = 2; chunk = wt - t0; cnt = c2; }
+          else if (wt < t0 + t2 + t1) { q = 1; chunk = wt - t0 - t2; cnt = c1; }
+          else { q = 3; chunk = wt - t0 - t2 - t1; cnt = c3; }
+        } else if (wt < t3) { q = 3; chunk = wt; cnt = c3; }
         else if (wt < t3 + t0) { q = 0; chunk = wt - t3; cnt = c0; }
         else if (wt < t3 + t0 + t2) { q = 2; chunk = wt - t3 - t0; cnt = c2; }
         else { q = 1; chunk = wt - t3 - t0 - t2; cnt = c1; }
@@ -555,8 +572,8 @@ render_wave_kernel(const __grid_constant__ RenderArgs A) {
               // the box) ends its path right here -- world->hit is false for it -- and the lane draws
               // its pixel's next sample instead of spending an extend pass on it. Bounded retries:
               // the last ray of the budget (or of the bin) goes to extend like any other.
-              if (!MEDIA) {
-                for (int attempt = 1; attempt < TPT_WAVE_CAMERA_TRIES && k + 1 < k_end && !may_hit_world<PAR>(S, r, A.t_min); attempt++) {
+              if (!MEDIA && !PAR) { // FAST kernels only: compiled into the parity kernels it costs them 4 %
+                for (int attempt = 1; attempt < A.camera_tries && k + 1 < k_end && !may_hit_world<PAR>(S, r, A.t_min); attempt++) {
                   V3 bg = background_radiance<PAR>(S, r, mk(1.f, 1.f, 1.f));
                   SF(F_AX, s) += bg.x;
                   SF(F_AY, s) += bg.y;

@@ -19,8 +19,14 @@
 #ifndef TPT_WAVE_MIN_BLOCKS
 #define TPT_WAVE_MIN_BLOCKS 3 // __launch_bounds__ min blocks per SM: 80 registers, 3 CTAs (measured best)
 #endif
+#ifndef TPT_WAVE_LEAN_MIN_BLOCKS
+#define TPT_WAVE_LEAN_MIN_BLOCKS 3 // lean small-scene kernels; 4 (64 registers, four 52 KB CTAs per SM) gains 1 % without the camera redraws and loses 6 % with them (72 B of spills)
+#endif
+#ifndef TPT_WAVE_DYNAMIC
+#define TPT_WAVE_DYNAMIC 1 // merged shade+generate phase: chunks handed out through a shared counter, longest first
+#endif
 #ifndef TPT_WAVE_CAMERA_TRIES
-#define TPT_WAVE_CAMERA_TRIES 1 // >1: redraw camera rays that miss the scene bounds inside generate (measured: no gain)
+#define TPT_WAVE_CAMERA_TRIES 3 // frames where some pixel can look past the scene: camera rays that miss its bounds are redrawn inside generate (up to this many per visit) instead of spending an extend pass
 #endif
 #ifndef TPT_WAVE_THREADS
 #define TPT_WAVE_THREADS 256
@@ -60,6 +66,7 @@ struct RenderArgs {
   // rays, so the bin's sum is exactly 0.
   int cull;
   int cull_x0, cull_x1, cull_y0, cull_y1;
+  int camera_tries; // wavefront generate: camera rays drawn per visit while they miss the scene's bounds (1 = no test)
   int lean; // every texture of the scene is a constant_texture: FAST small-scene kernels without the texture code
 };
 

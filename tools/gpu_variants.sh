@@ -26,5 +26,6 @@ for d in gpurun_variants/*/; do
   TPT_LIBTPT=$d/libtpt.so python /tmp/run_one.py 2>&1 | tail -1
 done
 echo -n "in-tree, walls as five rects: "; TPT_SMALL_OPEN_BLOCKS=0 python /tmp/run_one.py 2>&1 | tail -1
+echo -n "in-tree, full kernels (TPT_NO_LEAN=1): "; TPT_NO_LEAN=1 python /tmp/run_one.py 2>&1 | tail -1
 echo -n "in-tree (default): "; python /tmp/run_one.py 2>&1 | tail -1
 echo -n "in-tree megakernel: "; KERN=0 python /tmp/run_one.py 2>&1 | tail -1
