@@ -15,4 +15,6 @@ python bench.py --steps 3 --warmup 3 --variant B --no-cpu-baseline > gpurun_out/
 python bench.py --steps 3 --warmup 3 --kernel mega --no-cpu-baseline > gpurun_out/bench_ours_mega.json 2>/dev/null
 python bench.py --steps 2 --warmup 3 --mode parity --spp 256 --no-cpu-baseline > gpurun_out/bench_ours_parity256.json 2>/dev/null
 python tools/gpu_bvh_perf.py 32 > gpurun_out/bvh_perf.txt 2>&1; cat gpurun_out/bvh_perf.txt
+timeout 240 compute-sanitizer --tool memcheck python tools/gpu_sanitize.py > gpurun_out/sanitizer_memcheck.log 2>&1; tail -3 gpurun_out/sanitizer_memcheck.log
+timeout 400 compute-sanitizer --tool racecheck python tools/gpu_sanitize.py > gpurun_out/sanitizer_racecheck.log 2>&1; tail -3 gpurun_out/sanitizer_racecheck.log
 echo SESSION_DONE
