@@ -156,7 +156,7 @@ def run_reference_arm(args, rank, world):
     per_step = max(4.0, min(30.0, 150.0 / max(total, 1)))
     first = cpu_reference_sample(args.variant, per_step)
     if first is None:
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libtptref.so is not built"}))
+        emit({"impl": "reference", "unavailable": "oracle/_ref/libtptref.so is not built"})
         return
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_ref as O
@@ -183,7 +183,7 @@ def run_reference_arm(args, rank, world):
         "e2e": {"value": value, "unit": "Mpaths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # --------------------------------------------------------------------------------- our arm
@@ -194,8 +194,8 @@ def run_ours(args, rank, local_rank, world):
 
     dist = None
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: ONE JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ.pop("NCCL_DEBUG")  # the version banner goes to stdout; see emit() for the belt to these braces
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -437,12 +437,36 @@ def run_ours(args, rank, local_rank, world):
         line["bundle_cull"] = culled
     line["config"]["paths_traced"] = ("every (pixel, sample) traced (bundle test off)" if not args.bundle_cull
                                       else "pixel-bundle bounds test on (library default)")
-    print(json.dumps(line))
+    emit(line)
+
+
+_JSON_FD = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout. Native libraries write there too (NCCL prints its version
+    banner to fd 1 at several NCCL_DEBUG levels), so fd 1 is pointed at stderr for the whole run and the
+    result line goes to a private duplicate of the original stdout."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
 
 
 def main():
     global NX, NY
     args = parse()
+    claim_stdout()
     NX = NY = args.size
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -454,7 +478,7 @@ def main():
         # not launched under torchrun: re-launch one rank per GPU on this node
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", "29531", os.path.abspath(__file__)] + sys.argv[1:]
-        sys.exit(subprocess.call(cmd))
+        sys.exit(subprocess.call(cmd, stdout=_JSON_FD))  # the ranks' fd 1 is the real stdout again; rank 0 claims it itself
     run_ours(args, rank, local_rank, world)
     if world > 1:
         import torch.distributed as dist
