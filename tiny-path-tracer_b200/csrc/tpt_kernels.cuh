@@ -219,7 +219,8 @@ __global__ void __launch_bounds__(TPT_MEGA_THREADS) render_mega_kernel(const __g
 //
 // A CTA owns TPT_WAVE_SLOTS path slots (two per thread) whose state -- ray, throughput, per-pixel
 // accumulator, sample bookkeeping, pending hit -- lives in shared memory as structure-of-arrays.
-// Every iteration has two phases separated by __syncthreads():
+// Every iteration has two phases separated by __syncthreads() (three in the parity kernels, where
+// generate runs after shade as a phase of its own, see SPLIT_GEN below):
 //   extend          each thread intersects its slots (warp-uniform brute force on small scenes).
 //                   Paths that end here (miss, lamp, absorber, depth limit) add their radiance to
 //                   the slot's accumulator and go to the GENERATE queue, the others to the queue of
@@ -256,8 +257,7 @@ render_wave_kernel(const __grid_constant__ RenderArgs A) {
   constexpr int NWARP = TPT_WAVE_THREADS / 32;
   // structure-of-arrays slot state: field f of slot s at sf[f * NSLOT + s]
   // F_DEPTH < 0 marks a slot without a live path; F_NDRAW (draws a medium took inside world->hit)
-  // exists only in the media builds. 20 words per slot: with the queues 96 B, so that four 512-slot
-  // CTAs fit one SM's shared memory.
+  // exists only in the media builds. 20 words per slot, 96 B with the queues: 48 KB per 512-slot CTA.
   enum { F_OX, F_OY, F_OZ, F_DX, F_DY, F_DZ, F_TIME, F_TX, F_TY, F_TZ, F_AX, F_AY, F_AZ,
          F_PIXEL, F_K, F_KEND, F_ACCIDX, F_DEPTH, F_HPRIM, F_HT, F_NDRAW };
   constexpr int F_COUNT = wave_state_words(MEDIA);
@@ -437,7 +437,8 @@ render_wave_kernel(const __grid_constant__ RenderArgs A) {
       const int c0 = (int)(word_a & 0xffffu), c3 = (int)(word_a >> 16);
       const int c1 = (int)(word_b & 0xffffu), c2 = (int)(word_b >> 16);
       const int t0 = (c0 + 31) >> 5, t1 = (c1 + 31) >> 5, t2 = (c2 + 31) >> 5, t3 = (c3 + 31) >> 5;
-      // GENERATE chunks first (they are the most numerous and the most uniform), then the materials
+      // static share (parity kernels): GENERATE chunks first (the most numerous and the most uniform),
+      // then the materials; dynamic hand-out (fast kernels): materials first, generate chunks as fillers
       for (int pass = 0; pass < (SPLIT_GEN ? 2 : 1); pass++) {
       if (SPLIT_GEN && pass == 1) __syncthreads();
       const int lo_t = !SPLIT_GEN ? 0 : (pass == 0 ? t3 : 0), hi_t = !SPLIT_GEN ? t0 + t1 + t2 + t3 : (pass == 0 ? t0 + t1 + t2 + t3 : t3);
