@@ -270,3 +270,24 @@ def test_fp32_peak_probe_is_plausible(T, gpu):
     r = T.fp32_peak(0)
     assert 30.0 < r["tflops"] < 80.0, r
     assert 20.0 < r["ms"] < 120.0, r
+
+
+def test_camera_redraws_with_sky_background(T, gpu):
+    """fov 90 looks past the Cornell box: the fast wavefront kernel ends those camera paths inside its
+    generate step (sky radiance added there, next sample drawn in place) while the megakernel sends
+    every camera ray through extend. Same estimator sample by sample: equal path counts, the sky
+    pixels equal to the last bits, the rest within fast mode's contraction noise; a frame-filling
+    camera (nothing to redraw) likewise."""
+    sc = T.Scene(common.host_scene(T, "cornell_box", background=T.BG_SKY))
+    nx, ny, ns = 160, 120, 16
+    for fov in (90.0, 40.0):
+        cam = T.cornell_camera(nx, ny, fov=fov)
+        a = sc.render(cam, T.make_params(nx, ny, ns, 15, mode=T.MODE_FAST, seed=9, kernel=T.KERNEL_MEGA))
+        b = sc.render(cam, T.make_params(nx, ny, ns, 15, mode=T.MODE_FAST, seed=9, kernel=T.KERNEL_WAVEFRONT))
+        assert a.stats["paths"] == b.stats["paths"] == nx * ny * ns
+        assert abs(a.stats["rays"] - b.stats["rays"]) <= 2e-3 * a.stats["rays"]
+        rel = common.rel_err(b.sum_rgb, a.sum_rgb, 1e-3 * ns)
+        assert (rel > 1e-4).any(axis=-1).mean() < 0.02
+        if fov == 90.0:  # the frame's corners see only sky: every sample of those pixels was a redraw
+            corner_a, corner_b = a.sum_rgb[0, :8, :8], b.sum_rgb[0, :8, :8]
+            assert corner_a.min() > 0.0 and np.allclose(corner_a, corner_b, rtol=2e-6, atol=0)

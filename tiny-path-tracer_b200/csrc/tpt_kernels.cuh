@@ -576,9 +576,9 @@ render_wave_kernel(const __grid_constant__ RenderArgs A) {
               if (!MEDIA && !PAR) { // FAST kernels only: compiled into the parity kernels it costs them 4 %
                 for (int attempt = 1; attempt < A.camera_tries && k + 1 < k_end && !may_hit_world<PAR>(S, r, A.t_min); attempt++) {
                   V3 bg = background_radiance<PAR>(S, r, mk(1.f, 1.f, 1.f));
-                  SF(F_AX, s) += bg.x;
-                  SF(F_AY, s) += bg.y;
-                  SF(F_AZ, s) += bg.z;
+                  SF(F_AX, s) += isnan(bg.x) ? 0.f : bg.x; // col += de_nan(tmp), as in extend
+                  SF(F_AY, s) += isnan(bg.y) ? 0.f : bg.y;
+                  SF(F_AZ, s) += isnan(bg.z) ? 0.f : bg.z;
                   n_paths++;
                   n_rays++;
                   k++;
