@@ -121,3 +121,77 @@ def test_open_block_rule_equals_rect_by_rect(T):
     assert (~agree).sum() <= 2, int((~agree).sum())
     hit = agree & (bp >= 0)
     assert np.allclose(bt[hit], gt[hit], rtol=3e-7, atol=0)
+
+
+# ---------------------------------------------------------------------------------------------
+# hand-made scene descriptions (a hitable_list of loose rects under the identity chain)
+# ---------------------------------------------------------------------------------------------
+def rect_list_desc(T, rects):
+    """rects: (kind, a0, a1, b0, b1, k). Returns (desc, keep-alive)."""
+    import ctypes as C
+    n = len(rects)
+    nodes = (T.Node * (n + 1))()
+    prims = (T.Prim * n)()
+    nodes[0].kind = 1  # TPT_NODE_LIST, chain 0
+    nodes[0].end_or_prim = n + 1
+    for i, (kind, a0, a1, b0, b1, k) in enumerate(rects):
+        nodes[i + 1].kind = 2  # TPT_NODE_LEAF
+        nodes[i + 1].end_or_prim = i
+        prims[i].kind, prims[i].material, prims[i].chain, prims[i].flags = kind, 0, 0, 0
+        for j, x in enumerate((a0, a1, b0, b1, k)):
+            prims[i].p[j] = x
+    chains = (T.Chain * 1)()
+    mats = (T.Material * 1)()
+    texs = (T.Texture * 1)()
+    d = T.SceneDesc()
+    d.api_version = T.TPT_API_VERSION
+    d.n_nodes, d.n_prims, d.n_chains, d.n_materials, d.n_textures = n + 1, n, 1, 1, 1
+    d.nodes, d.prims, d.chains, d.materials, d.textures = nodes, prims, chains, mats, texs
+    return d, (nodes, prims, chains, mats, texs)
+
+
+def unit_room(faces="xXyYzZ", lo=-1.0, hi=2.0):
+    """faces of the block [lo, hi]^3 as loose rects: x/X = yz_rect at lo/hi, y/Y = xz_rect, z/Z = xy_rect"""
+    kinds = {"x": YZ, "y": XZ, "z": XY}
+    return [(kinds[f.lower()], lo, hi, lo, hi, lo if f.islower() else hi) for f in faces]
+
+
+def summary_of(T, rects):
+    import ctypes as C
+    d, keep = rect_list_desc(T, rects)
+    return T.small_scene_summary(C.pointer(d))
+
+
+def test_six_loose_faces_make_a_closed_block(T):
+    s = summary_of(T, unit_room("xXyYzZ"))
+    assert s["enabled"] and s["rects"] == 0 and len(s["blocks"]) == 1
+    assert s["blocks"][0]["open"] is False and sorted(s["blocks"][0]["faces"]) == [0, 1, 2, 3, 4, 5]
+    # slot order is -x +x -y +y -z +z whatever the order the rects come in
+    s = summary_of(T, unit_room("ZyxYzX"))
+    assert s["blocks"][0]["faces"] == [2, 5, 1, 3, 4, 0]
+
+
+def test_four_faces_fold_three_do_not(T):
+    s = summary_of(T, unit_room("xXyz"))
+    assert len(s["blocks"]) == 1 and s["blocks"][0]["open"] and s["rects"] == 0
+    assert s["blocks"][0]["faces"] == [0, 1, 2, -1, 3, -1]
+    s = summary_of(T, unit_room("xyz"))
+    assert s["blocks"] == [] and s["rects"] == 3
+
+
+def test_only_whole_faces_join_a_block(T):
+    room = unit_room("xXyYz")
+    lamp = (XZ, -0.5, 0.5, -0.5, 0.5, 1.9)        # inside the room, not on a face plane
+    patch = (XY, -1.0, 1.0, -1.0, 2.0, 2.0)       # on the +z plane but not the whole face
+    twin = (YZ, -1.0, 2.0, -1.0, 2.0, -1.0)       # a second rect on the -x face
+    s = summary_of(T, room + [lamp, patch, twin])
+    assert len(s["blocks"]) == 1 and s["blocks"][0]["open"]
+    assert s["blocks"][0]["faces"] == [0, 1, 2, 3, 4, -1]
+    assert s["rects"] == 3  # lamp, patch and the twin stay rectangle tests
+
+
+def test_two_separate_rooms(T):
+    s = summary_of(T, unit_room("xXyYz") + unit_room("xXyYzZ", lo=10.0, hi=11.0))
+    assert len(s["blocks"]) == 2 and s["rects"] == 0
+    assert sorted(b["open"] for b in s["blocks"]) == [False, True]
+    assert sorted(f for b in s["blocks"] for f in b["faces"] if f >= 0) == list(range(11))
