@@ -26,6 +26,13 @@ WANT = {
     "l1tex__t_bytes.sum": "l1_bytes",
     "lts__t_bytes.sum": "l2_bytes",
     "smsp__inst_executed.sum": "warp_instructions",
+    "sm__icc_request_hit_rate.pct": "icache_hit_pct",
+    "gcc__cache_requests_type_instruction.sum.pct_of_peak_sustained_elapsed": "gpc_instruction_fetch_pct_of_peak",
+    "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio": "stall_no_instruction_per_issue",
+    "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio": "stall_barrier_per_issue",
+    "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio": "stall_wait_per_issue",
+    "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio": "stall_long_scoreboard_per_issue",
+    "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio": "stall_short_scoreboard_per_issue",
 }
 out = {}
 for arg in sys.argv[1:]:

@@ -13,7 +13,8 @@ for i in range(2):
 print(scene, kern, st["render_ms"], "ms", st["paths"]/st["render_ms"]/1e3, "Mpaths/s", st["rays"]/st["render_ms"]/1e3, "Mrays/s")
 PY
 for sc in ${SCENES:-random_scene two_perlin_spheres earth}; do
-  ncu --set full --clock-control none --import-source on -k regex:render_ -s 1 -c 1 -f -o gpurun_out/scene_${sc}_k${KERN:-0} python /tmp/run_scene.py $sc ${KERN:-0} > gpurun_out/scene_$sc.log 2>&1
-  python /tmp/run_scene.py $sc 0 | tail -1
-  python /tmp/run_scene.py $sc 1 | tail -1
+  ncu --set full --clock-control none -k regex:render_ -s 1 -c 1 -f -o gpurun_out/scene_${sc}_k${KERN:-0} python /tmp/run_scene.py $sc ${KERN:-0} > gpurun_out/scene_$sc.log 2>&1
+  tail -1 gpurun_out/scene_$sc.log
+  [ -n "$QUICK" ] || python /tmp/run_scene.py $sc 0 | tail -1
+  [ -n "$QUICK" ] || python /tmp/run_scene.py $sc 1 | tail -1
 done
