@@ -838,7 +838,11 @@ int make_plan(tpt_scene *s, const tpt_camera *cam, const tpt_render_params *p, P
   int tail = p->ns - slices * per_slice;
   if (subs <= 0) {
     subs = 1;
-    if (!plan.parity) {
+    {
+      // both modes: PARITY sums a bin's samples in the reference's order (main.cpp:119-126) and the
+      // bins of a pixel in range order -- another association of the same fp32 sum (~1e-7
+      // relative, gate 2 allows 1e-4); reserved[1] = 1 keeps one bin per pixel and slice, i.e. the
+      // reference's strictly sequential sum
       const double slots = (double)s->prop.multiProcessorCount * 1536.0;
       const double local_pixels = (double)p->nx * p->ny / p->part_count;
       long long want = (long long)std::ceil(32.0 * slots / std::max(local_pixels, 1.0) / slices);

@@ -234,7 +234,7 @@ struct Rng {
 // ------------------------------------------------------------------------------------------
 struct XRay { // the ray expressed in the space of `chain`
   V3 o, d;
-  V3 inv; // FAST only: 1/d
+  V3 inv; // 1/d. PARITY: the IEEE quotient 1.0f / d of src/aabb.cc:5, taken once per chain instead of at every box
   int chain;
 };
 
@@ -268,7 +268,7 @@ template <bool PAR> TPT_DEV void to_chain(const SceneView &S, const Ray &r, int 
   x.o = o;
   x.d = d;
   x.chain = chain;
-  if (!PAR) x.inv = mk(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+  x.inv = mk(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
 }
 
 // hit point / normal back to world space: wrappers unwind innermost first
@@ -301,11 +301,13 @@ TPT_DEV void from_chain(const SceneView &S, int chain, V3 &p, V3 &n) {
 template <bool PAR>
 TPT_DEV bool aabb_hit(const XRay &x, float4 lo, float4 hi, float tmin, float tmax) {
   if (PAR) {
-    const float o[3] = {x.o.x, x.o.y, x.o.z}, d[3] = {x.d.x, x.d.y, x.d.z};
+    // `inv_D = 1.0f / r.direction()[i]` depends on the ray alone: the same IEEE quotient, computed
+    // where the ray enters the chain's space (to_chain) instead of at each of the tree's boxes
+    const float o[3] = {x.o.x, x.o.y, x.o.z}, iv[3] = {x.inv.x, x.inv.y, x.inv.z};
     const float mn[3] = {lo.x, lo.y, lo.z}, mx[3] = {hi.x, hi.y, hi.z};
 #pragma unroll
     for (int i = 0; i < 3; i++) {
-      float inv_d = 1.0f / d[i];
+      float inv_d = iv[i];
       float t0 = (mn[i] - o[i]) * inv_d;
       float t1 = (mx[i] - o[i]) * inv_d;
       if (inv_d < 0.0f) {
@@ -1315,6 +1317,7 @@ template <bool PAR> TPT_DEV bool may_hit_world(const SceneView &S, const Ray &r,
     XRay x;
     x.o = r.o;
     x.d = r.d;
+    x.inv = mk(1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z);
     x.chain = 0;
     return aabb_hit<true>(x, n0, n1, t_min, FLT_MAX);
   }
