@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define TPT_API_VERSION 1
+#define TPT_API_VERSION 2 /* 2: tpt_stats grew the per-GPU fields of tpt_render_multi */
 
 typedef enum tpt_status {
   TPT_OK = 0,
@@ -220,6 +220,7 @@ typedef struct tpt_render_params {
 } tpt_render_params;
 
 #define TPT_TILE 16
+#define TPT_MAX_GPUS 16
 
 /* caller-owned HOST buffers; any pointer may be NULL to skip that product */
 typedef struct tpt_image {
@@ -246,6 +247,13 @@ typedef struct tpt_stats {
   uint64_t culled_paths;   /* of `paths`: those of pixels whose whole ray bundle misses the scene's bounds;
                               world->hit is false for every ray they can generate, so they are finished
                               without tracing (0 rays counted for them). See tpt_render_params.reserved[2]. */
+  /* tpt_render_multi only (multi_gpus = 0 after a single-device call): what each GPU did */
+  int32_t multi_gpus;
+  int32_t multi_batches_total;            /* 8 x n_gpus batches of interleaved tiles                      */
+  int32_t multi_batches[TPT_MAX_GPUS];    /* batches rendered by GPU g: static share + stolen            */
+  int32_t multi_stolen[TPT_MAX_GPUS];     /* of those, taken from the shared work-stealing counter       */
+  double multi_busy_ms[TPT_MAX_GPUS];     /* device time of GPU g's batches (CUDA events on its stream)  */
+  double multi_gather_ms;                 /* peer gather on GPU 0 (host clock around its stream)         */
 } tpt_stats;
 
 typedef struct tpt_scene tpt_scene; /* opaque: owns the device copies */

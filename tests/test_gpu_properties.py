@@ -291,3 +291,34 @@ def test_camera_redraws_with_sky_background(T, gpu):
         if fov == 90.0:  # the frame's corners see only sky: every sample of those pixels was a redraw
             corner_a, corner_b = a.sum_rgb[0, :8, :8], b.sum_rgb[0, :8, :8]
             assert corner_a.min() > 0.0 and np.allclose(corner_a, corner_b, rtol=2e-6, atol=0)
+
+
+def test_fast_mode_sees_a_moving_sphere_outside_its_t0_box(T, gpu):
+    """a list-rooted scene whose moving sphere leaves its t = 0 position. FAST mode prunes
+    LIST nodes / culls pixels by node boxes, PARITY replays the reference (which never box-tests a list):
+    both must see the sphere along its whole path -- same hits on time-stamped rays, same picture."""
+    hs = T.HostScene("moving_list_test")
+    sc = T.Scene(hs)
+    rng = np.random.default_rng(3)
+    n = 20000
+    rays = np.zeros((n, 7), np.float32)
+    rays[:, 0:3] = (0, 2, 14) + rng.normal(size=(n, 3)) * 0.05
+    tt = rng.uniform(0, 1, n).astype(np.float32)
+    target = np.stack([-6 + 12 * tt, 3 * tt, np.zeros(n)], axis=1) + rng.normal(size=(n, 3)) * 0.6  # around the sphere at its own time
+    rays[:, 3:6] = target - rays[:, 0:3]
+    rays[:, 6] = tt
+    par = sc.intersect(rays, mode=T.MODE_PARITY)
+    fast = sc.intersect(rays, mode=T.MODE_FAST)
+    on_sphere = (par["hit"] == 1) & (par["prim"] == 0)
+    assert on_sphere.sum() > n // 4 and (on_sphere & (tt > 0.6)).sum() > n // 20  # hits far from the t = 0 box
+    assert np.array_equal(par["hit"], fast["hit"]) and np.array_equal(par["prim"][par["hit"] == 1], fast["prim"][par["hit"] == 1])
+    cam = T.make_camera((0, 2, 14), (0, 1, 0), (0, 1, 0), 50.0, 1.5, 0.0, 10.0, 0.0, 1.0)
+    lights = None
+    for kernel in (T.KERNEL_MEGA, T.KERNEL_WAVEFRONT):
+        a = sc.render(cam, T.make_params(96, 64, 64, 8, mode=T.MODE_PARITY, seed=5, kernel=kernel))
+        b = sc.render(cam, T.make_params(96, 64, 64, 8, mode=T.MODE_FAST, seed=5, kernel=kernel))
+        c = sc.render(cam, T.make_params(96, 64, 64, 8, mode=T.MODE_FAST, seed=5, kernel=kernel, bundle_cull=False))
+        assert np.array_equal(b.sum_rgb, c.sum_rgb)  # the bounds tests drop nothing
+        rel = common.rel_err(b.sum_rgb, a.sum_rgb, 1e-3 * 64)
+        assert (rel > 1e-4).any(axis=-1).mean() < 0.02
+        assert a.stats["rays"] == pytest.approx(b.stats["rays"], rel=2e-3)

@@ -50,6 +50,21 @@ def worker(rank, world, port, nx, ny, out_dir):
     dist.destroy_process_group()
 
 
+def worker_owned(rank, world, port, nx, ny, out_dir):
+    """bench.py's multi-rank e2e gather: each rank sends only the pixels of the tiles it owns"""
+    import bench
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    part, full = fake_render(nx, ny, rank, world)
+    for dtype in (np.float32, np.uint8):
+        frame = torch.from_numpy(part.astype(dtype).reshape(nx * ny, 3).copy())
+        bench.gather_owned_tiles(torch, dist, frame, nx, ny, rank, world)
+        if rank == 0:
+            np.save(os.path.join(out_dir, f"owned_{np.dtype(dtype).name}.npy"), frame.numpy().reshape(ny, nx, 3))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
 def free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
@@ -81,3 +96,26 @@ def test_static_split_is_balanced_and_complete(world):
     inside = (np.abs(ii - 600) < 225) & (np.abs(jj - 600) < 225)  # fov 90: the box opening covers ~37.5 % of each axis
     share = np.array([(inside & (own == r)).sum() for r in range(world)], float)
     assert share.max() <= 1.03 * share.mean()
+
+
+@pytest.mark.parametrize("nx,ny,world", [(1200, 1200, 2), (150, 90, 2), (100, 70, 3)])
+def test_tile_owned_gather_reproduces_the_frame(tmp_path, nx, ny, world):
+    """the gather bench.py uses under torchrun: 1/world of the frame per rank instead of a full-frame SUM;
+    ragged frames (partial tiles, unequal tile counts per rank) included"""
+    mp.spawn(worker_owned, args=(world, free_port(), nx, ny, str(tmp_path)), nprocs=world, join=True)
+    _, full = fake_render(nx, ny, 0, world)
+    assert np.array_equal(np.load(tmp_path / "owned_float32.npy"), full)
+    assert np.array_equal(np.load(tmp_path / "owned_uint8.npy"), full.astype(np.uint8))
+
+
+def test_owned_pixel_index_matches_the_kernel_split():
+    """bench.owned_pixel_index == the tile ownership rule of the kernels (tile t belongs to part t % parts)"""
+    import bench
+    for nx, ny, world in [(1200, 1200, 8), (150, 90, 3)]:
+        own = owner_map(nx, ny, world).ravel()
+        seen = np.zeros(nx * ny, np.int32)
+        for r in range(world):
+            idx = bench.owned_pixel_index(torch, nx, ny, r, world, "cpu").numpy()
+            assert (own[idx] == r).all() and len(idx) == (own == r).sum()
+            seen[idx] += 1
+        assert (seen == 1).all()

@@ -27,7 +27,8 @@ LIB_DIR = os.path.join(_HERE, "lib")
 LIBTPT = os.environ.get("TPT_LIBTPT", os.path.join(LIB_DIR, "libtpt.so"))  # override: tuning builds only
 LIBHOST = os.path.join(LIB_DIR, "libtpt_host.so")
 
-TPT_API_VERSION = 1
+TPT_API_VERSION = 2
+TPT_MAX_GPUS = 16
 TPT_TILE = 16
 MODE_PARITY, MODE_FAST = 0, 1
 KERNEL_MEGA, KERNEL_WAVEFRONT = 0, 1
@@ -128,7 +129,9 @@ class Stats(C.Structure):
                 ("d2h_ms", C.c_double), ("wall_ms", C.c_double), ("h2d_bytes", C.c_uint64),
                 ("d2h_bytes", C.c_uint64), ("kernel_launches", C.c_int32), ("sm_count", C.c_int32),
                 ("blocks", C.c_int32), ("threads_per_block", C.c_int32), ("reserved", C.c_int32 * 4),
-                ("culled_paths", C.c_uint64)]
+                ("culled_paths", C.c_uint64),
+                ("multi_gpus", C.c_int32), ("multi_batches_total", C.c_int32), ("multi_batches", C.c_int32 * 16),
+                ("multi_stolen", C.c_int32 * 16), ("multi_busy_ms", C.c_double * 16), ("multi_gather_ms", C.c_double)]
 
 
 RAY_DTYPE = np.dtype([("o", np.float32, 3), ("d", np.float32, 3), ("time", np.float32)])
@@ -324,8 +327,13 @@ class Scene:
     def stats(self) -> dict:
         st = Stats()
         _check(lib().tpt_get_stats(self._s, C.byref(st)))
-        d = {k: getattr(st, k) for k, _ in Stats._fields_ if k != "reserved"}
+        arrays = ("reserved", "multi_batches", "multi_stolen", "multi_busy_ms")
+        d = {k: getattr(st, k) for k, _ in Stats._fields_ if k not in arrays}
         d["reserved"] = [int(x) for x in st.reserved]
+        n = int(st.multi_gpus)
+        d["multi_batches"] = [int(x) for x in st.multi_batches][:n]
+        d["multi_stolen"] = [int(x) for x in st.multi_stolen][:n]
+        d["multi_busy_ms"] = [float(x) for x in st.multi_busy_ms][:n]
         return d
 
     def device_buffers(self):

@@ -14,6 +14,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <atomic>
+#include <functional>
 #include <string>
 #include <thread>
 #include <mutex>
@@ -130,6 +131,7 @@ struct tpt_scene {
   size_t blob_bytes = 0;
   bool use_smem = false;
   SmallScene small{}; // flat (chain, kind)-ordered geometry for the uniform brute-force closest hit
+  FlatTree flat{};    // PARITY mode: the reference's own tree for the warp-uniform replay (closest_hit_flat)
   std::vector<cudaArray_t> arrays;
   std::vector<cudaTextureObject_t> textures;
   bool has_lights = false;
@@ -663,6 +665,81 @@ void build_small_scene(const tpt_scene_desc *d, int n_root, bool smem_ok, SmallS
   Q.enabled = 1;
 }
 
+// PARITY mode: the reference's tree as a FlatTree (tpt_device.cuh) when it is small and has the shape
+// closest_hit_flat replays: bvh_nodes on top, leaves and hitable_lists (nested lists and `box`
+// objects concatenate) below them, no bvh_node under a list, no media, no moving spheres.
+// TPT_PARITY_FLAT=0 in the environment keeps the generic frame-stack replay (A/B and test use).
+void build_flat_tree(const tpt_scene_desc *d, int n_root, bool smem_ok, FlatTree &F) {
+  std::memset(&F, 0, sizeof(F));
+  if (const char *e = std::getenv("TPT_PARITY_FLAT"))
+    if (e[0] == '0') return;
+  if (!smem_ok) return;
+  bool ok = true;
+  int nb = 0, np = 0, ni = 0;
+  auto put_prim = [&](int id, int chain) {
+    const tpt_prim &p = d->prims[id];
+    if (np >= TPT_FLAT_MAX_PRIMS || p.kind == TPT_PRIM_MEDIUM || p.kind == TPT_PRIM_MOVING_SPHERE) {
+      ok = false;
+      return;
+    }
+    FlatPrim &q = F.prims[np++];
+    q.geo = make_float4(p.p[0], p.p[1], p.p[2], p.p[3]);
+    q.kind = p.kind;
+    q.prim = id;
+    q.chain = chain;
+    q.k = p.p[4];
+  };
+  // recursive descent over the pre-order array: [i, end) are the children of one group
+  std::function<void(int, int, int, bool)> walk = [&](int i, int end, int parent, bool in_list) {
+    while (ok && i < end) {
+      const tpt_node &nd = d->nodes[i];
+      const int k = nd.kind & 0xff, chain = nd.kind >> 16;
+      const int next = k == TPT_NODE_LEAF ? i + 1 : nd.end_or_prim;
+      if (nd.kind & TPT_NODE_DUP) { // second visit of a one-element bvh_node's child: same record twice
+        i = next;
+        continue;
+      }
+      if (k == TPT_NODE_BVH) {
+        if (in_list || nb >= TPT_FLAT_MAX_BOXES) {
+          ok = false;
+          return;
+        }
+        const int b = nb++;
+        int32_t pi = parent;
+        float cf, pf;
+        std::memcpy(&cf, &chain, 4);
+        std::memcpy(&pf, &pi, 4);
+        F.boxes[b].lo = make_float4(nd.bmin[0], nd.bmin[1], nd.bmin[2], cf);
+        F.boxes[b].hi = make_float4(nd.bmax[0], nd.bmax[1], nd.bmax[2], pf);
+        walk(i + 1, nd.end_or_prim, b, false);
+      } else {
+        const bool opens = !in_list; // a leaf or list directly below a bvh_node (or the root itself): one item
+        if (opens) {
+          if (ni >= TPT_FLAT_MAX_ITEMS) {
+            ok = false;
+            return;
+          }
+          F.items[ni].first = np;
+          F.items[ni].parent = parent;
+        }
+        if (k == TPT_NODE_LEAF) put_prim(nd.end_or_prim, d->prims[nd.end_or_prim].chain);
+        else walk(i + 1, nd.end_or_prim, parent, true);
+        if (opens) F.items[ni++].end = np;
+      }
+      i = next;
+    }
+  };
+  walk(0, n_root, -1, false);
+  if (!ok || ni == 0) {
+    std::memset(&F, 0, sizeof(F));
+    return;
+  }
+  F.n_boxes = nb;
+  F.n_items = ni;
+  F.n_prims = np;
+  F.enabled = 1;
+}
+
 // Render products come from the device's stream-ordered memory pool (cudaMallocAsync): the pool
 // keeps freed blocks (release threshold = max, set in tpt_scene_create), so creating a scene,
 // rendering and destroying it again -- the end-to-end pattern of a short-lived caller -- does not
@@ -718,7 +795,8 @@ int make_plan(tpt_scene *s, const tpt_camera *cam, const tpt_render_params *p, P
   RenderArgs &A = plan.args;
   std::memset(&A, 0, sizeof(A));
   A.scene = s->layout;
-  A.small = s->small;
+  if (plan.parity) A.flat = s->flat; // the two tables share storage: a launch reads the one of its mode
+  else A.small = s->small;
   // moving-sphere boxes of the fast BVH cover the spheres' own [time0,time1]; a shutter interval
   // outside it extrapolates the centres, so fall back to the reference tree for that render
   if (s->fbvh_has_moving && !(std::min(cam->time0, cam->time1) >= s->fbvh_t0 && std::max(cam->time0, cam->time1) <= s->fbvh_t1))
@@ -916,7 +994,7 @@ int run_plan(tpt_scene *s, Plan &plan, bool want_sum, bool want_rgb8, bool want_
   size_t smem = s->use_smem ? s->blob_bytes : 0;
   int bps = 0;
   const bool media = s->n_mediums > 0;
-  const bool small = s->small.enabled != 0 && !media;
+  const bool small = (plan.parity ? s->flat.enabled != 0 : s->small.enabled != 0) && !media;
   const bool trace = TPT_TRACE_ENABLE && !plan.parity && media && A.scene.n_fbvh > 0 && A.scene.fbvh_time_ok; // SAH BVH + media: 2-CTA variant with dynamic ray hand-out
   if (plan.wavefront)
     CK(plan.parity ? wave_occupancy_parity(A, small, s->use_smem, media, trace, &bps) : wave_occupancy_fast(A, small, s->use_smem, media, trace, &bps));
@@ -1015,7 +1093,7 @@ struct MultiWorker {
   tpt_scene *s = nullptr;
   int rc = TPT_OK;
   std::string err;
-  int batches = 0;
+  int batches = 0, stolen = 0;
   double busy_ms = 0;
   unsigned owned[TPT_MAX_BATCHES / 32] = {};
 };
@@ -1051,7 +1129,7 @@ int launch_batch(tpt_scene *s, const tpt_camera *cam, const tpt_render_params *p
   size_t smem = s->use_smem ? s->blob_bytes : 0;
   int bps = 0;
   const bool media = s->n_mediums > 0;
-  const bool small = s->small.enabled != 0 && !media;
+  const bool small = (plan.parity ? s->flat.enabled != 0 : s->small.enabled != 0) && !media;
   const bool trace = TPT_TRACE_ENABLE && !plan.parity && media && A.scene.n_fbvh > 0 && A.scene.fbvh_time_ok; // SAH BVH + media: 2-CTA variant with dynamic ray hand-out
   if (plan.wavefront)
     CK(plan.parity ? wave_occupancy_parity(A, small, s->use_smem, media, trace, &bps) : wave_occupancy_fast(A, small, s->use_smem, media, trace, &bps));
@@ -1077,6 +1155,7 @@ int render_multi(tpt_scene *const *scenes, int n, const tpt_camera *cam, const t
       if (scenes[j]->device == scenes[i]->device) return fail(TPT_ERR_INVALID, "two scenes on the same device");
   }
   if (p->part_count != 1 || p->part_index != 0) return fail(TPT_ERR_INVALID, "tpt_render_multi partitions the frame itself");
+  if (n > TPT_MAX_GPUS) return fail(TPT_ERR_UNSUPPORTED, "more than TPT_MAX_GPUS scenes");
   const double t_begin = now_ms();
   const int n_batches = std::min(TPT_MAX_BATCHES, 8 * n);
   const int n_static = (n_batches * 3 / 4) / n * n; // multiple of n: every GPU gets the same static share
@@ -1117,6 +1196,7 @@ int render_multi(tpt_scene *const *scenes, int n, const tpt_camera *cam, const t
         if (b >= n_batches) break;
         w.rc = launch_batch(s, cam, p, b, n_batches);
         w.batches++;
+        w.stolen++;
         w.owned[b >> 5] |= 1u << (b & 31);
       }
       if (w.rc != TPT_OK) {
@@ -1222,7 +1302,15 @@ int render_multi(tpt_scene *const *scenes, int n, const tpt_camera *cam, const t
     st.render_ms = std::max(st.render_ms, W[g].busy_ms);
     st.kernel_launches += W[g].batches + 1;
     st.reserved[g < 4 ? g : 3] = W[g].batches; // batches taken by the first GPUs (load-balance evidence)
+    if (g < TPT_MAX_GPUS) {
+      st.multi_batches[g] = W[g].batches;
+      st.multi_stolen[g] = W[g].stolen;
+      st.multi_busy_ms[g] = W[g].busy_ms;
+    }
   }
+  st.multi_gpus = n;
+  st.multi_batches_total = n_batches;
+  st.multi_gather_ms = t_gather;
   st.resolve_ms = t_gather;
   st.sm_count = s0->prop.multiProcessorCount;
   st.blocks = s0->stats.blocks;
@@ -1431,6 +1519,7 @@ int tpt_scene_create(const tpt_scene_desc *d, int device, tpt_scene **out) {
   L.blob_global = s->d_blob;
   s->use_smem = blob.size() <= 64 * 1024;
   build_small_scene(d, n_root, s->use_smem, s->small);
+  build_flat_tree(d, n_root, s->use_smem && mediums.empty(), s->flat);
 
   // ---- image textures: RGB -> RGBA8 cudaArray, point sampling, clamp, unnormalised coords ----
   for (int i = 0; i < d->n_images; i++) {
@@ -1502,13 +1591,14 @@ int tpt_intersect_batch(const tpt_scene *cs, const tpt_ray *rays, size_t n, floa
   CK(cudaMemcpyAsync(d_rays, rays, n * sizeof(tpt_ray), cudaMemcpyHostToDevice, s->stream));
   IntersectArgs A;
   A.scene = s->layout;
-  A.small = s->small;
+  if (mode == TPT_MODE_PARITY) A.flat = s->flat;
+  else A.small = s->small;
   A.rays = d_rays;
   A.n = n;
   A.tmin = tmin;
   A.tmax = tmax;
   A.out = d_out;
-  cudaError_t e = mode == TPT_MODE_PARITY ? launch_intersect_parity(A, s->use_smem, false, s->stream)
+  cudaError_t e = mode == TPT_MODE_PARITY ? launch_intersect_parity(A, s->use_smem, s->flat.enabled != 0, s->stream)
                                           : launch_intersect_fast(A, s->use_smem, s->small.enabled != 0, s->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, n * sizeof(tpt_hit), cudaMemcpyDeviceToHost, s->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);

@@ -25,6 +25,12 @@ namespace tptd {
 #define TPT_MAX_BOUNDARY_FRAMES 8 // nesting inside a constant_medium boundary (sphere / box / small list)
 #define TPT_MAX_IMAGES 8
 #define TPT_MAX_RANGES 256
+#ifndef TPT_EXACT_DOUBLE_ROOTS
+#define TPT_EXACT_DOUBLE_ROOTS 1 // FAST mode, huge "wall" spheres: roots in double like the reference (0: IEEE fp32)
+#endif
+#ifndef TPT_EAGER_CAMERA_BLOCK
+#define TPT_EAGER_CAMERA_BLOCK 2 // second Philox block of the camera stage expanded in line: 0 never, 1 always, 2 PARITY kernels only
+#endif
 
 // ------------------------------------------------------------------------------------------
 // Scene view: one contiguous blob of 16-byte words (shared memory when it fits, else global),
@@ -80,10 +86,41 @@ struct SmallScene {
   SmallBox boxes[TPT_SMALL_MAX_BOXES];
 };
 
+// PARITY mode, small trees: the reference's hitable tree (bvh_node / hitable_list / leaves) laid out
+// for a warp-uniform replay of world->hit from the constant bank -- closest_hit_flat below. It holds
+// the SAME boxes, primitives and nesting as the pre-order node array; only the bookkeeping differs
+// (no frame stack, no per-node kind decoding).
+//   boxes  every non-duplicate bvh_node in pre-order: box_, chain, index of the enclosing bvh_node
+//   items  what hangs below the bvh_nodes, in DFS order: one leaf, or one hitable_list (nested lists
+//          and `box` objects concatenated: a list hands closest_so_far down and its result up, so a
+//          list of lists is one list) as the run prims[first, end); `parent` = its bvh_node
+//   prims  the leaves of the runs, in list order
+#define TPT_FLAT_MAX_BOXES 32
+#define TPT_FLAT_MAX_PRIMS 48
+#define TPT_FLAT_MAX_ITEMS 48
+struct FlatBox {
+  float4 lo, hi; // lo.w = chain, hi.w = parent box (int bits; -1: a child of nothing)
+};
+struct FlatPrim {
+  float4 geo; // rect: a0,a1,b0,b1 ; sphere: cx,cy,cz,r
+  int kind, prim, chain;
+  float k;    // rect plane coordinate
+};
+struct FlatItem {
+  int first, end, parent, pad;
+};
+struct FlatTree {
+  int enabled, n_boxes, n_items, n_prims;
+  FlatBox boxes[TPT_FLAT_MAX_BOXES];
+  FlatPrim prims[TPT_FLAT_MAX_PRIMS];
+  FlatItem items[TPT_FLAT_MAX_ITEMS];
+};
+
 struct SceneView {
   const float4 *blob;      // shared-memory copy when it fits, else the global blob
   const SceneLayout *L;    // offsets / counts / texture objects (constant bank)
-  const SmallScene *small; // constant bank; valid when the kernel is instantiated with SMALL
+  const SmallScene *small; // constant bank; valid when a FAST kernel is instantiated with SMALL
+  const FlatTree *flat;    // constant bank; valid when a PARITY kernel is instantiated with SMALL
 };
 
 struct V3 {
@@ -104,8 +141,24 @@ TPT_DEV V3 cross(V3 a, V3 b) {
 }
 TPT_DEV float sqlen(V3 a) { return a.x * a.x + a.y * a.y + a.z * a.z; }
 TPT_DEV float length(V3 a) { return sqrtf(sqlen(a)); } // headers/vec3.h:44-46 (std::sqrt(float))
+// PARITY: the IEEE quotient a / b, written so that a ZERO dividend does not take the hardware
+// division's out-of-line slow path (FCHK rejects a zero or denormal operand; r02 capture: 38 % of the
+// warp-level rect tests called it for the 2.7 lanes whose ray starts ON that rect's plane, k - o == 0,
+// and every unit(cross(n, axis)) of an axis-aligned normal divides exact zeros). 0 / b is +-0 with the
+// XOR of the signs unless b is 0 or NaN (then NaN): the same value on every input, no call.
+TPT_DEV float pdiv(float a, float b) {
+  const bool zero = a == 0.0f;
+  const float q = (zero ? 1.0f : a) / b;
+  const float z = (b == 0.0f || b != b) ? __int_as_float(0x7fffffff)
+                                        : __int_as_float((__float_as_int(a) ^ __float_as_int(b)) & (int)0x80000000);
+  return zero ? z : q;
+}
+
 template <bool PAR> TPT_DEV V3 unit(V3 a) {         // headers/vec3.h:143-144: v / v.length()
-  if (PAR) return a / length(a);
+  if (PAR) {
+    const float l = length(a);
+    return mk(pdiv(a.x, l), pdiv(a.y, l), pdiv(a.z, l));
+  }
   float inv = rsqrtf(sqlen(a));
   return a * inv;
 }
@@ -212,6 +265,18 @@ struct Rng {
     b2 = o[2];
     b3 = o[3];
   }
+  // the stage's NEXT block, expanded in line where a stage is known to run past four draws (the
+  // camera stage: jitter u, v + lens y, x fill block 0 and a fifth of the lens samples are redrawn).
+  // ndraw must be a multiple of four.
+  TPT_DEV void next_block_inline() {
+    fresh = ndraw;
+    uint32_t o[4];
+    philox4x32_10_rk(pixel, sample, stage, ndraw >> 2, rk, o);
+    b0 = o[0];
+    b1 = o[1];
+    b2 = o[2];
+    b3 = o[3];
+  }
   TPT_DEV void refill() {
     uint4 o = philox_block_slow(pixel, sample, stage, ndraw >> 2, rk[0], rk[1]);
     b0 = o.x;
@@ -238,7 +303,7 @@ struct XRay { // the ray expressed in the space of `chain`
   int chain;
 };
 
-template <bool PAR> TPT_DEV void to_chain(const SceneView &S, const Ray &r, int chain, XRay &x) {
+template <bool PAR, bool INV = true> TPT_DEV void to_chain(const SceneView &S, const Ray &r, int chain, XRay &x) {
   if (x.chain == chain) return;
   V3 o = r.o, d = r.d;
   if (chain != 0) {
@@ -268,7 +333,7 @@ template <bool PAR> TPT_DEV void to_chain(const SceneView &S, const Ray &r, int 
   x.o = o;
   x.d = d;
   x.chain = chain;
-  x.inv = mk(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+  if (INV) x.inv = mk(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
 }
 
 // hit point / normal back to world space: wrappers unwind innermost first
@@ -342,9 +407,12 @@ TPT_DEV V3 moving_center(float4 a, float4 b, float4 c, float time) {
   return c0 + f * (c1 - c0);
 }
 
-// EXACT (fast mode only): IEEE fp32 sqrt / divide for the roots. Needed for the huge "wall"
-// spheres, where t decides which of two nearly coincident surfaces wins; ordinary spheres take the
-// approximate MUFU forms.
+// EXACT (fast mode only): the reference's own root arithmetic -- sqrt and the division in double,
+// rounded once (src/sphere.cc:23,32) -- for the huge "wall" spheres (radius >= 500), where the last
+// bit of t decides whether a ray that starts ON the wall re-hits it at t ~ 0.001 and which of two
+// nearly coincident surfaces wins (r02: with fp32 roots 47 of 2474 surface-start rays of
+// sphere_cornell_box picked another wall than the reference). Ordinary spheres take the approximate
+// MUFU forms.
 template <bool PAR, bool EXACT = true>
 TPT_DEV bool sphere_test(V3 center, float radius, const XRay &x, float tmin, float tmax, float &t) {
   // src/sphere.cc:15-41. The quadratic's coefficients and discriminant are evaluated with
@@ -358,7 +426,7 @@ TPT_DEV bool sphere_test(V3 center, float radius, const XRay &x, float tmin, flo
                       -__fmul_rn(radius, radius));
   float disc = __fadd_rn(__fmul_rn(b, b), -__fmul_rn(__fmul_rn(4.0f, a), c));
   if (disc > 0) {
-    if (PAR) {
+    if (PAR || (EXACT && TPT_EXACT_DOUBLE_ROOTS)) {
       // `sqrt` (unqualified) and the division are evaluated in double, rounded once to float
       double sq = sqrt((double)disc);
       float temp = (float)((-(double)b - sq) / (double)(2 * a));
@@ -434,7 +502,7 @@ TPT_DEV bool rect_test(int axis, float4 p, float k, const XRay &x, float tmin, f
   } else {
     ok = x.o.x; dk = x.d.x; oa = x.o.y; da = x.d.y; ob = x.o.z; db = x.d.z;
   }
-  float tt = (k - ok) / dk;
+  float tt = PAR ? pdiv(k - ok, dk) : (k - ok) / dk;
   if (tt > tmax || tt < tmin) return false;
   float a = oa + tt * da;
   float b = ob + tt * db;
@@ -628,6 +696,95 @@ TPT_DEV bool walk_range(const SceneView &S, const Ray &r, int first, int end_all
     prim_out = best_prim;
     return best_prim >= 0;
   }
+}
+
+// ------------------------------------------------------------------------------------------
+// PARITY mode, small trees: world->hit replayed from the FlatTree with warp-uniform control flow.
+// Why it is the same function as the recursive reference (and as walk_range<true> above):
+//  * bvh_node::hit (src/hitable.cc:63-90) hands its own t_max to both children, so below the
+//    bvh_nodes every leaf / list sees the caller's t_max, whatever its siblings found: the items
+//    are independent of each other. A node's box is consulted only when every bvh_node above it
+//    let the ray in -- `reach` bit b = box b passed AND its parent is reached.
+//  * hitable_list::hit (src/hitable_list.cc:38-51) is replayed literally per item: children in
+//    list order against closest_so_far, any success replaces the record (rect bounds inclusive,
+//    sphere bounds strict -- the primitive tests themselves are the ones walk_range uses).
+//  * the nested merge `left.t < right.t ? left : right` is a tournament whose winner is the
+//    smallest t, the LAST one in DFS order among equals -- unless a candidate's t is NaN (a rect
+//    "hit" of a ray lying in its plane through 0/0), where `<` stops being an order. Such a ray
+//    is handed to walk_range, the literal frame-by-frame replay.
+//  * a one-element bvh_node hits its child twice and merges two identical records: the duplicate
+//    is not replayed.
+// A lane outside a box idles through that sub-tree (its result is masked); a sub-tree is skipped
+// when no lane of the warp reaches it.
+// ------------------------------------------------------------------------------------------
+static __device__ __noinline__ float2 closest_hit_replay(const float4 *blob, const SceneLayout *L, float ox, float oy, float oz,
+                                                         float dx, float dy, float dz, float time, float tmin, float tmax) {
+  SceneView S;
+  S.blob = blob;
+  S.L = L;
+  S.small = nullptr;
+  S.flat = nullptr;
+  Ray r;
+  r.o = mk(ox, oy, oz);
+  r.d = mk(dx, dy, dz);
+  r.time = time;
+  float t = 0.f;
+  int prim = -1;
+  walk_range<true, true>(S, r, 0, L->n_nodes, tmin, tmax, t, prim, nullptr);
+  return make_float2(t, __int_as_float(prim));
+}
+
+TPT_DEV bool closest_hit_flat(const SceneView &S, const Ray &r, float tmin, float tmax, float &t_out, int &prim_out) {
+  const FlatTree &F = *S.flat;
+  XRay x;
+  x.chain = -1;
+  unsigned reach = 0u;
+  for (int b = 0; b < F.n_boxes; b++) {
+    const float4 lo = F.boxes[b].lo, hi = F.boxes[b].hi;
+    const int parent = __float_as_int(hi.w);
+    const bool open = parent < 0 || ((reach >> parent) & 1u);
+    if (!__any_sync(__activemask(), open)) continue;
+    to_chain<true>(S, r, __float_as_int(lo.w), x);
+    if (open && aabb_hit<true>(x, lo, hi, tmin, tmax)) reach |= 1u << b;
+  }
+  x.chain = -1; // the primitive tests below need no 1/d: their chain changes skip the three quotients
+  float best_t = 0.f;
+  int best_prim = -1;
+  bool unordered = false;
+  for (int it = 0; it < F.n_items; it++) {
+    const FlatItem I = F.items[it];
+    const bool act = I.parent < 0 || ((reach >> I.parent) & 1u);
+    if (!__any_sync(__activemask(), act)) continue;
+    float run_t = tmax; // closest_so_far of this list (a lone leaf: the caller's t_max)
+    int run_prim = -1;
+    for (int k = I.first; k < I.end; k++) {
+      const FlatPrim P = F.prims[k];
+      to_chain<true, false>(S, r, P.chain, x);
+      float t;
+      bool hit;
+      if (P.kind == TPT_PRIM_SPHERE) hit = sphere_test<true>(mk(P.geo.x, P.geo.y, P.geo.z), P.geo.w, x, tmin, run_t, t);
+      else hit = rect_test<true>(P.kind - TPT_PRIM_XY_RECT, P.geo, P.k, x, tmin, run_t, t);
+      if (act && hit) {
+        run_t = t;
+        run_prim = P.prim;
+      }
+    }
+    if (run_prim >= 0) {
+      unordered = unordered || isnan(run_t);
+      if (best_prim < 0 || !(best_t < run_t)) {
+        best_t = run_t;
+        best_prim = run_prim;
+      }
+    }
+  }
+  if (unordered) {
+    const float2 w = closest_hit_replay(S.blob, S.L, r.o.x, r.o.y, r.o.z, r.d.x, r.d.y, r.d.z, r.time, tmin, tmax);
+    best_t = w.x;
+    best_prim = __float_as_int(w.y);
+  }
+  t_out = best_t;
+  prim_out = best_prim;
+  return best_prim >= 0;
 }
 
 // world->hit: the root tree is nodes [0, n_nodes)
@@ -969,7 +1126,12 @@ TPT_DEV void fill_hit(const SceneView &S, const Ray &r, int prim, float t, bool 
 // ------------------------------------------------------------------------------------------
 template <bool PAR> TPT_DEV float round_sin(float x) {
   if (PAR) return (float)sin((double)x); // std::sin(float) -> sinf, correctly-rounded stand-in
-  return __sinf(x);
+  // FAST: MUFU.SIN is only accurate near the origin (absolute error grows with |x|; texture arguments
+  // reach 10 * coordinate). Two-constant reduction to [-pi, pi] first: 2 pi = 6.2831855f - 1.7484556e-7f.
+  const float k = rintf(x * 0.15915494309189535f);
+  float r = fmaf(k, -6.2831854820251465f, x);
+  r = fmaf(k, 1.7484555314695172e-7f, r);
+  return __sinf(r);
 }
 template <bool PAR> TPT_DEV float round_cos(float x) {
   if (PAR) return (float)cos((double)x);
@@ -1106,8 +1268,12 @@ template <bool PAR> TPT_DEV V3 random_on_hemisphere(Rng &g) {
   float sr = sqrtf(r2);
   float x, y;
   if (PAR) {
-    x = round_cos<PAR>(phi) * sr;
-    y = round_sin<PAR>(phi) * sr;
+    // std::cos(float) / std::sin(float): one double sincos (shared argument reduction, half the code
+    // of two calls), each result rounded once to float
+    double sd, cd;
+    sincos((double)phi, &sd, &cd);
+    x = (float)cd * sr;
+    y = (float)sd * sr;
   } else {
     float s, c;
     __sincosf(phi, &s, &c);
@@ -1162,8 +1328,10 @@ template <bool PAR> TPT_DEV V3 light_random(const SceneView &S, V3 origin, Rng &
     float sq = sqrtf(1 - z * z);
     float x, y;
     if (PAR) {
-      x = (float)(cos(2 * TPT_PI_D * (double)r1) * (double)sq);
-      y = (float)(sin(2 * TPT_PI_D * (double)r1) * (double)sq);
+      double sd, cd;
+      sincos(2 * TPT_PI_D * (double)r1, &sd, &cd);
+      x = (float)(cd * (double)sq);
+      y = (float)(sd * (double)sq);
     } else {
       float s, co;
       __sincosf((2.f * TPT_PI_F) * r1, &s, &co);
@@ -1237,7 +1405,13 @@ template <bool PAR> TPT_DEV bool refract(V3 v, V3 n, float ni_over_nt, V3 &refra
 template <bool PAR> TPT_DEV float schlick(float cosine, float ref_index) {
   float r0 = (1 - ref_index) / (1 + ref_index);
   r0 = r0 * r0;
-  if (PAR) return (float)((double)r0 + (double)(1 - r0) * pow((double)(1 - cosine), 5.0));
+  if (PAR) {
+    // pow(double, 5): four double multiplications are within 2 ulp(double) of the exact power, like
+    // libm's pow -- the float the sum rounds to is the same except on ~2^-28 of the inputs -- at a
+    // twentieth of the code of the general pow
+    const double m = (double)(1 - cosine), m2 = m * m;
+    return (float)((double)r0 + (double)(1 - r0) * (m2 * m2 * m));
+  }
   float m = 1 - cosine;
   float m2 = m * m;
   return r0 + (1 - r0) * (m2 * m2 * m);
@@ -1266,12 +1440,22 @@ TPT_DEV Ray camera_sample(const CamView &C, int i, int j, int nx, int ny, Rng &g
   }
   // random_in_unit_disk, src/utils.cc:13-19: vec3(drand_r(), drand_r(), 0) -> y drawn first
   float px, py;
-  do {
+  {
     float y = g.next();
     float x = g.next();
     px = 2.0f * x - 1.0f;
     py = 2.0f * y - 1.0f;
-  } while (px * px + py * py >= 1.0f);
+  }
+  // Block 0 is used up. In nearly every warp some lane redraws its lens sample (21 % of the draws
+  // fall outside the disk) or draws a shutter time: the out-of-line refill then ran for ~6 of the 32
+  // lanes in every camera chunk (ncu, r01 capture). Block 1 is expanded here for all lanes instead.
+  if (TPT_EAGER_CAMERA_BLOCK == 1 || (TPT_EAGER_CAMERA_BLOCK == 2 && PAR)) g.next_block_inline();
+  while (px * px + py * py >= 1.0f) {
+    float y = g.next();
+    float x = g.next();
+    px = 2.0f * x - 1.0f;
+    py = 2.0f * y - 1.0f;
+  }
   float rdx = C.lens_radius * px, rdy = C.lens_radius * py;
   V3 offset = C.u * rdx + C.v * rdy;
   Ray r;
@@ -1393,8 +1577,9 @@ TPT_DEV int extend(const SceneView &S, const PathState &ps, int max_depth, float
     gp = &g;
   }
   bool any_hit;
-  if (PAR) {
-    any_hit = closest_hit<PAR>(S, ps.ray, t_min, FLT_MAX, t, prim, gp);
+  if constexpr (PAR) {
+    if constexpr (SMALL && !MEDIA) any_hit = closest_hit_flat(S, ps.ray, t_min, FLT_MAX, t, prim);
+    else any_hit = closest_hit<PAR>(S, ps.ray, t_min, FLT_MAX, t, prim, gp);
   } else {
     if (SMALL) any_hit = closest_hit_uniform(S, ps.ray, t_min, FLT_MAX, t, prim);
     else if (S.L->n_fbvh > 0 && S.L->fbvh_time_ok) any_hit = closest_hit_fbvh(S, ps.ray, t_min, FLT_MAX, t, prim);

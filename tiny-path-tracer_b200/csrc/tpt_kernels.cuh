@@ -29,6 +29,7 @@ __global__ void __launch_bounds__(128) intersect_kernel(const __grid_constant__ 
   S.blob = stage_scene<SMEM>(A.scene, sblob);
   S.L = &A.scene;
   S.small = &A.small;
+  S.flat = &A.flat;
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= A.n) return;
   const float *q = A.rays + 7 * idx;
@@ -46,7 +47,8 @@ __global__ void __launch_bounds__(128) intersect_kernel(const __grid_constant__ 
   float t;
   int prim;
   bool any_hit;
-  if (SMALL && !PAR) any_hit = closest_hit_uniform(S, r, A.tmin, A.tmax, t, prim);
+  if constexpr (SMALL && PAR) any_hit = closest_hit_flat(S, r, A.tmin, A.tmax, t, prim);
+  else if constexpr (SMALL && !PAR) any_hit = closest_hit_uniform(S, r, A.tmin, A.tmax, t, prim);
   else if (!PAR && A.scene.n_fbvh > 0) any_hit = closest_hit_fbvh(S, r, A.tmin, A.tmax, t, prim);
   else any_hit = closest_hit<PAR>(S, r, A.tmin, A.tmax, t, prim, nullptr);
   if (any_hit) {
@@ -156,6 +158,7 @@ __global__ void __launch_bounds__(TPT_MEGA_THREADS) render_mega_kernel(const __g
   S.blob = stage_scene<SMEM>(A.scene, sblob);
   S.L = &A.scene;
   S.small = &A.small;
+  S.flat = &A.flat;
   const unsigned FULL = 0xffffffffu;
   const unsigned lane = threadIdx.x & 31u;
 
@@ -244,7 +247,7 @@ __global__ void __launch_bounds__(TPT_MEGA_THREADS) render_mega_kernel(const __g
 __host__ __device__ constexpr int wave_state_words(bool media) { return media ? 21 : 20; } // 32-bit words of path state per slot
 
 template <bool PAR, bool SMALL, bool SMEM, bool MEDIA, bool CULL, bool TRACE = false, bool LEAN = false>
-__global__ void __launch_bounds__(TPT_WAVE_THREADS, TRACE ? TPT_TRACE_MIN_BLOCKS : (LEAN ? TPT_WAVE_LEAN_MIN_BLOCKS : TPT_WAVE_MIN_BLOCKS))
+__global__ void __launch_bounds__(TPT_WAVE_THREADS, TRACE ? TPT_TRACE_MIN_BLOCKS : (LEAN ? TPT_WAVE_LEAN_MIN_BLOCKS : (PAR ? TPT_WAVE_PAR_MIN_BLOCKS : TPT_WAVE_MIN_BLOCKS)))
 render_wave_kernel(const __grid_constant__ RenderArgs A) {
   // shade and generate as ONE phase (a warp takes material chunks and generate chunks from one list:
   // better balance, one barrier fewer) or as two (each phase's code stays hot in the instruction
@@ -278,6 +281,7 @@ render_wave_kernel(const __grid_constant__ RenderArgs A) {
   S.blob = stage_scene<SMEM>(A.scene, sblob + (STATE_BYTES + QUEUE_BYTES) / 16); // > 64 KB: stays in global memory
   S.L = &A.scene;
   S.small = &A.small;
+  S.flat = &A.flat;
   __shared__ unsigned q_cnt[2][2];
   __shared__ int n_idle;
   __shared__ int trace_next; // TRACE: next slot whose ray nobody has taken yet
@@ -573,7 +577,7 @@ render_wave_kernel(const __grid_constant__ RenderArgs A) {
               // the box) ends its path right here -- world->hit is false for it -- and the lane draws
               // its pixel's next sample instead of spending an extend pass on it. Bounded retries:
               // the last ray of the budget (or of the bin) goes to extend like any other.
-              if (!MEDIA && !PAR) { // FAST kernels only: compiled into the parity kernels it costs them 4 %
+              if (!MEDIA && (!PAR || TPT_PAR_CAMERA_TRIES)) { // PARITY: the reference's own root-box test (may_hit_world<true>), same outcome as the extend pass it replaces
                 for (int attempt = 1; attempt < A.camera_tries && k + 1 < k_end && !may_hit_world<PAR>(S, r, A.t_min); attempt++) {
                   V3 bg = background_radiance<PAR>(S, r, mk(1.f, 1.f, 1.f));
                   SF(F_AX, s) += isnan(bg.x) ? 0.f : bg.x; // col += de_nan(tmp), as in extend
@@ -631,6 +635,7 @@ template <bool PAR> __global__ void texture_probe_kernel(const __grid_constant__
   S.blob = A.scene.blob_global;
   S.L = &A.scene;
   S.small = nullptr;
+  S.flat = nullptr;
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= A.n) return;
   const float *q = A.uvp + 5 * idx;
@@ -698,6 +703,9 @@ typedef void (*wave_fn)(RenderArgs);
 // `trace` (FAST only): closest hits through the library's SAH BVH with dynamic ray hand-out; the
 // scene tables are read through L1 there and shared memory holds TPT_TRACE_SLOTS path slots.
 template <bool CULL> static wave_fn wave_variant_c(bool small, bool smem, bool media, bool trace, bool lean) {
+#if TPT_PAR && TPT_PAR_LEAN
+  if (lean && small && smem && !media) return render_wave_kernel<true, true, true, false, CULL, false, true>;
+#endif
 #if !TPT_PAR
   if (lean && small && smem && !media && !trace) return render_wave_kernel<false, true, true, false, CULL, false, true>;
   if (trace) return media ? render_wave_kernel<false, false, false, true, CULL, true> : render_wave_kernel<false, false, false, false, CULL, true>;

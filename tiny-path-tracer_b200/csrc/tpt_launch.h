@@ -19,6 +19,15 @@
 #ifndef TPT_WAVE_MIN_BLOCKS
 #define TPT_WAVE_MIN_BLOCKS 3 // __launch_bounds__ min blocks per SM: 80 registers, 3 CTAs (measured best)
 #endif
+#ifndef TPT_PAR_CAMERA_TRIES
+#define TPT_PAR_CAMERA_TRIES 0 // parity kernels redraw camera rays that miss the root bvh_node's box inside generate (like the fast kernels)
+#endif
+#ifndef TPT_PAR_LEAN
+#define TPT_PAR_LEAN 1 // parity wavefront kernel without the texture / uv code for scenes whose textures are all constant
+#endif
+#ifndef TPT_WAVE_PAR_MIN_BLOCKS
+#define TPT_WAVE_PAR_MIN_BLOCKS TPT_WAVE_MIN_BLOCKS // parity kernels
+#endif
 #ifndef TPT_WAVE_LEAN_MIN_BLOCKS
 #define TPT_WAVE_LEAN_MIN_BLOCKS 3 // lean small-scene kernels; 4 (64 registers, four 52 KB CTAs per SM) gains 1 % without the camera redraws and loses 6 % with them (72 B of spills)
 #endif
@@ -39,7 +48,10 @@ namespace tptd {
 
 struct IntersectArgs {
   SceneLayout scene;
-  SmallScene small;
+  union { // one of the two per launch: FAST kernels read `small`, PARITY kernels read `flat`
+    SmallScene small;
+    FlatTree flat;
+  };
   const float *rays; // n x 7
   size_t n;
   float tmin, tmax;
@@ -48,7 +60,10 @@ struct IntersectArgs {
 
 struct RenderArgs {
   SceneLayout scene;
-  SmallScene small;
+  union { // one of the two per launch: FAST kernels read `small`, PARITY kernels read `flat`
+    SmallScene small;
+    FlatTree flat;
+  };
   CamView cam;
   int nx, ny, ns, max_depth;
   float t_min;

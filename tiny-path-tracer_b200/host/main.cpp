@@ -18,7 +18,7 @@
 #include "tpt.h"
 #include "tpt_flatten.h"
 #include "tpt_image_io.h"
-#include "tpt_ini.h"
+#include "inipp.h" // third_party/inipp.h, vendored verbatim (MIT)
 #include "tpt_scene.h"
 
 #include <chrono>

@@ -2,6 +2,7 @@
 #include "tpt_flatten.h"
 
 #include <cstring>
+#include <algorithm>
 #include <limits>
 
 namespace tpt {
@@ -82,8 +83,32 @@ int Flattener::begin_group(int kind, const AABB &bounds) {
 }
 
 void Flattener::end_group(int node_index) {
-  out_.nodes[node_index].end_or_prim = (int32_t)out_.nodes.size();
+  tpt_node &g = out_.nodes[node_index];
+  g.end_or_prim = (int32_t)out_.nodes.size();
   --depth_;
+  if ((g.kind & 0xff) == TPT_NODE_LIST) {
+    // The reference never box-tests a hitable_list (src/hitable_list.cc:38-51); the FAST walk and the
+    // scene-bounds tests do. hitable_list::bounding_box(0, 0) only covers a moving_sphere's t = 0
+    // position, so the node's box is rebuilt here as the union of its children's NODE boxes (a
+    // moving sphere's leaf box spans its own [time0, time1], a bvh_node carries the box its ctor
+    // built). A child stated in another chain's space cannot be united: then the list is unbounded.
+    const float m = std::numeric_limits<float>::max();
+    float lo[3] = {m, m, m}, hi[3] = {-m, -m, -m};
+    bool bounded = g.end_or_prim > node_index + 1;
+    for (int i = node_index + 1; bounded && i < g.end_or_prim;) {
+      const tpt_node &c = out_.nodes[i];
+      if ((c.kind >> 16) != (g.kind >> 16)) bounded = false;
+      for (int k = 0; k < 3; k++) {
+        lo[k] = std::min(lo[k], c.bmin[k]);
+        hi[k] = std::max(hi[k], c.bmax[k]);
+      }
+      i = (c.kind & 0xff) == TPT_NODE_LEAF ? i + 1 : c.end_or_prim;
+    }
+    for (int k = 0; k < 3; k++) {
+      g.bmin[k] = bounded ? lo[k] : -m;
+      g.bmax[k] = bounded ? hi[k] : m;
+    }
+  }
 }
 
 void Flattener::leaf(const hitable *self, int prim_kind, const float *params, int n_params,

@@ -66,6 +66,16 @@ hitable *build_named(const std::string &name, const unsigned char *img, int iw, 
     l[4] = new sphere(vec3(5, -1, -2), 2, new lambertian(new perlin_noise_texture(2.0f)));
     return new hitable_list(l, 5);
   }
+  if (name == "moving_list_test") {
+    // test scene: a hitable_list ROOT that holds a moving_sphere which travels far outside its t = 0
+    // position, a lamp and a floor -- list boxes must cover the whole motion (nothing in the reference
+    // box-tests a hitable_list; the FAST walk and the scene-bounds tests do)
+    hitable **l = new hitable *[3];
+    l[0] = new moving_sphere(vec3(-6, 0, 0), vec3(6, 3, 0), 0.0f, 1.0f, 1.0f, new lambertian(new constant_texture({0.7, 0.3, 0.3})));
+    l[1] = new flip_normal(new xz_rect(-2, 2, -2, 2, 6, new diffuse_light(new constant_texture(vec3(6, 6, 6)))));
+    l[2] = new xz_rect(-8, 8, -4, 4, -1.5f, new lambertian(new constant_texture({0.6, 0.6, 0.6})));
+    return new hitable_list(l, 3);
+  }
   if (name == "earth") { // main.cpp:78-81
     if (!img) return nullptr;
     unsigned char *copy = new unsigned char[(size_t)iw * ih * 3];

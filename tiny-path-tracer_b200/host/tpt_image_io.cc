@@ -1,5 +1,8 @@
 // host/tpt_image_io.cc -- see tpt_image_io.h
 #include "tpt_image_io.h"
+
+#define STB_IMAGE_IMPLEMENTATION // as src/utils.cc:11-12
+#include "stb_image.h"
 #include "tpt_scene.h"
 
 #include <cstdio>
@@ -102,32 +105,9 @@ bool read_ppm(const std::string &path, std::vector<uint8_t> &rgb, int &w, int &h
 
 } // namespace tpt
 
-// Texture input. The reference decodes through stb_image (src/utils.cc:236-240); the decoded
-// RGB bytes are what crosses the boundary (tpt_image_desc). This front end decodes baseline JPEG
-// itself (tpt_jpeg.cc: same integer IDCT / colour conversion, byte-identical on earthmap.jpg),
-// reads binary/ASCII PPM directly, and for anything else shells out to ImageMagick
-// (`convert`), the external tool the reference's output stage already depends on
-// (main.cpp:224-245). Returns malloc'ed memory like stbi_load, or nullptr.
+// Texture input, exactly as the reference: stb_image (third_party/stb_image.h, vendored verbatim,
+// v2.23, public domain) behind the same wrapper, src/utils.cc:236-240. Returns stbi's malloc'ed
+// memory (channels as in the file; the scene builders expect 3, src/texture.cc:27-42), or nullptr.
 unsigned char *load_image_texture(std::string filename, int &width, int &height, int &channels) {
-  std::vector<uint8_t> rgb;
-  std::string path = filename;
-  bool is_ppm = filename.size() > 4 && filename.substr(filename.size() - 4) == ".ppm";
-  if (!is_ppm && tpt::read_jpeg(filename, rgb, width, height)) { // the built-in baseline decoder
-    channels = 3;
-    unsigned char *out = static_cast<unsigned char *>(std::malloc(rgb.size()));
-    if (out) std::memcpy(out, rgb.data(), rgb.size());
-    return out;
-  }
-  if (!is_ppm) {
-    std::string tmp = filename + ".tpt_decoded.ppm";
-    std::string cmd = "convert '" + filename + "' -depth 8 '" + tmp + "' 2>/dev/null";
-    if (std::system(cmd.c_str()) != 0) return nullptr;
-    path = tmp;
-  }
-  if (!tpt::read_ppm(path, rgb, width, height)) return nullptr;
-  if (!is_ppm) std::remove(path.c_str());
-  channels = 3;
-  unsigned char *out = static_cast<unsigned char *>(std::malloc(rgb.size()));
-  if (out) std::memcpy(out, rgb.data(), rgb.size());
-  return out;
+  return stbi_load(filename.c_str(), &width, &height, &channels, 0);
 }

@@ -24,8 +24,6 @@ void append_pictures(const std::vector<const uint8_t *> &pictures, const std::ve
                      const std::vector<int> &heights, std::vector<uint8_t> &out, int &w, int &h);
 // binary PPM ("P6"), rows top to bottom; rgb8 is the library's bottom-up layout
 bool write_ppm_binary(const std::string &path, const uint8_t *rgb8, int nx, int ny);
-// baseline JPEG (8-bit, 1 or 3 components, no chroma subsampling): tpt_jpeg.cc
-bool read_jpeg(const std::string &path, std::vector<uint8_t> &rgb, int &w, int &h);
 // PPM (P6/P3) reader used by tests and as a texture source
 bool read_ppm(const std::string &path, std::vector<uint8_t> &rgb, int &w, int &h);
 } // namespace tpt

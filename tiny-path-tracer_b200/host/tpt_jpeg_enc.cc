@@ -11,7 +11,7 @@
 // quantisation tables are the T.81 annex K examples scaled by the IJG quality rule; the Huffman
 // tables are built per picture from the symbol statistics with the annex K.2 procedure (two
 // passes over the coefficients), so no fixed code tables are embedded. tests/test_host_frontend.py
-// decodes the result with an independent decoder (PIL) and with tpt_jpeg.cc and checks the PSNR.
+// decodes the result with PIL and with the vendored stb_image and checks the PSNR.
 #include "tpt_image_io.h"
 
 #include <algorithm>
