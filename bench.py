@@ -272,7 +272,7 @@ def stock_reference_fit(c, budget_s=40.0):
             t0 = time.perf_counter()
             r = subprocess.run([exe], cwd=d, capture_output=True, text=True, timeout=600)
             wall = time.perf_counter() - t0
-            m = re.search(r"time:\s*([0-9.eE+-]+)\s*s", r.stdout)
+            m = re.search(r"^time:\s*([0-9.eE+-]+)\s*s", r.stdout, re.M)  # not the bogus "estimate time:" line (main.cpp:160-172)
             return (float(m.group(1)) if m else None), wall
         finally:
             shutil.rmtree(d, ignore_errors=True)
@@ -320,7 +320,7 @@ def program_e2e(c, mode):
                 wall = time.perf_counter() - t0
                 if r.returncode != 0:
                     return {"error": (r.stderr or r.stdout)[-300:]}
-                m = re.search(r"time:\s*([0-9.eE+-]+)\s*s", r.stdout)
+                m = re.search(r"^time:\s*([0-9.eE+-]+)\s*s", r.stdout, re.M)  # not the bogus "estimate time:" line (main.cpp:160-172)
                 g = re.search(r"gpu render:\s*([0-9.eE+-]+)\s*s", r.stdout)
                 row = {"time_line_s": float(m.group(1)) if m else None, "process_wall_s": wall,
                        "gpu_render_s": float(g.group(1)) if g else None,

@@ -1,0 +1,81 @@
+"""The reference-side binding compiled for real (oracle/flatten_ref.cc -> oracle/_ref/libtptbind.so):
+built against the UNMODIFIED reference headers, it walks scenes made by the reference's own builders
+(src/utils.cc) with dynamic_cast over the reference's classes and calls libtpt.so.
+
+* no GPU: the tpt_scene_desc tables it produces equal, byte for byte, the ones the repo's own front
+  end (host/tpt_scene.h classes + host/tpt_flatten.cc) produces -- the C-ABI is a drop-in for the real
+  classes, not only for the repo's look-alikes;
+* GPU: cornell_box() built by the reference and rendered through the binding is bit-identical to the
+  render through the repo's front end."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import common
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIND = os.path.join(ROOT, "oracle", "_ref", "libtptbind.so")
+SCENES = ["cornell_box", "sphere_cornell_box", "random_scene", "two_perlin_spheres", "light_spheres", "earth"]
+
+
+@pytest.fixture(scope="module")
+def B(T):
+    if not os.path.exists(BIND):
+        pytest.skip("oracle/_ref/libtptbind.so is not built (needs /root/reference: __graft_entry__.build())")
+    lib = C.CDLL(BIND)
+    lib.tptbind_last_error.restype = C.c_char_p
+    lib.tptbind_describe.restype = C.c_long
+    lib.tptbind_describe.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_long, C.POINTER(C.c_int32)]
+    lib.tptbind_render.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float),
+                                   C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.POINTER(T.RenderParams),
+                                   C.c_void_p, C.c_void_p, C.POINTER(T.Stats)]
+    return lib
+
+
+def host_tables(T, hs):
+    """the same tables, in the same order, from the repo front end's description"""
+    d = hs.desc.contents
+    parts = [(d.nodes, d.n_nodes, T.Node), (d.prims, d.n_prims, T.Prim), (d.chains, d.n_chains, T.Chain),
+             (d.xform_ops, d.n_xform_ops, T.XformOp), (d.materials, d.n_materials, T.Material),
+             (d.textures, d.n_textures, T.Texture), (d.lights, d.n_lights, T.Light)]
+    blob = b"".join(C.string_at(p, n * C.sizeof(t)) if n else b"" for p, n, t in parts)
+    counts = [d.n_nodes, d.n_prims, d.n_chains, d.n_xform_ops, d.n_materials, d.n_textures, d.n_images, d.n_lights]
+    return blob, counts
+
+
+@pytest.mark.parametrize("scene", SCENES)
+def test_binding_describes_the_reference_scene_like_the_front_end(T, B, scene):
+    img = common.earth_small() if scene == "earth" else None
+    img_p = np.ascontiguousarray(img).ctypes.data if img is not None else None
+    ih, iw = (img.shape[:2] if img is not None else (0, 0))
+    out = (C.c_ubyte * (1 << 20))()
+    counts = (C.c_int32 * 8)()
+    n = B.tptbind_describe(scene.encode(), img_p, iw, ih, out, len(out), counts)
+    assert n > 0, B.tptbind_last_error()
+    mine, my_counts = host_tables(T, common.host_scene(T, scene))
+    assert list(counts) == my_counts
+    assert bytes(out[:n]) == mine
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("scene,cam", [("cornell_box", common.CORNELL_CAM), ("sphere_cornell_box", common.CORNELL_CAM),
+                                       ("light_spheres", dict(common.BOOK_CAM, vfov=40.0))])
+def test_render_through_the_binding_is_bit_identical(T, B, gpu, scene, cam):
+    nx, ny, ns, depth = 160, 120, 16, 15
+    if scene == "light_spheres":
+        pytest.skip("Perlin tables are re-randomised by every perlin_noise ctor (wall-clock seed): two builds never share them")
+    for mode in (T.MODE_PARITY, T.MODE_FAST):
+        p = T.make_params(nx, ny, ns, depth, mode=mode, seed=11, kernel=T.KERNEL_WAVEFRONT)
+        mine = T.Scene(common.host_scene(T, scene)).render(common.product_camera(T, cam, nx, ny), p)
+        s = np.zeros((1, ny, nx, 3), np.float32)
+        r = np.zeros((ny, nx, 3), np.uint8)
+        st = T.Stats()
+        f3 = lambda v: (C.c_float * 3)(*[float(x) for x in v])
+        rc = B.tptbind_render(scene.encode(), None, 0, 0, f3(cam["lookfrom"]), f3(cam["lookat"]), cam["vfov"], cam["aperture"],
+                              cam["focus_dist"], 0.0, 0.0, C.byref(p), s.ctypes.data, r.ctypes.data, C.byref(st))
+        assert rc == 0, B.tptbind_last_error()
+        assert np.array_equal(s, mine.sum_rgb) and np.array_equal(r, mine.rgb8)
+        assert st.paths == nx * ny * ns == mine.stats["paths"] and st.rays == mine.stats["rays"]
+        assert mine.sum_rgb.max() > 0

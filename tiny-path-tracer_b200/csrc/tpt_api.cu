@@ -921,7 +921,10 @@ int make_plan(tpt_scene *s, const tpt_camera *cam, const tpt_render_params *p, P
       // bins of a pixel in range order -- another association of the same fp32 sum (~1e-7
       // relative, gate 2 allows 1e-4); reserved[1] = 1 keeps one bin per pixel and slice, i.e. the
       // reference's strictly sequential sum
-      const double slots = (double)s->prop.multiProcessorCount * 1536.0;
+      // resident path slots per SM: 2 CTAs x 1152 (fast) / 768 (parity) on small scenes, 3 x 512 otherwise
+      const bool small_scene = plan.parity ? s->flat.enabled != 0 : s->small.enabled != 0;
+      const double slots = (double)s->prop.multiProcessorCount *
+                           (small_scene ? TPT_SMALL_MIN_BLOCKS * (plan.parity ? TPT_SMALL_SLOTS_PAR : TPT_SMALL_SLOTS_FAST) : 1536.0);
       const double local_pixels = (double)p->nx * p->ny / p->part_count;
       long long want = (long long)std::ceil(32.0 * slots / std::max(local_pixels, 1.0) / slices);
       long long by_samples = std::max(1, per_slice / 8);                       // >= 8 samples per bin
@@ -1034,7 +1037,9 @@ int run_plan(tpt_scene *s, Plan &plan, bool want_sum, bool want_rgb8, bool want_
   st.kernel_launches = 2;
   st.sm_count = s->prop.multiProcessorCount;
   st.blocks = plan.blocks;
-  st.threads_per_block = plan.wavefront ? TPT_WAVE_THREADS : TPT_MEGA_THREADS;
+  st.threads_per_block = !plan.wavefront ? TPT_MEGA_THREADS
+                                          : (plan.parity ? wave_threads_parity(A, small, s->use_smem, media, trace)
+                                                         : wave_threads_fast(A, small, s->use_smem, media, trace));
   st.reserved[0] = A.n_ranges; // sample ranges per pixel (accumulator planes written by the kernel)
   st.h2d_bytes = s->blob_bytes + sizeof(RenderArgs) + sizeof(ResolveArgs); // scene blob + launch arguments
   s->last_nx = A.nx;
@@ -1144,6 +1149,9 @@ int launch_batch(tpt_scene *s, const tpt_camera *cam, const tpt_render_params *p
     CK(plan.parity ? launch_mega_parity(A, s->use_smem, small, media, blocks, s->stream)
                    : launch_mega_fast(A, s->use_smem, small, media, blocks, s->stream));
   s->stats.blocks = blocks;
+  s->stats.threads_per_block = !plan.wavefront ? TPT_MEGA_THREADS
+                                               : (plan.parity ? wave_threads_parity(A, small, s->use_smem, media, trace)
+                                                              : wave_threads_fast(A, small, s->use_smem, media, trace));
   return TPT_OK;
 }
 
@@ -1314,7 +1322,7 @@ int render_multi(tpt_scene *const *scenes, int n, const tpt_camera *cam, const t
   st.resolve_ms = t_gather;
   st.sm_count = s0->prop.multiProcessorCount;
   st.blocks = s0->stats.blocks;
-  st.threads_per_block = plan0.wavefront ? TPT_WAVE_THREADS : TPT_MEGA_THREADS;
+  st.threads_per_block = s0->stats.threads_per_block;
   st.h2d_bytes = (s0->blob_bytes + sizeof(RenderArgs) + sizeof(ResolveArgs)) * n;
   s0->stats = st;
   rc = fetch(s0, out);

@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(TPT_MEGA_THREADS) render_mega_kernel(const __g
 // ------------------------------------------------------------------------------------------
 // Persistent WAVEFRONT kernel: generate / extend / shade queues in shared memory.
 //
-// A CTA owns TPT_WAVE_SLOTS path slots (two per thread) whose state -- ray, throughput, per-pixel
+// A CTA owns wave_slots() path slots (two or three per thread, tpt_launch.h) whose state -- ray, throughput, per-pixel
 // accumulator, sample bookkeeping, pending hit -- lives in shared memory as structure-of-arrays.
 // Every iteration has two phases separated by __syncthreads() (three in the parity kernels, where
 // generate runs after shade as a phase of its own, see SPLIT_GEN below):
@@ -247,17 +247,20 @@ __global__ void __launch_bounds__(TPT_MEGA_THREADS) render_mega_kernel(const __g
 __host__ __device__ constexpr int wave_state_words(bool media) { return media ? 21 : 20; } // 32-bit words of path state per slot
 
 template <bool PAR, bool SMALL, bool SMEM, bool MEDIA, bool CULL, bool TRACE = false, bool LEAN = false>
-__global__ void __launch_bounds__(TPT_WAVE_THREADS, TRACE ? TPT_TRACE_MIN_BLOCKS : (LEAN ? TPT_WAVE_LEAN_MIN_BLOCKS : (PAR ? TPT_WAVE_PAR_MIN_BLOCKS : TPT_WAVE_MIN_BLOCKS)))
+__global__ void __launch_bounds__(wave_threads(SMALL, TRACE), wave_min_blocks(PAR, SMALL, TRACE, LEAN))
 render_wave_kernel(const __grid_constant__ RenderArgs A) {
   // shade and generate as ONE phase (a warp takes material chunks and generate chunks from one list:
   // better balance, one barrier fewer) or as two (each phase's code stays hot in the instruction
   // cache). Measured on the Cornell frame: the split form won by 8 % while the kernel carried the
   // texture code it never runs; with the lean build the merged form wins by 6 % (fast mode). The
   // parity kernels are several times larger and keep the split (merged: -6 %).
-  constexpr bool SPLIT_GEN = TPT_WAVE_SPLIT_GEN == 1 || (TPT_WAVE_SPLIT_GEN == 2 && PAR);
+  // r02: the small-scene parity kernels (flat replay of the reference tree, lean build) are small enough
+  // for the merged form as well: +4.6 % / +5.5 % (Cornell A / B).
+  constexpr bool SPLIT_GEN = TPT_WAVE_SPLIT_GEN == 1 || (TPT_WAVE_SPLIT_GEN == 2 && PAR && !SMALL);
   extern __shared__ float4 sblob[];
-  constexpr int NSLOT = TRACE ? TPT_TRACE_SLOTS : TPT_WAVE_SLOTS;
-  constexpr int NWARP = TPT_WAVE_THREADS / 32;
+  constexpr int NSLOT = wave_slots(PAR, SMALL, TRACE);
+  constexpr int THREADS = wave_threads(SMALL, TRACE);
+  constexpr int NWARP = THREADS / 32;
   // structure-of-arrays slot state: field f of slot s at sf[f * NSLOT + s]
   // F_DEPTH < 0 marks a slot without a live path; F_NDRAW (draws a medium took inside world->hit)
   // exists only in the media builds. 20 words per slot, 96 B with the queues: 48 KB per 512-slot CTA.
@@ -302,7 +305,7 @@ render_wave_kernel(const __grid_constant__ RenderArgs A) {
   const unsigned bins_per_tile = (unsigned)(TPT_TILE * TPT_TILE) * (unsigned)A.n_ranges;
   unsigned long long n_rays = 0, n_nan = 0, n_paths = 0, n_culled = 0;
 
-  for (int s = tid; s < NSLOT; s += TPT_WAVE_THREADS) {
+  for (int s = tid; s < NSLOT; s += THREADS) {
     SI(F_DEPTH, s) = -1;
     SI(F_K, s) = 0;
     SI(F_KEND, s) = -1; // no bin yet
@@ -371,7 +374,7 @@ render_wave_kernel(const __grid_constant__ RenderArgs A) {
       }
       __syncthreads();
     }
-    for (int s0 = warp * 32; s0 < NSLOT; s0 += TPT_WAVE_THREADS) {
+    for (int s0 = warp * 32; s0 < NSLOT; s0 += THREADS) {
       const int s = s0 + (int)lane;
       int cls = -2; // -2: nothing to do
       const int depth_s = SI(F_DEPTH, s);
@@ -700,42 +703,55 @@ cudaError_t TPT_FN(launch_mega_)(const RenderArgs &A, bool smem, bool small, boo
 }
 
 typedef void (*wave_fn)(RenderArgs);
+struct WaveVariant {
+  wave_fn fn;
+  int threads, slots;
+};
+template <bool SMALL, bool SMEM, bool MEDIA, bool CULL, bool TRACE, bool LEAN> static WaveVariant wave_pick() {
+  return WaveVariant{render_wave_kernel<TPT_PAR, SMALL, SMEM, MEDIA, CULL, TRACE, LEAN>, wave_threads(SMALL, TRACE),
+                     wave_slots(TPT_PAR, SMALL, TRACE)};
+}
 // `trace` (FAST only): closest hits through the library's SAH BVH with dynamic ray hand-out; the
 // scene tables are read through L1 there and shared memory holds TPT_TRACE_SLOTS path slots.
-template <bool CULL> static wave_fn wave_variant_c(bool small, bool smem, bool media, bool trace, bool lean) {
+template <bool CULL> static WaveVariant wave_variant_c(bool small, bool smem, bool media, bool trace, bool lean) {
 #if TPT_PAR && TPT_PAR_LEAN
-  if (lean && small && smem && !media) return render_wave_kernel<true, true, true, false, CULL, false, true>;
+  if (lean && small && smem && !media) return wave_pick<true, true, false, CULL, false, true>();
 #endif
 #if !TPT_PAR
-  if (lean && small && smem && !media && !trace) return render_wave_kernel<false, true, true, false, CULL, false, true>;
-  if (trace) return media ? render_wave_kernel<false, false, false, true, CULL, true> : render_wave_kernel<false, false, false, false, CULL, true>;
+  if (lean && small && smem && !media && !trace) return wave_pick<true, true, false, CULL, false, true>();
+  if (trace) return media ? wave_pick<false, false, true, CULL, true, false>() : wave_pick<false, false, false, CULL, true, false>();
 #endif
   (void)trace;
   (void)lean;
-  if (media) return smem ? render_wave_kernel<TPT_PAR, false, true, true, CULL> : render_wave_kernel<TPT_PAR, false, false, true, CULL>;
-  if (!smem) return render_wave_kernel<TPT_PAR, false, false, false, CULL>;
-  return small ? render_wave_kernel<TPT_PAR, true, true, false, CULL> : render_wave_kernel<TPT_PAR, false, true, false, CULL>;
+  if (media) return smem ? wave_pick<false, true, true, CULL, false, false>() : wave_pick<false, false, true, CULL, false, false>();
+  if (!smem) return wave_pick<false, false, false, CULL, false, false>();
+  return small ? wave_pick<true, true, false, CULL, false, false>() : wave_pick<false, true, false, CULL, false, false>();
 }
-static wave_fn wave_variant(const RenderArgs &A, bool small, bool smem, bool media, bool trace) {
+static WaveVariant wave_variant(const RenderArgs &A, bool small, bool smem, bool media, bool trace) {
   return A.cull ? wave_variant_c<true>(small, smem, media, trace, A.lean != 0) : wave_variant_c<false>(small, smem, media, trace, A.lean != 0);
 }
-static size_t wave_smem_bytes(const RenderArgs &A, bool smem, bool media, bool trace) {
+static size_t wave_smem_bytes(const RenderArgs &A, const WaveVariant &v, bool smem, bool media, bool trace) {
   const size_t per_slot = (size_t)wave_state_words(media) * 4 + 2 * TPT_WAVE_NQ * 2;
-  if (trace && !TPT_PAR) return (size_t)TPT_TRACE_SLOTS * per_slot;
-  return (smem ? (size_t)A.scene.blob_words * 16 : 0) + (size_t)TPT_WAVE_SLOTS * per_slot;
+  if (trace && !TPT_PAR) return (size_t)v.slots * per_slot;
+  return (smem ? (size_t)A.scene.blob_words * 16 : 0) + (size_t)v.slots * per_slot;
 }
 
 cudaError_t TPT_FN(wave_occupancy_)(const RenderArgs &A, bool small, bool smem, bool media, bool trace, int *blocks_per_sm) {
-  wave_fn k = wave_variant(A, small, smem, media, trace);
-  size_t bytes = wave_smem_bytes(A, smem, media, trace);
-  cudaError_t e = allow_smem(k, bytes);
+  const WaveVariant v = wave_variant(A, small, smem, media, trace);
+  size_t bytes = wave_smem_bytes(A, v, smem, media, trace);
+  cudaError_t e = allow_smem(v.fn, bytes);
   if (e != cudaSuccess) return e;
-  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k, TPT_WAVE_THREADS, bytes);
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, v.fn, v.threads, bytes);
 }
 
 cudaError_t TPT_FN(launch_wave_)(const RenderArgs &A, bool small, bool smem, bool media, bool trace, int blocks, cudaStream_t st) {
-  wave_variant(A, small, smem, media, trace)<<<blocks, TPT_WAVE_THREADS, wave_smem_bytes(A, smem, media, trace), st>>>(A);
+  const WaveVariant v = wave_variant(A, small, smem, media, trace);
+  v.fn<<<blocks, v.threads, wave_smem_bytes(A, v, smem, media, trace), st>>>(A);
   return cudaGetLastError();
+}
+
+int TPT_FN(wave_threads_)(const RenderArgs &A, bool small, bool smem, bool media, bool trace) {
+  return wave_variant(A, small, smem, media, trace).threads;
 }
 
 cudaError_t TPT_FN(launch_texture_probe_)(const TextureProbeArgs &A, cudaStream_t st) {

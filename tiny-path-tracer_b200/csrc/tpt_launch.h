@@ -5,7 +5,7 @@
 
 #define TPT_MEGA_THREADS 256
 #ifndef TPT_WAVE_SPLIT_GEN
-#define TPT_WAVE_SPLIT_GEN 2 // generate as its own phase after shade: 0 never, 1 always, 2 in the parity kernels only (see render_wave_kernel)
+#define TPT_WAVE_SPLIT_GEN 2 // generate as its own phase after shade: 0 never, 1 always, 2 in the LARGE-scene parity kernels only (see render_wave_kernel)
 #endif
 #ifndef TPT_TRACE_ENABLE
 #define TPT_TRACE_ENABLE 1
@@ -44,7 +44,36 @@
 #define TPT_WAVE_SLOTS 512 // path slots per CTA (two per thread)
 #endif
 
+#ifndef TPT_SMALL_THREADS
+#define TPT_SMALL_THREADS 384 // small-scene (constant-bank intersector) kernels: 384 threads, 2 CTAs/SM
+#endif
+#ifndef TPT_SMALL_MIN_BLOCKS
+#define TPT_SMALL_MIN_BLOCKS 2
+#endif
+#ifndef TPT_SMALL_SLOTS_FAST
+#define TPT_SMALL_SLOTS_FAST 1152 // three path slots per thread
+#endif
+#ifndef TPT_SMALL_SLOTS_PAR
+#define TPT_SMALL_SLOTS_PAR 768
+#endif
+
 namespace tptd {
+
+// CTA shape of a wavefront kernel instantiation: threads, path slots, minimum resident CTAs per SM.
+// Chosen per kernel family from measurements on B200 (profiles/r02_tuning_sweeps.txt):
+//  * small scenes (everything on chip, warp-uniform intersectors): the hot code is about as large as
+//    the SM's instruction cache, and CTAs sit in different phases of it. Two CTAs of 384 threads
+//    instead of three of 256 keep fewer phases' code live at once (same 24 warps per SM):
+//    parity +6 %, and with three slots per thread the fast kernels gain another 3-5 % (fuller
+//    chunks, fewer barriers per path); parity prefers two slots per thread.
+//  * SAH-BVH / large scenes: 256 x 512 x 3 (r01 sweep), the media build 256 x 768 x 2 (128 registers).
+__host__ __device__ constexpr int wave_threads(bool small, bool trace) { return (small && !trace) ? TPT_SMALL_THREADS : TPT_WAVE_THREADS; }
+__host__ __device__ constexpr int wave_slots(bool par, bool small, bool trace) {
+  return trace ? TPT_TRACE_SLOTS : (small ? (par ? TPT_SMALL_SLOTS_PAR : TPT_SMALL_SLOTS_FAST) : TPT_WAVE_SLOTS);
+}
+__host__ __device__ constexpr int wave_min_blocks(bool par, bool small, bool trace, bool lean) {
+  return trace ? TPT_TRACE_MIN_BLOCKS : (small ? TPT_SMALL_MIN_BLOCKS : (lean ? TPT_WAVE_LEAN_MIN_BLOCKS : (par ? TPT_WAVE_PAR_MIN_BLOCKS : TPT_WAVE_MIN_BLOCKS)));
+}
 
 struct IntersectArgs {
   SceneLayout scene;
@@ -107,6 +136,9 @@ cudaError_t wave_occupancy_parity(const RenderArgs &A, bool small, bool smem, bo
 cudaError_t wave_occupancy_fast(const RenderArgs &A, bool small, bool smem, bool media, bool trace, int *blocks_per_sm);
 cudaError_t launch_wave_parity(const RenderArgs &A, bool small, bool smem, bool media, bool trace, int blocks, cudaStream_t st);
 cudaError_t launch_wave_fast(const RenderArgs &A, bool small, bool smem, bool media, bool trace, int blocks, cudaStream_t st);
+// threads per CTA of the variant the arguments select (statistics)
+int wave_threads_parity(const RenderArgs &A, bool small, bool smem, bool media, bool trace);
+int wave_threads_fast(const RenderArgs &A, bool small, bool smem, bool media, bool trace);
 cudaError_t launch_texture_probe_parity(const TextureProbeArgs &A, cudaStream_t st);
 cudaError_t launch_texture_probe_fast(const TextureProbeArgs &A, cudaStream_t st);
 // iters x 64 FMAs per thread, 256 threads per block (tpt_debug_fp32_peak)
