@@ -281,7 +281,9 @@ def stock_reference_fit(c, budget_s=40.0):
     t1, w1 = run(s1)
     if t1 is None:
         return None
-    s2 = int(max(2, min(16, (budget_s - 2 * w1) / max(w1 * 0.5, 0.05))))  # second point sized to the budget
+    # second point sized to the budget: w1 is mostly the program's fixed cost (1.44 M string-keyed map inserts,
+    # 1200 threads, P3 output), so w1 / 4 per spp is a safe over-estimate of the slope
+    s2 = int(max(2, min(256, c["spp"], (budget_s - 2 * w1) / max(w1 * 0.25, 0.05))))
     t2, w2 = run(s2)
     if t2 is None:
         return None
@@ -380,9 +382,19 @@ def run_reference_arm(args, rank, world):
 
 
 # ------------------------------------------------------------------- multi-rank tile gather
+_OWNED_CACHE = {}
+
+
 def owned_pixel_index(torch, nx, ny, rank, world, device):
     """flat indices of the pixels whose 16x16 tile t satisfies t % world == rank (the static split
-    tpt_render_params.part_index / part_count describes), row-major"""
+    tpt_render_params.part_index / part_count describes), row-major; computed once per frame shape"""
+    key = (nx, ny, rank, world, str(device))
+    if key not in _OWNED_CACHE:
+        _OWNED_CACHE[key] = _owned_pixel_index(torch, nx, ny, rank, world, device)
+    return _OWNED_CACHE[key]
+
+
+def _owned_pixel_index(torch, nx, ny, rank, world, device):
     tx = (nx + TILE - 1) // TILE
     jj = torch.arange(ny, device=device).view(-1, 1)
     ii = torch.arange(nx, device=device).view(1, -1)
@@ -546,7 +558,8 @@ def run_ours(args, rank, local_rank, world):
             d2h = int(st2["d2h_bytes"]) if rank == 0 else 0
         step = max_over_ranks(statistics.mean(e2e_s))
         return {"seconds_per_step": step, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "checksum": loss,
-                "image_sha1": hashlib.sha1(rgb_host.numpy().tobytes()).hexdigest()[:16] if rank == 0 else None}
+                "image_sha1": hashlib.sha1(rgb_host.numpy().tobytes()).hexdigest()[:16] if rank == 0 else None,
+                "_rgb8": rgb_host.numpy().copy() if rank == 0 else None}
 
     mode = T.MODE_FAST if args.mode == "fast" else T.MODE_PARITY
     params = params_for(mode, args.bundle_cull)
@@ -630,12 +643,17 @@ def run_ours(args, rank, local_rank, world):
                     if i >= (0 if big else 2):
                         secs.append(time.perf_counter() - t0)
                 sha = hashlib.sha1(rgb_host.numpy().tobytes()).hexdigest()[:16]
+                # same Philox stream per (pixel, sample) on both paths; the two split the frame differently (N parts
+                # vs 8 N batches), so a pixel's samples are summed in differently sized sub-ranges: the fp32 sums
+                # agree to rounding, the 8-bit pictures to +-1 on a few pixels
+                diff = np.abs(rgb_host.numpy().astype(np.int16) - e2e["_rgb8"].astype(np.int16))
                 step = statistics.mean(secs)
                 inproc = {"value": NX * NY * NS / step / 1e6, "unit": "Mpaths/s", "seconds_per_step": step, "n_gpus": world,
                           "batches_per_gpu": [int(x) for x in last.get("multi_batches", [])][:world],
                           "busy_ms_per_gpu": [round(float(x), 3) for x in last.get("multi_busy_ms", [])][:world],
                           "gather_ms": last["resolve_ms"], "render_ms_slowest_gpu": last["render_ms"],
-                          "image_sha1": sha, "image_equals_torchrun_e2e": sha == e2e["image_sha1"],
+                          "image_sha1": sha, "rgb8_max_abs_diff_vs_torchrun_e2e": int(diff.max()),
+                          "rgb8_values_differing": int((diff > 0).sum()), "rgb8_values": int(diff.size),
                           "note": "tpt_render_multi from ONE process (rank 0; the other ranks wait at a gloo barrier): scene created on "
                                   "every GPU, 8 x N batches of interleaved tiles, 3/4 static + work stealing, GPU 0 reads the peers' "
                                   "partial frames over NVLink, one download; no NCCL on this path"}
@@ -739,7 +757,7 @@ def run_ours(args, rank, local_rank, world):
                                           "(fov / depth / build flags unstated)") if published_mpaths else None},
         "wall_seconds_per_step": main["wall_ms"] / args.steps / 1e3, "mrays_per_s": main["rays"] / (main["dev_ms"] * 1e-3) / 1e6,
         "rays_per_path": main["rays"] / main["paths"], "clocks": clocks, "gpu_launches": int(main["launches"]),
-        "e2e": {"value": e2e_value, "unit": "Mpaths/s", "h2d_bytes_per_step": e2e["h2d_bytes_per_step"],
+        "e2e": {"value": e2e_value, "unit": "Mpaths/s", "h2d_bytes_per_step": e2e["h2d_bytes_per_step"],  # noqa: E501
                 "d2h_bytes_per_step": e2e["d2h_bytes_per_step"], "seconds_per_step": e2e["seconds_per_step"],
                 "checksum": e2e["checksum"], "image_sha1": e2e["image_sha1"],
                 "gather": None if world == 1 else "NCCL gather of the tiles each rank owns (1/N of the frame per rank), one D2H on rank 0"},

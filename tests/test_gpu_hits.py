@@ -51,44 +51,50 @@ def test_parity_hits_vs_golden(T, gpu, scene):
     assert st["rel_uv"] <= 2e-6, st  # atan2f/asinf: glibc vs correctly-rounded, <= 1 ulp of [0,1]
 
 
+N_PRIMARY = {"cornell_box": 3000, "sphere_cornell_box": 1200, "random_scene": 3000, "random_scene_list": 800,
+             "two_perlin_spheres": 600, "light_spheres": 600, "earth": 600, "textured_lit": 800}
+# OBSERVED on B200 (profiles/r02_fast_mismatch.json, tools/gpu_mismatch.py): fast mode picks the reference's
+# closest object on EVERY well-posed ray of every scene -- 0 hit/miss and 0 object-id mismatches. The budget is
+# therefore 0, not a percentage. "Well-posed" excludes (a) the hand-made adversarial block (rays lying IN a
+# rectangle's plane, zero direction components that turn 0 * inf into NaN, exact corner hits: ties the reference
+# resolves by evaluation order) and (b) rays with a non-finite component (secondary rays spawned from a NaN hit
+# record of that block).
+FAST_ID_BUDGET = {scene: 0 for scene in common.HIT_SCENES}
+
+
+def well_posed(scene, rays):
+    n_adv = len(raygen.adversarial_rays(*raygen.SCENE_INFO[scene][:2]))
+    ok = np.isfinite(rays).all(axis=1)
+    ok[N_PRIMARY[scene]:N_PRIMARY[scene] + n_adv] = False
+    return ok
+
+
 @pytest.mark.parametrize("scene", common.HIT_SCENES)
 def test_fast_hits_vs_golden(T, gpu, scene):
-    """fast mode: fp32 + FMA + culled traversal. Same closest object except at ties / ulp-level
-    edge cases; records within 1e-3 relative of the reference's."""
+    """fast mode: fp32 + FMA + its own acceleration structures (uniform brute force / SAH BVH, slab-folded
+    boxes). Gate 1 asks for bit-exact hit/miss and closest-object ids: measured and asserted with budget 0 on
+    every well-posed ray; records within the stated tolerances of the reference's."""
     g = common.golden("hits_" + scene)
     rays, exp = g["rays"], g["hits"]
-    # fast mode does not promise the reference's behaviour on exact ties and degenerate rays (a
-    # ray lying IN a slab / rectangle plane, zero direction components that turn 0*inf into NaN):
-    # the hand-made adversarial block of the batch is checked for robustness only (no crash, a
-    # record for every ray), the id comparison runs on the camera / interior / secondary rays.
-    n_adv = len(raygen.adversarial_rays(*raygen.SCENE_INFO[scene][:2]))
-    n_primary = {"cornell_box": 3000, "sphere_cornell_box": 1200, "random_scene": 3000, "random_scene_list": 800,
-                 "two_perlin_spheres": 600, "light_spheres": 600, "earth": 600, "textured_lit": 800}[scene]
-    ok = np.ones(len(rays), bool)
-    ok[n_primary:n_primary + n_adv] = False
+    ok = well_posed(scene, rays)
     sc = T.Scene(common.host_scene(T, scene))
-    assert len(sc.intersect(rays, mode=T.MODE_FAST)) == len(rays)
+    assert len(sc.intersect(rays, mode=T.MODE_FAST)) == len(rays)  # degenerate rays: a record for every ray, no crash
     got = sc.intersect(rays[ok], mode=T.MODE_FAST)
     exp = exp[ok]
     st = compare_hits(got, exp)
-    n = int(ok.sum())
-    # sphere_cornell_box builds its walls from 1e5-radius spheres (src/utils.cc:267-271). A secondary
-    # ray that starts ON such a wall re-hits it at t ~ 0.02 or not at all depending on the last bits
-    # of sqrt(discriminant): the reference keeps that sqrt in double (src/sphere.cc:23), fast mode in
-    # fp32, so a few percent of those surface-start rays legitimately pick another wall. Parity mode
-    # (double sqrt) matches bit for bit -- see test_parity_hits_vs_golden.
-    budget = n // 30 if scene == "sphere_cornell_box" else max(2, n // 500)
-    assert st["hit_mismatch"] <= budget, st
-    assert st["prim_mismatch"] <= budget, st
+    print(f"\nfast-mode gate 1 [{scene}]: {int(ok.sum())} rays, hit/miss mismatches {st['hit_mismatch']}, "
+          f"object-id mismatches {st['prim_mismatch']}, max rel t error {st['rel_t']:.3g}")
+    assert st["hit_mismatch"] <= FAST_ID_BUDGET[scene], st
+    assert st["prim_mismatch"] <= FAST_ID_BUDGET[scene], st
     # hit points: within 1e-3 of the scene extent, except for a handful of ill-conditioned rays
-    # (self-intersection of a surface-start ray on a 1e5-radius sphere, grazing hits) where fp32
-    # with and without FMA legitimately disagree -- the reference's own answer is one of several
-    # equally valid ones there
+    # (grazing hits on the 1000-radius ground sphere: the fp32 discriminant is a catastrophic cancellation
+    # there and differs with and without FMA -- the reference's own answer is one of several equally
+    # valid ones)
     same = (got["hit"] == 1) & (exp["hit"] == 1) & (got["prim"] == exp["prim"])
     fin = same & np.isfinite(exp["p"]).all(axis=1) & np.isfinite(got["p"]).all(axis=1)
     dp = np.linalg.norm(got["p"][fin].astype(np.float64) - exp["p"][fin], axis=1)
     extent = raygen.SCENE_INFO[scene][0]
-    assert (dp > 1e-3 * extent).mean() < (2e-2 if scene == "sphere_cornell_box" else 2e-3), (scene, float(dp.max()))
+    assert (dp > 1e-3 * extent).mean() < 2e-3, (scene, float(dp.max()))
     assert np.percentile(dp, 99) < 1e-4 * extent
 
 

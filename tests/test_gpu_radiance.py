@@ -63,14 +63,26 @@ def test_media_scene_fast_mode_and_hit_batch(T, gpu):
     assert e.value.code == -4
 
 
+# OBSERVED on B200 (profiles/r02_fast_mismatch.json): share of pixels whose fast-mode sum differs from the
+# reference's (same injected stream) by more than 1e-4 relative -- paths where a one-ulp difference flips a
+# discrete decision (which side of an edge, reflect or refract) and the path continues elsewhere.
+#   cornell_A 4/2304 (0.17 %), cornell_B 4/1024 (0.39 %), textured_lit 7/1600 (0.44 %), light_spheres 19/1600 (1.19 %)
+# Budget: 0.5 % of the pixels and a mean within 0.1 %. light_spheres is the exception, by construction: its
+# ground is marble, 0.5 * (1 + sin(4 z + 10 turb(p))) (src/texture.cc:18-25); the reference evaluates the
+# fade polynomial through double pow, fast mode in fp32, and where the albedo goes to zero in the dark veins a
+# 1e-6 absolute difference in turb is more than 1e-4 RELATIVE in the pixel (17 of its 19 outliers are below 1e-3,
+# none reaches 1e-2; the image mean agrees to the last digit).
+FAST_OUTLIER_BUDGET = {"cornell_A": 0.005, "cornell_B": 0.005, "textured_lit": 0.005, "light_spheres": 0.015}
+
+
 @pytest.mark.parametrize("case", ["cornell_A", "cornell_B", "light_spheres", "textured_lit"])
 def test_fast_radiance_vs_golden(T, gpu, case):
     res, g, c = run_case(T, case, T.MODE_FAST)
     n_bad, n, worst = outliers(res.sum_rgb, g["sum_rgb"], c["ns"])
-    # same stream, fp32 arithmetic: the bulk of the pixels still agree to 1e-4; paths that flip a
-    # discrete decision show up as isolated outliers
-    assert n_bad <= 0.02 * n, f"{case}: {n_bad}/{n} outliers (worst {worst})"
-    assert abs(res.sum_rgb.mean() - g["sum_rgb"].mean()) <= 0.02 * max(g["sum_rgb"].mean(), 1e-6)
+    shift = abs(res.sum_rgb.mean() - g["sum_rgb"].mean()) / max(g["sum_rgb"].mean(), 1e-6)
+    print(f"\nfast-mode gate 2 [{case}]: {n_bad}/{n} pixels beyond {REL_TOL} ({100.0 * n_bad / n:.2f} %), mean shift {shift:.2e}")
+    assert n_bad <= FAST_OUTLIER_BUDGET[case] * n, f"{case}: {n_bad}/{n} outliers (worst {worst})"
+    assert shift <= 1e-3
 
 
 def test_slices_are_running_sums(T, gpu):

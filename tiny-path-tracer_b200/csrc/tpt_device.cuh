@@ -407,12 +407,12 @@ TPT_DEV V3 moving_center(float4 a, float4 b, float4 c, float time) {
   return c0 + f * (c1 - c0);
 }
 
-// EXACT (fast mode only): the reference's own root arithmetic -- sqrt and the division in double,
-// rounded once (src/sphere.cc:23,32) -- for the huge "wall" spheres (radius >= 500), where the last
-// bit of t decides whether a ray that starts ON the wall re-hits it at t ~ 0.001 and which of two
-// nearly coincident surfaces wins (r02: with fp32 roots 47 of 2474 surface-start rays of
-// sphere_cornell_box picked another wall than the reference). Ordinary spheres take the approximate
-// MUFU forms.
+// EXACT (fast mode only), for the huge "wall" / ground spheres (radius >= 500), where the last bit of
+// t decides whether a ray that starts ON the sphere re-hits it at t ~ 0.001 and which of two nearly
+// coincident surfaces wins: IEEE fp32 sqrt / divide, and from radius 1e4 up the reference's own root
+// arithmetic -- sqrt and the division in double, rounded once (src/sphere.cc:23,32; r02: with fp32
+// roots 47 of 2474 surface-start rays of sphere_cornell_box, whose walls are 1e5-radius spheres, picked
+// another wall than the reference). Ordinary spheres take the approximate MUFU forms.
 template <bool PAR, bool EXACT = true>
 TPT_DEV bool sphere_test(V3 center, float radius, const XRay &x, float tmin, float tmax, float &t) {
   // src/sphere.cc:15-41. The quadratic's coefficients and discriminant are evaluated with
@@ -426,7 +426,10 @@ TPT_DEV bool sphere_test(V3 center, float radius, const XRay &x, float tmin, flo
                       -__fmul_rn(radius, radius));
   float disc = __fadd_rn(__fmul_rn(b, b), -__fmul_rn(__fmul_rn(4.0f, a), c));
   if (disc > 0) {
-    if (PAR || (EXACT && TPT_EXACT_DOUBLE_ROOTS)) {
+    // FAST: double only for the truly gigantic spheres (1e5-radius "walls", src/utils.cc:267-271); a
+    // 1000-radius ground sphere is tested by every ray of its scene and matched the reference on every
+    // ray with IEEE fp32 roots already (r02: double roots there cost two_perlin_spheres 30 %)
+    if (PAR || (EXACT && TPT_EXACT_DOUBLE_ROOTS && radius >= 1.0e4f)) {
       // `sqrt` (unqualified) and the division are evaluated in double, rounded once to float
       double sq = sqrt((double)disc);
       float temp = (float)((-(double)b - sq) / (double)(2 * a));

@@ -3,8 +3,7 @@
 
 gate 1: fast-mode tpt_intersect_batch against the golden hit records the reference produced
         (tests/golden/hits_*.npz): hit/miss and closest-object mismatches on the non-adversarial
-        rays, each mismatching ray saved with both records for classification
-        (tools/classify_mismatch.py, run where oracle/_ref is available).
+        rays, each mismatching ray saved with both records so that it can be classified by hand.
 gate 2: fast-mode render under the injected stream against the golden radiance: outlier pixels
         beyond 1e-4 relative, mean shift.
 Writes gpurun_out/r02_fast_mismatch.json and gpurun_out/r02_fast_mismatch_rays.npz."""
@@ -32,7 +31,8 @@ def main():
         g = common.golden("hits_" + scene)
         rays, exp = g["rays"], g["hits"]
         n_adv = len(raygen.adversarial_rays(*raygen.SCENE_INFO[scene][:2]))
-        ok = np.ones(len(rays), bool)
+        ok = np.isfinite(rays).all(axis=1)  # secondary rays spawned from a NaN hit record of the adversarial block
+        n_nonfinite = int((~ok).sum())
         ok[N_PRIMARY[scene]:N_PRIMARY[scene] + n_adv] = False
         sc = T.Scene(common.host_scene(T, scene))
         got = sc.intersect(rays, mode=T.MODE_FAST)
@@ -45,7 +45,7 @@ def main():
         rel_t = np.abs(got["t"][same].astype(np.float64) - exp["t"][same]) / np.maximum(np.abs(exp["t"][same]), 1e-6)
         dt_tie = np.abs(got["t"][prim_mis].astype(np.float64) - exp["t"][prim_mis]) / np.maximum(np.abs(exp["t"][prim_mis]), 1e-6)
         out["gate1"][scene] = {
-            "rays": int(ok.sum()), "adversarial_rays": int(n_adv),
+            "rays": int(ok.sum()), "adversarial_rays": int(n_adv), "non_finite_rays": n_nonfinite,
             "hit_mismatch": int((hit_mis & ok).sum()), "prim_mismatch": int((prim_mis & ok).sum()),
             "hit_mismatch_adversarial": int((hit_mis & ~ok).sum()), "prim_mismatch_adversarial": int((prim_mis & ~ok).sum()),
             "parity_hit_mismatch_all": int((par["hit"] != exp["hit"]).sum()),
