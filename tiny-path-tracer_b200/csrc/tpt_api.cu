@@ -41,6 +41,9 @@ int cuda_fail(cudaError_t e, const char *what) {
   } while (0)
 
 #define TPT_MAX_BATCHES 256 // work-stealing batches of one multi-GPU render
+#ifndef TPT_FBVH_LEAF
+#define TPT_FBVH_LEAF 2 // primitives per leaf of the SAH BVH (<= 8: the leaf code keeps count - 1 in three bits)
+#endif
 
 struct ResolveArgs {
   const float *acc; // [n_ranges][npix][3]
@@ -135,7 +138,7 @@ struct tpt_scene {
   std::vector<cudaArray_t> arrays;
   std::vector<cudaTextureObject_t> textures;
   bool has_lights = false;
-  bool constant_textures_only = false; // no checker / Perlin / image texture anywhere: lean kernel builds apply
+  int tex_mask = TPT_TEXF_ALL; // TPT_TEXF_* features present among the scene's textures (0: all constant -> lean kernel builds)
   int n_mediums = 0;
   bool fbvh_has_moving = false; // the fast BVH boxes moving spheres over [fbvh_t0, fbvh_t1] only
   float fbvh_t0 = 0, fbvh_t1 = 0;
@@ -305,7 +308,7 @@ int32_t build_fbvh_rec(std::vector<BuildItem> &items, int begin, int end, FastBv
 // returns the child reference: >= 0 inner node index, < 0 ~((first << 3) | (count - 1))
 int32_t make_child(std::vector<BuildItem> &items, int begin, int end, FastBvh &out, Box3 &box) {
   int n = end - begin;
-  if (n <= 2) {
+  if (n <= TPT_FBVH_LEAF) {
     box.reset();
     int first = (int)out.leaf_prims.size();
     for (int i = begin; i < end; i++) {
@@ -388,6 +391,55 @@ int32_t build_fbvh_rec(std::vector<BuildItem> &items, int begin, int end, FastBv
   std::memcpy(&n[12], &c0, 4);
   std::memcpy(&n[13], &c1, 4);
   return me;
+}
+
+// BVH2 -> BVH4: every node keeps absorbing its largest inner child's two children until it has four
+// (surface-area heuristic for which child to open). Half the levels of the binary tree: half the
+// dependent node fetches per ray and, in a warp whose lanes walk different sub-trees, half the loop
+// trips over which their counts can differ. Node = 8 float4, structure-of-arrays over the four
+// children: lo.x[4] lo.y[4] lo.z[4] hi.x[4] hi.y[4] hi.z[4] child[4] unused[4]; a child reference is
+// >= 0 (inner node), < 0 (leaf code as in the binary tree) or TPT_FBVH_EMPTY.
+void collapse_to_bvh4(const FastBvh &b2, std::vector<float> &out, int &max_depth) {
+  struct Kid { Box3 box; int32_t ref; };
+  auto kids_of = [&b2](int32_t node, Kid k[2]) {
+    const float *n = &b2.nodes[(size_t)node * 16];
+    for (int c = 0; c < 2; c++) {
+      for (int a = 0; a < 3; a++) { k[c].box.lo[a] = n[6 * c + a]; k[c].box.hi[a] = n[6 * c + 3 + a]; }
+      std::memcpy(&k[c].ref, &n[12 + c], 4);
+    }
+  };
+  max_depth = 0;
+  std::function<int32_t(int32_t, int)> emit = [&](int32_t node2, int depth) -> int32_t {
+    max_depth = std::max(max_depth, depth);
+    std::vector<Kid> kids(2);
+    kids_of(node2, kids.data());
+    while (kids.size() < 4) {
+      int open = -1;
+      float best = -1.f;
+      for (size_t i = 0; i < kids.size(); i++)
+        if (kids[i].ref >= 0 && kids[i].box.area() > best) { best = kids[i].box.area(); open = (int)i; }
+      if (open < 0) break;
+      Kid two[2];
+      kids_of(kids[open].ref, two);
+      kids[open] = two[0];
+      kids.push_back(two[1]);
+    }
+    const int me = (int)(out.size() / 32);
+    out.resize(out.size() + 32, 0.f);
+    std::vector<int32_t> refs(4, TPT_FBVH_EMPTY);
+    for (size_t i = 0; i < kids.size(); i++) refs[i] = kids[i].ref >= 0 ? emit(kids[i].ref, depth + 1) : kids[i].ref;
+    float *n = &out[(size_t)me * 32];
+    for (int i = 0; i < 4; i++) {
+      const bool used = i < (int)kids.size();
+      for (int a = 0; a < 3; a++) {
+        n[4 * a + i] = used ? kids[i].box.lo[a] : FLT_MAX;       // an empty slot: a point at +FLT_MAX, never hit
+        n[12 + 4 * a + i] = used ? kids[i].box.hi[a] : FLT_MAX;
+      }
+      std::memcpy(&n[24 + i], &refs[i], 4);
+    }
+    return me;
+  };
+  if (!b2.nodes.empty()) emit(0, 1);
 }
 
 // surface primitives reachable from the root tree (media and their boundaries excluded)
@@ -829,7 +881,7 @@ int make_plan(tpt_scene *s, const tpt_camera *cam, const tpt_render_params *p, P
   // the test altogether.
   A.cull = 0;
   A.camera_tries = 1;
-  A.lean = s->constant_textures_only ? 1 : 0;
+  A.tex_mask = s->tex_mask;
   const bool want_cull = p->reserved[2] == 0 && s->background == TPT_BG_BLACK;
   if (s->root_box_ok &&
       (!s->any_moving || (std::min(cam->time0, cam->time1) >= s->moving_t0 && std::max(cam->time0, cam->time1) <= s->moving_t1))) {
@@ -924,7 +976,7 @@ int make_plan(tpt_scene *s, const tpt_camera *cam, const tpt_render_params *p, P
       // resident path slots per SM: 2 CTAs x 1152 (fast) / 768 (parity) on small scenes, 3 x 512 otherwise
       const bool small_scene = plan.parity ? s->flat.enabled != 0 : s->small.enabled != 0;
       const double slots = (double)s->prop.multiProcessorCount *
-                           (small_scene ? TPT_SMALL_MIN_BLOCKS * (plan.parity ? TPT_SMALL_SLOTS_PAR : TPT_SMALL_SLOTS_FAST) : 1536.0);
+                           (small_scene ? TPT_SMALL_MIN_BLOCKS * wave_slots(plan.parity, true, false, s->tex_mask == 0) : 1536.0);
       const double local_pixels = (double)p->nx * p->ny / p->part_count;
       long long want = (long long)std::ceil(32.0 * slots / std::max(local_pixels, 1.0) / slices);
       long long by_samples = std::max(1, per_slice / 8);                       // >= 8 samples per bin
@@ -1419,6 +1471,36 @@ int tpt_scene_create(const tpt_scene_desc *d, int device, tpt_scene **out) {
   append(blob, d->nodes, d->n_nodes);
   L.off_prims = words();
   append(blob, d->prims, d->n_prims);
+  {
+    // FAST mode reads a world-space normal (rects) / centre (spheres) from the last four words of a
+    // primitive's record (fill_hit): the object-space value carried out of its transform chain,
+    // innermost wrapper first (src/rect_box.cc:185-189, headers/rect_box.h:91). The caller's description
+    // is not touched; moving spheres and media keep their own data there.
+    for (int i = 0; i < d->n_prims; i++) {
+      const tpt_prim &p = d->prims[i];
+      if (p.kind == TPT_PRIM_MOVING_SPHERE || p.kind == TPT_PRIM_MEDIUM) continue;
+      const bool sph = p.kind == TPT_PRIM_SPHERE;
+      double v[3] = {0, 0, 0};
+      if (sph) { v[0] = p.p[0]; v[1] = p.p[1]; v[2] = p.p[2]; }
+      else v[p.kind == TPT_PRIM_XY_RECT ? 2 : (p.kind == TPT_PRIM_XZ_RECT ? 1 : 0)] = 1.0;
+      const tpt_chain &ch = d->chains[p.chain];
+      for (int k = ch.n_ops - 1; k >= 0; k--) {
+        const tpt_xform_op &op = d->xform_ops[ch.first_op + k];
+        if (op.kind == TPT_XF_TRANSLATE) {
+          if (sph) { v[0] += op.a; v[1] += op.b; v[2] += op.c; }
+        } else {
+          const double x = op.b * v[0] + op.a * v[2], z = -op.a * v[0] + op.b * v[2];
+          v[0] = x;
+          v[2] = z;
+        }
+      }
+      const float sign = (p.flags & TPT_PRIM_FLIP) ? -1.0f : 1.0f;
+      float w[4] = {(float)v[0], (float)v[1], (float)v[2], sign};
+      if (!sph)
+        for (int c = 0; c < 3; c++) w[c] *= sign;
+      std::memcpy(blob.data() + (size_t)L.off_prims * 16 + (size_t)i * sizeof(tpt_prim) + 16 + 8 * sizeof(float), w, sizeof(w));
+    }
+  }
   L.off_chains = words();
   {
     std::vector<int32_t> padded((size_t)d->n_chains * 4, 0);
@@ -1461,7 +1543,17 @@ int tpt_scene_create(const tpt_scene_desc *d, int device, tpt_scene **out) {
   FastBvh fb;
   if (count_root_surface_prims(d, n_root) > TPT_SMALL_MAX_PRIMS) build_fast_bvh(d, n_root, fb);
   L.off_fbvh = words();
-  append(blob, fb.nodes.data(), fb.nodes.size());
+  int fbvh_depth = 0;
+  std::vector<float> wide;
+  if (TPT_FBVH_WIDE) collapse_to_bvh4(fb, wide, fbvh_depth);
+  // the traversal stack holds at most 3 deferred children per level (1 in the binary form): a tree too
+  // deep for it (a degenerate, sliver-by-sliver split) falls back to the reference's own tree
+  if (TPT_FBVH_WIDE && 3 * fbvh_depth + 4 > TPT_FBVH_STACK) {
+    fb = FastBvh();
+    wide.clear();
+  }
+  if (TPT_FBVH_WIDE) append(blob, wide.data(), wide.size());
+  else append(blob, fb.nodes.data(), fb.nodes.size());
   L.off_fleaf = words();
   {
     // leaf records in leaf order, 3 float4 each (read by closest_hit_fbvh):
@@ -1485,7 +1577,7 @@ int tpt_scene_create(const tpt_scene_desc *d, int device, tpt_scene **out) {
     }
     append(blob, rec.data(), rec.size());
   }
-  L.n_fbvh = (int)(fb.nodes.size() / 16);
+  L.n_fbvh = TPT_FBVH_WIDE ? (int)(wide.size() / 32) : (int)(fb.nodes.size() / 16);
   {
     // world bounds = the root node's box, when the root sits outside any transform wrapper
     const tpt_node &root = d->nodes[0];
@@ -1515,11 +1607,13 @@ int tpt_scene_create(const tpt_scene_desc *d, int device, tpt_scene **out) {
   L.n_lights = d->n_lights;
   L.background = d->background;
   s->has_lights = d->n_lights > 0;
-  s->constant_textures_only = true; // TPT_NO_LEAN=1 in the environment keeps the full kernels (A/B measurements)
-  for (int i = 0; i < d->n_textures; i++)
-    if (d->textures[i].kind != TPT_TEX_CONSTANT) s->constant_textures_only = false;
+  s->tex_mask = 0; // TPT_NO_LEAN=1 in the environment keeps the full kernels (A/B measurements)
+  for (int i = 0; i < d->n_textures; i++) {
+    if (d->textures[i].kind == TPT_TEX_IMAGE) s->tex_mask |= TPT_TEXF_IMAGE;
+    if (d->textures[i].kind == TPT_TEX_CHECKER || d->textures[i].kind == TPT_TEX_PERLIN) s->tex_mask |= TPT_TEXF_PROCEDURAL;
+  }
   if (const char *e = std::getenv("TPT_NO_LEAN"))
-    if (e[0] == '1') s->constant_textures_only = false;
+    if (e[0] == '1') s->tex_mask = TPT_TEXF_ALL;
   s->blob_bytes = blob.size();
   CK(cudaMallocAsync((void **)&s->d_blob, blob.size(), s->stream));
   CK(cudaMemcpyAsync(s->d_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice, s->stream));

@@ -25,6 +25,9 @@ namespace tptd {
 #define TPT_MAX_BOUNDARY_FRAMES 8 // nesting inside a constant_medium boundary (sphere / box / small list)
 #define TPT_MAX_IMAGES 8
 #define TPT_MAX_RANGES 256
+#define TPT_TEXF_IMAGE 1      // texture feature bits of a kernel build (texture_value / fill_hit)
+#define TPT_TEXF_PROCEDURAL 2
+#define TPT_TEXF_ALL 3
 #ifndef TPT_EXACT_DOUBLE_ROOTS
 #define TPT_EXACT_DOUBLE_ROOTS 1 // FAST mode, huge "wall" spheres: roots in double like the reference (0: IEEE fp32)
 #endif
@@ -961,7 +964,14 @@ TPT_DEV bool sphere_test_quick(V3 center, float radius, const XRay &x, float tmi
 // The state is a struct so that a kernel can interleave traversal steps of many rays with other
 // work (render_mega_bvh_kernel postpones shading until enough lanes of the warp wait for it).
 #define TPT_FBVH_DONE 0x7fffffff
-#define TPT_FBVH_STACK 32
+#define TPT_FBVH_EMPTY 0x7ffffffe // BVH4: unused child slot
+#ifndef TPT_FBVH_WIDE
+#define TPT_FBVH_WIDE 0 // 1: four-wide nodes (collapse_to_bvh4 in tpt_api.cu), 0: the binary tree. Measured on B200 (profiles/r02_tuning_sweeps.txt): the per-lane BVH4 walk is 14 % SLOWER than the binary one on random_scene (1 798 vs 2 088 Mpaths/s; 1 888 with unsorted pushes) and 11 % on oneweek_final -- 28 live box words per node spill at 80 registers, and at 128 registers / 2 CTAs it is slower still (1 599)
+#endif
+#ifndef TPT_FBVH_SORT
+#define TPT_FBVH_SORT 1 // BVH4: deferred children pushed far-to-near (0: in slot order)
+#endif
+#define TPT_FBVH_STACK (TPT_FBVH_WIDE ? 48 : 32)
 struct FbvhTrav {
   float ix, iy, iz, ox, oy, oz; // t = p * inv + (-o * inv)
   float best;
@@ -980,6 +990,62 @@ struct FbvhTrav {
   // descend to the next leaf (or run out of nodes), then test that leaf's primitives
   TPT_DEV void step(const SceneView &S, const Ray &r, float tmin, int *stack) {
     const float4 *N = S.blob + S.L->off_fbvh;
+#if TPT_FBVH_WIDE
+    while ((unsigned)node < (unsigned)TPT_FBVH_EMPTY) {
+      const float4 *M = N + 8 * node;
+      const float4 lx = M[0], ly = M[1], lz = M[2], hx = M[3], hy = M[4], hz = M[5];
+      const int4 ch = *reinterpret_cast<const int4 *>(M + 6);
+      // entry distance of child k, or "miss"; packed with the slot number in the two low mantissa bits
+      // so that unsigned order = distance order (entry distances are >= tmin > 0)
+      unsigned key[4];
+      const float clx[4] = {lx.x, lx.y, lx.z, lx.w}, cly[4] = {ly.x, ly.y, ly.z, ly.w}, clz[4] = {lz.x, lz.y, lz.z, lz.w};
+      const float chx[4] = {hx.x, hx.y, hx.z, hx.w}, chy[4] = {hy.x, hy.y, hy.z, hy.w}, chz[4] = {hz.x, hz.y, hz.z, hz.w};
+      const int cref[4] = {ch.x, ch.y, ch.z, ch.w};
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const float t0x = fmaf(clx[k], ix, ox), t1x = fmaf(chx[k], ix, ox);
+        const float t0y = fmaf(cly[k], iy, oy), t1y = fmaf(chy[k], iy, oy);
+        const float t0z = fmaf(clz[k], iz, oz), t1z = fmaf(chz[k], iz, oz);
+        const float nr = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), tmin));
+        const float fr = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), best));
+        const bool hit = (nr <= fr) & (cref[k] != TPT_FBVH_EMPTY);
+        key[k] = hit ? ((__float_as_uint(nr) & ~3u) | (unsigned)k) : 0xffffffffu;
+      }
+#if TPT_FBVH_SORT
+#define TPT_CE(a, b) { const unsigned lo_ = min(key[a], key[b]), hi_ = max(key[a], key[b]); key[a] = lo_; key[b] = hi_; }
+      TPT_CE(0, 1) TPT_CE(2, 3) TPT_CE(0, 2) TPT_CE(1, 3) TPT_CE(1, 2)
+#undef TPT_CE
+      if (key[0] == 0xffffffffu) {
+        node = sp > 0 ? stack[--sp] : TPT_FBVH_DONE;
+        continue;
+      }
+      // farthest first, so that the nearest deferred child is popped first
+#pragma unroll
+      for (int k = 3; k >= 1; k--)
+        if (key[k] != 0xffffffffu) {
+          const unsigned slot = key[k] & 3u;
+          stack[sp++] = slot == 0 ? cref[0] : (slot == 1 ? cref[1] : (slot == 2 ? cref[2] : cref[3]));
+        }
+      {
+        const unsigned slot = key[0] & 3u;
+        node = slot == 0 ? cref[0] : (slot == 1 ? cref[1] : (slot == 2 ? cref[2] : cref[3]));
+      }
+#else
+      const unsigned nearest = min(min(key[0], key[1]), min(key[2], key[3]));
+      if (nearest == 0xffffffffu) {
+        node = sp > 0 ? stack[--sp] : TPT_FBVH_DONE;
+        continue;
+      }
+#pragma unroll
+      for (int k = 0; k < 4; k++)
+        if (key[k] != 0xffffffffu && key[k] != nearest) stack[sp++] = cref[k];
+      {
+        const unsigned slot = nearest & 3u;
+        node = slot == 0 ? cref[0] : (slot == 1 ? cref[1] : (slot == 2 ? cref[2] : cref[3]));
+      }
+#endif
+    }
+#else
     while ((unsigned)node < (unsigned)TPT_FBVH_DONE) {
       const float4 a = N[4 * node], b = N[4 * node + 1], c = N[4 * node + 2], d = N[4 * node + 3];
       // child 0: lo = (a.x,a.y,a.z) hi = (a.w,b.x,b.y) ; child 1: lo = (b.z,b.w,c.x) hi = (c.y,c.z,c.w)
@@ -1003,6 +1069,7 @@ struct FbvhTrav {
       else if (h1) node = i1;
       else node = sp > 0 ? stack[--sp] : TPT_FBVH_DONE;
     }
+#endif
     if (node < 0) {
       // leaf: ~node = first << 3 | (count - 1); records of 3 float4 (tpt_api.cu, off_fleaf)
       const int code = ~node, count = (code & 7) + 1;
@@ -1081,19 +1148,33 @@ template <bool PAR> TPT_DEV void get_uv_map(V3 p, float &u, float &v) {
 
 // LEAN (FAST kernels of small scenes whose textures are all constant_texture, e.g. the Cornell box):
 // nobody reads (u, v), so the atan2f / asinf sequence is not even compiled in
-template <bool PAR, bool LEAN = false>
+template <bool PAR, int TEX = TPT_TEXF_ALL>
 TPT_DEV void fill_hit(const SceneView &S, const Ray &r, int prim, float t, bool want_uv, HitRec &h) {
   const float4 *P = S.blob + S.L->off_prims + 4 * prim;
   float4 hd = P[0], a = P[1];
   int kind = __float_as_int(hd.x);
   int chain = __float_as_int(hd.z);
   int flags = __float_as_int(hd.w);
-  XRay x;
-  x.chain = -1;
-  to_chain<PAR>(S, r, chain, x);
   h.t = t;
   h.prim = prim;
   h.mat = __float_as_int(hd.y);
+  if (!PAR && !want_uv && kind != TPT_PRIM_MOVING_SPHERE) {
+    // FAST, nobody reads (u, v): t is the same in every space, so the hit point is taken on the WORLD ray
+    // and the normal from what tpt_scene_create stored in the record's last word (rects: the face normal
+    // carried back to world space, flip included; spheres: the world-space centre, w = +-1 for the flip).
+    // No trip into the primitive's transform chain and back (r01 capture: to_chain / from_chain ran at 8-9
+    // of 32 lanes in the shade stage, 4.9 % of the kernel's warp instructions).
+    const float4 w = P[3];
+    h.p = r.o + t * r.d;
+    h.u = 0.f;
+    h.v = 0.f;
+    if (kind == TPT_PRIM_SPHERE) h.n = (h.p - mk(w.x, w.y, w.z)) * (w.w / a.w);
+    else h.n = mk(w.x, w.y, w.z);
+    return;
+  }
+  XRay x;
+  x.chain = -1;
+  to_chain<PAR>(S, r, chain, x);
   h.p = x.o + t * x.d; // ray::point_at_parameter, headers/ray.h:13
   h.u = 0.f;
   h.v = 0.f;
@@ -1102,7 +1183,7 @@ TPT_DEV void fill_hit(const SceneView &S, const Ray &r, int prim, float t, bool 
     V3 cn = c;
     if (kind == TPT_PRIM_MOVING_SPHERE) cn = moving_center(a, P[2], P[3], r.time);
     h.n = (h.p - cn) / a.w;                                 // src/sphere.cc:28,59
-    if (!LEAN && want_uv) get_uv_map<PAR>((h.p - c) / a.w, h.u, h.v); // src/sphere.cc:27,60 (center0_)
+    if ((TEX & TPT_TEXF_IMAGE) && want_uv) get_uv_map<PAR>((h.p - c) / a.w, h.u, h.v); // src/sphere.cc:27,60 (center0_)
   } else {
     float k = P[2].x;
     (void)k;
@@ -1189,14 +1270,16 @@ template <bool PAR> TPT_DEV float perlin_turb(const SceneView &S, V3 p) {
   return fabsf(accum);
 }
 
-// LEAN: the scene's textures are all constant_texture (checked at upload): the checker / Perlin /
-// image code -- a third of the kernel's instructions, never executed on such a scene -- is left out.
+// TEX = the texture features of the scene (checked at upload): TPT_TEXF_IMAGE (image textures: uv of
+// sphere hits + texel fetch), TPT_TEXF_PROCEDURAL (checker, Perlin marble). A kernel build carries only
+// the code of the features its scene has; TEX == 0 (every texture a constant_texture, e.g. the Cornell
+// box) leaves out a third of the kernel's instructions, never executed on such a scene.
 // The hot loop of the render kernels is about as large as the SM's 32 KB instruction cache (ncu on
 // the Cornell frame: 92.8 % hit rate and the GPC's instruction fetch at 79 % of its peak with
 // everything compiled in; 97.5 % and 43 % without the dead code), so what a scene cannot reach is
 // kept out of its kernel.
-template <bool PAR, bool LEAN = false> TPT_DEV V3 texture_value(const SceneView &S, int tex, float u, float v, V3 p) {
-  if (LEAN) {
+template <bool PAR, int TEX = TPT_TEXF_ALL> TPT_DEV V3 texture_value(const SceneView &S, int tex, float u, float v, V3 p) {
+  if (TEX == 0) {
     const float4 t0 = S.blob[S.L->off_texs + 2 * tex];
     return mk(t0.y, t0.z, t0.w);
   }
@@ -1204,28 +1287,31 @@ template <bool PAR, bool LEAN = false> TPT_DEV V3 texture_value(const SceneView 
     float4 t0 = S.blob[S.L->off_texs + 2 * tex], t1 = S.blob[S.L->off_texs + 2 * tex + 1];
     int kind = __float_as_int(t0.x);
     if (kind == TPT_TEX_CONSTANT) return mk(t0.y, t0.z, t0.w);
-    if (kind == TPT_TEX_CHECKER) { // src/texture.cc:4-16
+    if ((TEX & TPT_TEXF_PROCEDURAL) && kind == TPT_TEX_CHECKER) { // src/texture.cc:4-16
       float s = round_sin<PAR>(10 * p.x) * round_sin<PAR>(10 * p.y) * round_sin<PAR>(10 * p.z);
       tex = (s < 0.0f) ? __float_as_int(t1.x) : __float_as_int(t1.y);
       continue;
     }
-    if (kind == TPT_TEX_PERLIN) { // src/texture.cc:18-25
+    if ((TEX & TPT_TEXF_PROCEDURAL) && kind == TPT_TEX_PERLIN) { // src/texture.cc:18-25
       float scale = t1.z;
       float s = round_sin<PAR>(scale * p.z + 10 * perlin_turb<PAR>(S, p));
       float g = 0.5f * (1 + s);
       return mk(g, g, g);
     }
-    // TPT_TEX_IMAGE: src/texture.cc:27-42, nearest texel, clamp, /255.0f
-    int img = __float_as_int(t1.w);
-    int W = S.L->image_w[img], H = S.L->image_h[img];
-    int i = (int)(u * W);
-    int j = (int)((1 - v) * H);
-    if (i < 0) i = 0;
-    if (i > W - 1) i = W - 1;
-    if (j > H - 1) j = H - 1;
-    if (j < 0) j = 0;
-    uchar4 c = tex2D<uchar4>(S.L->images[img], (float)i, (float)j);
-    return mk((int)c.x / 255.0f, (int)c.y / 255.0f, (int)c.z / 255.0f);
+    if (TEX & TPT_TEXF_IMAGE) {
+      // TPT_TEX_IMAGE: src/texture.cc:27-42, nearest texel, clamp, /255.0f
+      int img = __float_as_int(t1.w);
+      int W = S.L->image_w[img], H = S.L->image_h[img];
+      int i = (int)(u * W);
+      int j = (int)((1 - v) * H);
+      if (i < 0) i = 0;
+      if (i > W - 1) i = W - 1;
+      if (j > H - 1) j = H - 1;
+      if (j < 0) j = 0;
+      uchar4 c = tex2D<uchar4>(S.L->images[img], (float)i, (float)j);
+      return mk((int)c.x / 255.0f, (int)c.y / 255.0f, (int)c.z / 255.0f);
+    }
+    break; // a texture kind this build was not compiled for: tpt_scene_create never selects it for such a scene
   }
   return mk(0, 0, 0);
 }
@@ -1529,6 +1615,27 @@ template <bool PAR> TPT_DEV V3 background_radiance(const SceneView &S, const Ray
   return T * sky;
 }
 
+// FAST mode without a usable SAH BVH (a shutter interval outside the one the moving spheres' boxes
+// were built for, or a tree the builder gave up on): the culled walk over the reference's own tree.
+// Rare, and several KB of code: kept out of line so that the SAH-BVH kernels do not carry it in
+// their hot loop's instruction-cache lines.
+static __device__ __noinline__ float2 closest_hit_reftree_slow(const float4 *blob, const SceneLayout *L, float ox, float oy, float oz,
+                                                               float dx, float dy, float dz, float time, float tmin, float tmax) {
+  SceneView S;
+  S.blob = blob;
+  S.L = L;
+  S.small = nullptr;
+  S.flat = nullptr;
+  Ray r;
+  r.o = mk(ox, oy, oz);
+  r.d = mk(dx, dy, dz);
+  r.time = time;
+  float t = tmax;
+  int prim = -1;
+  walk_range<false, false>(S, r, 0, L->n_nodes, tmin, tmax, t, prim, nullptr);
+  return make_float2(t, __int_as_float(prim));
+}
+
 // extend(): world->hit plus every outcome that ends the path without a scatter() call
 // (src/utils.cc:61-66,82-86). Returns TPT_EXT_DONE with the sample's radiance, or the kind of the
 // scattering material (LAMBERTIAN / METAL / DIELECTRIC) with (prim, t) of the hit.
@@ -1537,7 +1644,7 @@ template <bool PAR> TPT_DEV V3 background_radiance(const SceneView &S, const Ray
 // carry the stream through world->hit (taking the Rng's address costs registers everywhere else).
 // Everything extend() does once the closest surface hit (any_hit, t, prim) is known: the media
 // pass of FAST mode, the miss / lamp / absorber / depth-limit endings, else the material kind.
-template <bool PAR, bool MEDIA, bool LEAN = false>
+template <bool PAR, bool MEDIA, int TEX = TPT_TEXF_ALL>
 TPT_DEV int extend_finish(const SceneView &S, const PathState &ps, int max_depth, float t_min, bool any_hit, float &t,
                           int &prim, V3 &radiance, Rng &g, uint32_t &ndraw_out) {
   if (!PAR && MEDIA) {
@@ -1562,15 +1669,15 @@ TPT_DEV int extend_finish(const SceneView &S, const PathState &ps, int max_depth
     // src/material.cc:79-86: one-sided; base scatter() is false -> return emitted
     const int mtex = __float_as_int(m0.y);
     HitRec h;
-    fill_hit<PAR, LEAN>(S, ps.ray, prim, t, !LEAN && texture_needs_uv(S, mtex), h);
-    if (dot(h.n, ps.ray.d) < 0) radiance = ps.T * texture_value<PAR, LEAN>(S, mtex, h.u, h.v, h.p);
+    fill_hit<PAR, TEX>(S, ps.ray, prim, t, (TEX & TPT_TEXF_IMAGE) && texture_needs_uv(S, mtex), h);
+    if (dot(h.n, ps.ray.d) < 0) radiance = ps.T * texture_value<PAR, TEX>(S, mtex, h.u, h.v, h.p);
     return TPT_EXT_DONE;
   }
   if (mkind == TPT_MAT_ABSORBER || mkind == TPT_MAT_ISOTROPIC || ps.depth >= max_depth) return TPT_EXT_DONE; // emitted == 0
   return mkind;
 }
 
-template <bool PAR, bool SMALL, bool MEDIA, bool LEAN = false>
+template <bool PAR, bool SMALL, bool MEDIA, int TEX = TPT_TEXF_ALL>
 TPT_DEV int extend(const SceneView &S, const PathState &ps, int max_depth, float t_min, float &t, int &prim,
                    V3 &radiance, Rng &g, uint32_t &ndraw_out) {
   // scenes with participating media draw inside world->hit: the stage's stream starts here
@@ -1586,14 +1693,20 @@ TPT_DEV int extend(const SceneView &S, const PathState &ps, int max_depth, float
   } else {
     if (SMALL) any_hit = closest_hit_uniform(S, ps.ray, t_min, FLT_MAX, t, prim);
     else if (S.L->n_fbvh > 0 && S.L->fbvh_time_ok) any_hit = closest_hit_fbvh(S, ps.ray, t_min, FLT_MAX, t, prim);
-    else any_hit = walk_range<false, false>(S, ps.ray, 0, S.L->n_nodes, t_min, FLT_MAX, t, prim, nullptr);
+    else {
+      const float2 w = closest_hit_reftree_slow(S.blob, S.L, ps.ray.o.x, ps.ray.o.y, ps.ray.o.z, ps.ray.d.x, ps.ray.d.y, ps.ray.d.z,
+                                                ps.ray.time, t_min, FLT_MAX);
+      t = w.x;
+      prim = __float_as_int(w.y);
+      any_hit = prim >= 0;
+    }
   }
-  return extend_finish<PAR, MEDIA, LEAN>(S, ps, max_depth, t_min, any_hit, t, prim, radiance, g, ndraw_out);
+  return extend_finish<PAR, MEDIA, TEX>(S, ps, max_depth, t_min, any_hit, t, prim, radiance, g, ndraw_out);
 }
 
 // shade(): material::scatter + the mixture-pdf step of color() for the hit (prim, t).
 // Returns true while the path continues (ps holds the next ray, throughput, depth).
-template <bool PAR, bool LEAN = false>
+template <bool PAR, int TEX = TPT_TEXF_ALL>
 TPT_DEV bool shade(const SceneView &S, PathState &ps, Rng &g, int prim, float t, uint32_t ndraw0) {
   // stage d+1 = the draws color() makes at depth d; ndraw0 of them were already taken inside
   // world->hit by participating media (0 in scenes without any)
@@ -1604,9 +1717,9 @@ TPT_DEV bool shade(const SceneView &S, PathState &ps, Rng &g, int prim, float t,
   const float4 m1 = S.blob[S.L->off_mats + 2 * mat + 1];
   const int mkind = __float_as_int(m0.x);
   const int mtex = __float_as_int(m0.y);
-  bool want_uv = !LEAN && mkind == TPT_MAT_LAMBERTIAN && texture_needs_uv(S, mtex);
+  bool want_uv = (TEX & TPT_TEXF_IMAGE) && mkind == TPT_MAT_LAMBERTIAN && texture_needs_uv(S, mtex);
   HitRec h;
-  fill_hit<PAR, LEAN>(S, ps.ray, prim, t, want_uv, h);
+  fill_hit<PAR, TEX>(S, ps.ray, prim, t, want_uv, h);
   if (mkind == TPT_MAT_METAL) { // src/material.cc:88-98
     V3 reflected = reflect(unit<PAR>(ps.ray.d), h.n);
     V3 dir = reflected + m1.y * random_in_unit_sphere(g); // fuzz_
@@ -1642,7 +1755,7 @@ TPT_DEV bool shade(const SceneView &S, PathState &ps, Rng &g, int prim, float t,
     ps.ray.d = (xi < reflect_prob) ? reflected : refracted; // attenuation (1,1,1)
   } else {
     // lambertian: src/material.cc:3-17 + mixture sampling src/utils.cc:73-81
-    V3 atten = texture_value<PAR, LEAN>(S, mtex, h.u, h.v, h.p);
+    V3 atten = texture_value<PAR, TEX>(S, mtex, h.u, h.v, h.p);
     Onb uvw = onb_from_w<PAR>(h.n);
     V3 dir;
     if (g.next() < 0.5f) {
@@ -1672,14 +1785,14 @@ TPT_DEV bool shade(const SceneView &S, PathState &ps, Rng &g, int prim, float t,
 }
 
 // one bounce = extend + shade (megakernel form)
-template <bool PAR, bool SMALL, bool MEDIA, bool LEAN = false>
+template <bool PAR, bool SMALL, bool MEDIA, int TEX = TPT_TEXF_ALL>
 TPT_DEV bool bounce(const SceneView &S, PathState &ps, Rng &g, int max_depth, float t_min, V3 &radiance) {
   float t;
   int prim;
   uint32_t ndraw0;
-  int cls = extend<PAR, SMALL, MEDIA, LEAN>(S, ps, max_depth, t_min, t, prim, radiance, g, ndraw0);
+  int cls = extend<PAR, SMALL, MEDIA, TEX>(S, ps, max_depth, t_min, t, prim, radiance, g, ndraw0);
   if (cls == TPT_EXT_DONE) return false;
-  return shade<PAR, LEAN>(S, ps, g, prim, t, ndraw0);
+  return shade<PAR, TEX>(S, ps, g, prim, t, ndraw0);
 }
 
 } // namespace tptd

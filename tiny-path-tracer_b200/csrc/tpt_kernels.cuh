@@ -151,7 +151,7 @@ TPT_DEV void lane_bin_refill(const RenderArgs &A, LaneBin &B, bool need, unsigne
 // Bins are ordered tile-major with the pixel index fastest: the 32 lanes of a warp work on 32
 // neighbouring pixels of one tile.
 // ------------------------------------------------------------------------------------------
-template <bool PAR, bool SMEM, bool SMALL, bool MEDIA, bool CULL, bool LEAN = false>
+template <bool PAR, bool SMEM, bool SMALL, bool MEDIA, bool CULL, int TEX = TPT_TEXF_ALL>
 __global__ void __launch_bounds__(TPT_MEGA_THREADS) render_mega_kernel(const __grid_constant__ RenderArgs A) {
   extern __shared__ float4 sblob[];
   SceneView S;
@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(TPT_MEGA_THREADS) render_mega_kernel(const __g
     if (active) {
       V3 rad;
       n_rays++;
-      if (!bounce<PAR, SMALL, MEDIA, LEAN>(S, ps, rng, A.max_depth, A.t_min, rad)) {
+      if (!bounce<PAR, SMALL, MEDIA, TEX>(S, ps, rng, A.max_depth, A.t_min, rad)) {
         // col += de_nan(tmp): main.cpp:126, headers/utils.h:100-109
         bool nan_any = isnan(rad.x) || isnan(rad.y) || isnan(rad.z) || isnan(ps.T.x) ||
                        isnan(ps.T.y) || isnan(ps.T.z);
@@ -246,8 +246,8 @@ __global__ void __launch_bounds__(TPT_MEGA_THREADS) render_mega_kernel(const __g
 #define TPT_WAVE_NQ 4 // queues: 0 lambertian, 1 metal, 2 dielectric (= TPT_MAT_*), 3 generate
 __host__ __device__ constexpr int wave_state_words(bool media) { return media ? 21 : 20; } // 32-bit words of path state per slot
 
-template <bool PAR, bool SMALL, bool SMEM, bool MEDIA, bool CULL, bool TRACE = false, bool LEAN = false>
-__global__ void __launch_bounds__(wave_threads(SMALL, TRACE), wave_min_blocks(PAR, SMALL, TRACE, LEAN))
+template <bool PAR, bool SMALL, bool SMEM, bool MEDIA, bool CULL, bool TRACE = false, int TEX = TPT_TEXF_ALL>
+__global__ void __launch_bounds__(wave_threads(SMALL, TRACE), wave_min_blocks(PAR, SMALL, TRACE, TEX == 0))
 render_wave_kernel(const __grid_constant__ RenderArgs A) {
   // shade and generate as ONE phase (a warp takes material chunks and generate chunks from one list:
   // better balance, one barrier fewer) or as two (each phase's code stays hot in the instruction
@@ -258,7 +258,7 @@ render_wave_kernel(const __grid_constant__ RenderArgs A) {
   // for the merged form as well: +4.6 % / +5.5 % (Cornell A / B).
   constexpr bool SPLIT_GEN = TPT_WAVE_SPLIT_GEN == 1 || (TPT_WAVE_SPLIT_GEN == 2 && PAR && !SMALL);
   extern __shared__ float4 sblob[];
-  constexpr int NSLOT = wave_slots(PAR, SMALL, TRACE);
+  constexpr int NSLOT = wave_slots(PAR, SMALL, TRACE, TEX == 0);
   constexpr int THREADS = wave_threads(SMALL, TRACE);
   constexpr int NWARP = THREADS / 32;
   // structure-of-arrays slot state: field f of slot s at sf[f * NSLOT + s]
@@ -397,9 +397,9 @@ render_wave_kernel(const __grid_constant__ RenderArgs A) {
           t = SF(F_HT, s);
           prim = SI(F_HPRIM, s);
           if (MEDIA) rng.set_stage((uint32_t)ps.depth + 1u);
-          cls = extend_finish<PAR, MEDIA, LEAN>(S, ps, A.max_depth, A.t_min, prim >= 0, t, prim, rad, rng, ndraw0);
+          cls = extend_finish<PAR, MEDIA, TEX>(S, ps, A.max_depth, A.t_min, prim >= 0, t, prim, rad, rng, ndraw0);
         } else {
-          cls = extend<PAR, SMALL, MEDIA, LEAN>(S, ps, A.max_depth, A.t_min, t, prim, rad, rng, ndraw0);
+          cls = extend<PAR, SMALL, MEDIA, TEX>(S, ps, A.max_depth, A.t_min, t, prim, rad, rng, ndraw0);
         }
         if (cls == TPT_EXT_DONE) {
           // col += de_nan(tmp): main.cpp:126, headers/utils.h:100-109
@@ -481,7 +481,7 @@ render_wave_kernel(const __grid_constant__ RenderArgs A) {
             Rng rng;
             const int pk = SI(F_PIXEL, s);
             rng.begin(A.rk, (uint32_t)((pk >> 16) * A.nx + (pk & 0xffff)), (uint32_t)SI(F_K, s));
-            bool alive = shade<PAR, LEAN>(S, ps, rng, SI(F_HPRIM, s), SF(F_HT, s), MEDIA ? (uint32_t)SI(F_NDRAW, s) : 0u);
+            bool alive = shade<PAR, TEX>(S, ps, rng, SI(F_HPRIM, s), SF(F_HT, s), MEDIA ? (uint32_t)SI(F_NDRAW, s) : 0u);
             if (alive) {
               SF(F_OX, s) = ps.ray.o.x; SF(F_OY, s) = ps.ray.o.y; SF(F_OZ, s) = ps.ray.o.z;
               SF(F_DX, s) = ps.ray.d.x; SF(F_DY, s) = ps.ray.d.y; SF(F_DZ, s) = ps.ray.d.z;
@@ -678,7 +678,7 @@ cudaError_t TPT_FN(launch_intersect_)(const IntersectArgs &A, bool smem, bool sm
 typedef void (*mega_fn)(RenderArgs);
 template <bool CULL> static mega_fn mega_variant_c(bool smem, bool small, bool media, bool lean) {
 #if !TPT_PAR
-  if (lean && small && smem && !media) return render_mega_kernel<false, true, true, false, CULL, true>;
+  if (lean && small && smem && !media) return render_mega_kernel<false, true, true, false, CULL, 0>;
 #endif
   (void)lean;
   if (media) return smem ? render_mega_kernel<TPT_PAR, true, false, true, CULL> : render_mega_kernel<TPT_PAR, false, false, true, CULL>;
@@ -686,7 +686,7 @@ template <bool CULL> static mega_fn mega_variant_c(bool smem, bool small, bool m
   return render_mega_kernel<TPT_PAR, false, false, false, CULL>;
 }
 static mega_fn mega_variant(const RenderArgs &A, bool smem, bool small, bool media) {
-  return A.cull ? mega_variant_c<true>(smem, small, media, A.lean != 0) : mega_variant_c<false>(smem, small, media, A.lean != 0);
+  return A.cull ? mega_variant_c<true>(smem, small, media, A.tex_mask == 0) : mega_variant_c<false>(smem, small, media, A.tex_mask == 0);
 }
 
 cudaError_t TPT_FN(mega_occupancy_)(const RenderArgs &A, bool smem, bool small, bool media, size_t smem_bytes, int *blocks_per_sm) {
@@ -707,28 +707,35 @@ struct WaveVariant {
   wave_fn fn;
   int threads, slots;
 };
-template <bool SMALL, bool SMEM, bool MEDIA, bool CULL, bool TRACE, bool LEAN> static WaveVariant wave_pick() {
-  return WaveVariant{render_wave_kernel<TPT_PAR, SMALL, SMEM, MEDIA, CULL, TRACE, LEAN>, wave_threads(SMALL, TRACE),
-                     wave_slots(TPT_PAR, SMALL, TRACE)};
+template <bool SMALL, bool SMEM, bool MEDIA, bool CULL, bool TRACE, int TEX> static WaveVariant wave_pick() {
+  return WaveVariant{render_wave_kernel<TPT_PAR, SMALL, SMEM, MEDIA, CULL, TRACE, TEX>, wave_threads(SMALL, TRACE),
+                     wave_slots(TPT_PAR, SMALL, TRACE, TEX == 0)};
 }
 // `trace` (FAST only): closest hits through the library's SAH BVH with dynamic ray hand-out; the
 // scene tables are read through L1 there and shared memory holds TPT_TRACE_SLOTS path slots.
-template <bool CULL> static WaveVariant wave_variant_c(bool small, bool smem, bool media, bool trace, bool lean) {
+template <bool CULL> static WaveVariant wave_variant_c(bool small, bool smem, bool media, bool trace, int tex) {
+  constexpr int ALL = TPT_TEXF_ALL;
 #if TPT_PAR && TPT_PAR_LEAN
-  if (lean && small && smem && !media) return wave_pick<true, true, false, CULL, false, true>();
+  if (tex == 0 && small && smem && !media) return wave_pick<true, true, false, CULL, false, 0>();
 #endif
 #if !TPT_PAR
-  if (lean && small && smem && !media && !trace) return wave_pick<true, true, false, CULL, false, true>();
-  if (trace) return media ? wave_pick<false, false, true, CULL, true, false>() : wave_pick<false, false, false, CULL, true, false>();
+  // small scenes: one build per texture feature set (constant only | + image | + procedural | both)
+  if (small && smem && !media && !trace) {
+    if (tex == 0) return wave_pick<true, true, false, CULL, false, 0>();
+    if (tex == TPT_TEXF_IMAGE) return wave_pick<true, true, false, CULL, false, TPT_TEXF_IMAGE>();
+    if (tex == TPT_TEXF_PROCEDURAL) return wave_pick<true, true, false, CULL, false, TPT_TEXF_PROCEDURAL>();
+    return wave_pick<true, true, false, CULL, false, ALL>();
+  }
+  if (trace) return media ? wave_pick<false, false, true, CULL, true, ALL>() : wave_pick<false, false, false, CULL, true, ALL>();
 #endif
   (void)trace;
-  (void)lean;
-  if (media) return smem ? wave_pick<false, true, true, CULL, false, false>() : wave_pick<false, false, true, CULL, false, false>();
-  if (!smem) return wave_pick<false, false, false, CULL, false, false>();
-  return small ? wave_pick<true, true, false, CULL, false, false>() : wave_pick<false, true, false, CULL, false, false>();
+  (void)tex;
+  if (media) return smem ? wave_pick<false, true, true, CULL, false, ALL>() : wave_pick<false, false, true, CULL, false, ALL>();
+  if (!smem) return wave_pick<false, false, false, CULL, false, ALL>();
+  return small ? wave_pick<true, true, false, CULL, false, ALL>() : wave_pick<false, true, false, CULL, false, ALL>();
 }
 static WaveVariant wave_variant(const RenderArgs &A, bool small, bool smem, bool media, bool trace) {
-  return A.cull ? wave_variant_c<true>(small, smem, media, trace, A.lean != 0) : wave_variant_c<false>(small, smem, media, trace, A.lean != 0);
+  return A.cull ? wave_variant_c<true>(small, smem, media, trace, A.tex_mask) : wave_variant_c<false>(small, smem, media, trace, A.tex_mask);
 }
 static size_t wave_smem_bytes(const RenderArgs &A, const WaveVariant &v, bool smem, bool media, bool trace) {
   const size_t per_slot = (size_t)wave_state_words(media) * 4 + 2 * TPT_WAVE_NQ * 2;

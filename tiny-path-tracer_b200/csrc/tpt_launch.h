@@ -53,6 +53,9 @@
 #ifndef TPT_SMALL_SLOTS_FAST
 #define TPT_SMALL_SLOTS_FAST 1152 // three path slots per thread
 #endif
+#ifndef TPT_SMALL_SLOTS_FAST_TEX
+#define TPT_SMALL_SLOTS_FAST_TEX 1024 // textured small scenes: their tables (Perlin: +7 KB) must still leave room for two CTAs (r02 sweep: 768 / 960 / 1024 slots = 6 647 / 6 842 / 6 947 Mpaths/s on two_perlin_spheres)
+#endif
 #ifndef TPT_SMALL_SLOTS_PAR
 #define TPT_SMALL_SLOTS_PAR 768
 #endif
@@ -68,8 +71,12 @@ namespace tptd {
 //    chunks, fewer barriers per path); parity prefers two slots per thread.
 //  * SAH-BVH / large scenes: 256 x 512 x 3 (r01 sweep), the media build 256 x 768 x 2 (128 registers).
 __host__ __device__ constexpr int wave_threads(bool small, bool trace) { return (small && !trace) ? TPT_SMALL_THREADS : TPT_WAVE_THREADS; }
-__host__ __device__ constexpr int wave_slots(bool par, bool small, bool trace) {
-  return trace ? TPT_TRACE_SLOTS : (small ? (par ? TPT_SMALL_SLOTS_PAR : TPT_SMALL_SLOTS_FAST) : TPT_WAVE_SLOTS);
+// Two CTAs must fit the SM's 227 KB of shared memory together with their copies of the scene tables:
+// 1152 slots (108 KB of path state) leave room for the 4 KB tables of a constant-texture scene only; a
+// scene with Perlin tables (+7 KB) would drop to ONE resident CTA (r02: two_perlin_spheres 6 860 -> 4 720
+// Mpaths/s), so the textured builds take 1024 slots (room for 14 KB of tables).
+__host__ __device__ constexpr int wave_slots(bool par, bool small, bool trace, bool lean) {
+  return trace ? TPT_TRACE_SLOTS : (small ? (par ? TPT_SMALL_SLOTS_PAR : (lean ? TPT_SMALL_SLOTS_FAST : TPT_SMALL_SLOTS_FAST_TEX)) : TPT_WAVE_SLOTS);
 }
 __host__ __device__ constexpr int wave_min_blocks(bool par, bool small, bool trace, bool lean) {
   return trace ? TPT_TRACE_MIN_BLOCKS : (small ? TPT_SMALL_MIN_BLOCKS : (lean ? TPT_WAVE_LEAN_MIN_BLOCKS : (par ? TPT_WAVE_PAR_MIN_BLOCKS : TPT_WAVE_MIN_BLOCKS)));
@@ -111,7 +118,7 @@ struct RenderArgs {
   int cull;
   int cull_x0, cull_x1, cull_y0, cull_y1;
   int camera_tries; // wavefront generate: camera rays drawn per visit while they miss the scene's bounds (1 = no test)
-  int lean; // every texture of the scene is a constant_texture: FAST small-scene kernels without the texture code
+  int tex_mask; // TPT_TEXF_* features of the scene's textures: small-scene kernels are built per feature set (0 = every texture is a constant_texture)
 };
 
 struct TextureProbeArgs {
