@@ -786,6 +786,11 @@ void build_flat_tree(const tpt_scene_desc *d, int n_root, bool smem_ok, FlatTree
     std::memset(&F, 0, sizeof(F));
     return;
   }
+  // visit order: grouped by the transform chain of the item's first primitive (stable), DFS rank kept for ties
+  for (int i = 0; i < ni; i++) F.items[i].rank = i;
+  std::stable_sort(F.items, F.items + ni, [&F](const FlatItem &a, const FlatItem &b) {
+    return F.prims[a.first].chain < F.prims[b.first].chain;
+  });
   F.n_boxes = nb;
   F.n_items = ni;
   F.n_prims = np;
