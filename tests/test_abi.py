@@ -58,3 +58,48 @@ def test_product_does_not_reference_oracle(T):
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cc", ".cpp")) or f == "Makefile":
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "oracle/" not in text and "oracle_ref" not in text and "libtptref" not in text, (dirpath, f)
+
+
+def _medium_desc(T, nesting):
+    """hand-made description: root list = [one constant_medium]; its boundary = a sphere wrapped in
+    `nesting` hitable_lists (kept behind the root tree, as the flattener lays media out)"""
+    n_nodes = 2 + nesting + 1
+    nodes = (T.Node * n_nodes)()
+    prims = (T.Prim * 2)()
+    nodes[0].kind, nodes[0].end_or_prim = 1, 2           # root LIST
+    nodes[1].kind, nodes[1].end_or_prim = 2, 0           # LEAF -> prim 0 (the medium)
+    for k in range(nesting):                             # boundary: LIST(LIST(...(sphere)))
+        nodes[2 + k].kind, nodes[2 + k].end_or_prim = 1, n_nodes
+    nodes[2 + nesting].kind, nodes[2 + nesting].end_or_prim = 2, 1
+    prims[0].kind, prims[0].material = 5, 0              # TPT_PRIM_MEDIUM
+    prims[0].p[0] = 0.01
+    first_end = (C.c_int32 * 2)(2, n_nodes)
+    C.memmove(C.addressof(prims[0].p) + 4, first_end, 8)
+    prims[1].kind, prims[1].material = 0, 0              # sphere
+    prims[1].p[3] = 1.0
+    chains, mats, texs = (T.Chain * 1)(), (T.Material * 1)(), (T.Texture * 1)()
+    mats[0].kind = 5                                     # isotropic
+    lights = (T.Light * 1)()
+    d = T.SceneDesc()
+    d.api_version = T.TPT_API_VERSION
+    d.n_nodes, d.n_prims, d.n_chains, d.n_materials, d.n_textures, d.n_lights = n_nodes, 2, 1, 1, 1, 1
+    d.nodes, d.prims, d.chains, d.materials, d.textures, d.lights = nodes, prims, chains, mats, texs, lights
+    d.n_root_nodes = 2
+    return d, (nodes, prims, chains, mats, texs, lights)
+
+
+def test_deep_medium_boundary_is_refused(T):
+    """the parity walk of a medium's boundary keeps 8 frames; a boundary nested deeper must be
+    refused at upload (TPT_ERR_UNSUPPORTED), not overflow a device-side array. Validation runs before any
+    device is touched, so this holds with and without a GPU."""
+    lib = T.lib()
+    for nesting, refused in ((3, False), (7, False), (8, True), (20, True)):
+        d, keep = _medium_desc(T, nesting)
+        out = C.c_void_p()
+        rc = lib.tpt_scene_create(C.byref(d), 0, C.byref(out))
+        if refused:
+            assert rc == -4 and b"boundary nests deeper" in lib.tpt_last_error(), (nesting, rc, lib.tpt_last_error())
+        else:
+            assert rc in (0, -3), (nesting, rc, lib.tpt_last_error())  # fine: created, or no device here
+            if rc == 0:
+                lib.tpt_scene_destroy(out)

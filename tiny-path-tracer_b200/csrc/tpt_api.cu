@@ -211,6 +211,21 @@ int validate_desc(const tpt_scene_desc *d, int &depth_out) {
       std::memcpy(&be, &p.p[2], 4);
       if (bf < n_root || be <= bf || be > d->n_nodes) return fail(TPT_ERR_INVALID, "medium boundary range out of bounds");
       if (!(p.p[0] > 0)) return fail(TPT_ERR_INVALID, "medium density must be positive");
+      {
+        // the parity walk of a boundary sub-tree keeps TPT_MAX_BOUNDARY_FRAMES frames (one is the virtual
+        // root): a boundary nested deeper than that (a bvh_node or lists of lists) is refused here
+        std::vector<int> open_ends;
+        int deepest = 0;
+        for (int k = bf; k < be; k++) {
+          while (!open_ends.empty() && open_ends.back() == k) open_ends.pop_back();
+          if ((d->nodes[k].kind & 0xff) != TPT_NODE_LEAF) {
+            open_ends.push_back(d->nodes[k].end_or_prim);
+            deepest = std::max(deepest, (int)open_ends.size());
+          }
+        }
+        if (deepest + 1 > TPT_MAX_BOUNDARY_FRAMES)
+          return fail(TPT_ERR_UNSUPPORTED, "medium boundary nests deeper than TPT_MAX_BOUNDARY_FRAMES");
+      }
       for (int k = bf; k < be; k++)
         if ((d->nodes[k].kind & 0xff) == TPT_NODE_LEAF && d->prims[d->nodes[k].end_or_prim].kind == TPT_PRIM_MEDIUM)
           return fail(TPT_ERR_UNSUPPORTED, "medium inside a medium boundary");
@@ -1404,7 +1419,24 @@ int tpt_device_count(void) {
 
 const char *tpt_last_error(void) { return g_error.c_str(); }
 
+static int scene_create_impl(const tpt_scene_desc *d, int device, tpt_scene **out, tpt_scene **partial);
+
 int tpt_scene_create(const tpt_scene_desc *d, int device, tpt_scene **out) {
+  // every early return of the builder below leaves what it had allocated so far in `partial`: released here,
+  // so a failed create leaks neither the stream, the events, device memory nor the texture arrays
+  tpt_scene *partial = nullptr;
+  const int rc = scene_create_impl(d, device, out, &partial);
+  if (rc != TPT_OK && partial) {
+    const std::string keep = g_error;
+    tpt_scene_destroy(partial);
+    cudaGetLastError();
+    g_error = keep;
+    if (out) *out = nullptr;
+  }
+  return rc;
+}
+
+static int scene_create_impl(const tpt_scene_desc *d, int device, tpt_scene **out, tpt_scene **partial) {
   if (!out) return fail(TPT_ERR_INVALID, "null out pointer");
   *out = nullptr;
   int depth = 0;
@@ -1419,6 +1451,7 @@ int tpt_scene_create(const tpt_scene_desc *d, int device, tpt_scene **out) {
   if (device < 0 || device >= ndev) return fail(TPT_ERR_INVALID, "device ordinal out of range");
   CK(cudaSetDevice(device));
   tpt_scene *s = new tpt_scene();
+  *partial = s;
   s->device = device;
   {
     // cudaGetDeviceProperties is a slow driver query (3 ms typical, 100+ ms now and then): once
@@ -1433,10 +1466,7 @@ int tpt_scene_create(const tpt_scene_desc *d, int device, tpt_scene **out) {
     if (!hit) {
       cudaDeviceProp prop;
       cudaError_t pe = cudaGetDeviceProperties(&prop, device);
-      if (pe != cudaSuccess) {
-        delete s;
-        return fail(TPT_ERR_CUDA, cudaGetErrorString(pe));
-      }
+      if (pe != cudaSuccess) return fail(TPT_ERR_CUDA, cudaGetErrorString(pe));
       cudaMemPool_t pool;
       if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
         unsigned long long keep = ~0ULL;
@@ -1461,10 +1491,7 @@ int tpt_scene_create(const tpt_scene_desc *d, int device, tpt_scene **out) {
     s->prop = hit->prop;
     s->products = hit->products;
   }
-  if (s->prop.major < 10) {
-    delete s;
-    return fail(TPT_ERR_NO_DEVICE, "device is not sm_100-class; kernels are built for sm_100a only");
-  }
+  if (s->prop.major < 10) return fail(TPT_ERR_NO_DEVICE, "device is not sm_100-class; kernels are built for sm_100a only");
   CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
   for (auto &ev : s->ev) CK(cudaEventCreate(&ev));
 
@@ -1658,6 +1685,7 @@ int tpt_scene_create(const tpt_scene_desc *d, int device, tpt_scene **out) {
   CK(cudaMallocAsync((void **)&s->d_counters, TPT_MAX_BATCHES * 8 * sizeof(unsigned long long), s->stream));
   s->stats.h2d_bytes = blob.size();
   *out = s;
+  *partial = nullptr;
   return TPT_OK;
 }
 
@@ -1693,9 +1721,14 @@ int tpt_intersect_batch(const tpt_scene *cs, const tpt_ray *rays, size_t n, floa
   CK(cudaSetDevice(s->device));
   float *d_rays = nullptr;
   tpt_hit *d_out = nullptr;
-  CK(cudaMalloc((void **)&d_rays, n * sizeof(tpt_ray)));
-  CK(cudaMalloc((void **)&d_out, n * sizeof(tpt_hit)));
-  CK(cudaMemcpyAsync(d_rays, rays, n * sizeof(tpt_ray), cudaMemcpyHostToDevice, s->stream));
+  cudaError_t e = cudaMalloc((void **)&d_rays, n * sizeof(tpt_ray));
+  if (e == cudaSuccess) e = cudaMalloc((void **)&d_out, n * sizeof(tpt_hit));
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_rays, rays, n * sizeof(tpt_ray), cudaMemcpyHostToDevice, s->stream);
+  if (e != cudaSuccess) { // nothing allocated so far outlives a failed call
+    cudaFree(d_rays);
+    cudaFree(d_out);
+    return cuda_fail(e, "intersect batch: device buffers");
+  }
   IntersectArgs A;
   A.scene = s->layout;
   if (mode == TPT_MODE_PARITY) A.flat = s->flat;
@@ -1705,7 +1738,7 @@ int tpt_intersect_batch(const tpt_scene *cs, const tpt_ray *rays, size_t n, floa
   A.tmin = tmin;
   A.tmax = tmax;
   A.out = d_out;
-  cudaError_t e = mode == TPT_MODE_PARITY ? launch_intersect_parity(A, s->use_smem, s->flat.enabled != 0, s->stream)
+  e = mode == TPT_MODE_PARITY ? launch_intersect_parity(A, s->use_smem, s->flat.enabled != 0, s->stream)
                                           : launch_intersect_fast(A, s->use_smem, s->small.enabled != 0, s->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, n * sizeof(tpt_hit), cudaMemcpyDeviceToHost, s->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
@@ -1793,11 +1826,18 @@ int tpt_debug_fp32_peak(int device, double *tflops, double *ms) {
   const int blocks = sms * 8, iters = 1 << 16;
   float *sink = nullptr;
   cudaEvent_t e0, e1;
-  CK(cudaMalloc((void **)&sink, 4));
-  CK(cudaEventCreate(&e0));
-  CK(cudaEventCreate(&e1));
+  cudaEvent_t none = nullptr;
+  e0 = e1 = none;
+  cudaError_t e = cudaMalloc((void **)&sink, 4);
+  if (e == cudaSuccess) e = cudaEventCreate(&e0);
+  if (e == cudaSuccess) e = cudaEventCreate(&e1);
+  if (e != cudaSuccess) {
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    cudaFree(sink);
+    return cuda_fail(e, "fp32 peak probe: setup");
+  }
   float best = 0.f;
-  cudaError_t e = cudaSuccess;
   for (int rep = 0; rep < 4 && e == cudaSuccess; rep++) { // first pass warms the clocks up
     cudaEventRecord(e0, 0);
     e = launch_fp32_peak_probe(blocks, iters, sink, 0);
@@ -1849,16 +1889,21 @@ int tpt_debug_texture(const tpt_scene *cs, int texture, const float *uvp, size_t
   if (n == 0) return TPT_OK;
   CK(cudaSetDevice(s->device));
   float *d_in = nullptr, *d_out = nullptr;
-  CK(cudaMalloc((void **)&d_in, n * 5 * sizeof(float)));
-  CK(cudaMalloc((void **)&d_out, n * 3 * sizeof(float)));
-  CK(cudaMemcpy(d_in, uvp, n * 5 * sizeof(float), cudaMemcpyHostToDevice));
+  cudaError_t e = cudaMalloc((void **)&d_in, n * 5 * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc((void **)&d_out, n * 3 * sizeof(float));
+  if (e == cudaSuccess) e = cudaMemcpy(d_in, uvp, n * 5 * sizeof(float), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    cudaFree(d_in);
+    cudaFree(d_out);
+    return cuda_fail(e, "texture probe: device buffers");
+  }
   TextureProbeArgs A;
   A.scene = s->layout;
   A.texture = texture;
   A.uvp = d_in;
   A.n = n;
   A.out = d_out;
-  cudaError_t e = mode == TPT_MODE_PARITY ? launch_texture_probe_parity(A, s->stream)
+  e = mode == TPT_MODE_PARITY ? launch_texture_probe_parity(A, s->stream)
                                           : launch_texture_probe_fast(A, s->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
   if (e == cudaSuccess) e = cudaMemcpy(out_rgb, d_out, n * 3 * sizeof(float), cudaMemcpyDeviceToHost);
