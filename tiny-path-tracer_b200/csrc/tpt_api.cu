@@ -1630,6 +1630,18 @@ static int scene_create_impl(const tpt_scene_desc *d, int device, tpt_scene **ou
     s->background = d->background;
   }
   L.fbvh_time_ok = 1;
+  {
+    // closest_hit_skip (PARITY) needs: no medium, no bvh_node anywhere below a hitable_list
+    bool simple = mediums.empty();
+    int list_until = -1;
+    for (int i = 0; simple && i < n_root; i++) {
+      const int k = d->nodes[i].kind & 0xff;
+      if (i >= list_until) list_until = -1;
+      if (k == TPT_NODE_BVH && list_until >= 0) simple = false;
+      if (k == TPT_NODE_LIST && list_until < 0) list_until = d->nodes[i].end_or_prim;
+    }
+    L.tree_simple = simple ? 1 : 0;
+  }
   s->fbvh_has_moving = fb.has_moving;
   s->fbvh_t0 = fb.moving_t0;
   s->fbvh_t1 = fb.moving_t1;

@@ -28,6 +28,9 @@ namespace tptd {
 #define TPT_TEXF_IMAGE 1      // texture feature bits of a kernel build (texture_value / fill_hit)
 #define TPT_TEXF_PROCEDURAL 2
 #define TPT_TEXF_ALL 3
+#ifndef TPT_PAR_SKIP_WALK
+#define TPT_PAR_SKIP_WALK 1 // PARITY, large simple trees: per-lane skip-pointer walk instead of the lock-step frame replay
+#endif
 #ifndef TPT_EXACT_DOUBLE_ROOTS
 #define TPT_EXACT_DOUBLE_ROOTS 1 // FAST mode, huge "wall" spheres: roots in double like the reference (0: IEEE fp32)
 #endif
@@ -45,6 +48,7 @@ struct SceneLayout { // host-computed, lives in kernel parameter (constant) spac
   int off_nodes, off_prims, off_chains, off_ops, off_mats, off_texs, off_lights, off_perlin;
   int off_mediums, n_mediums; // MEDIUM primitive ids in DFS order (int list); boundaries live behind n_nodes
   int off_fbvh, off_fleaf, n_fbvh, fbvh_time_ok; // FAST-mode SAH BVH over world-space leaf boxes (0 nodes = none)
+  int tree_simple; // no medium and no bvh_node below a hitable_list: PARITY walks the tree with skip pointers (closest_hit_skip)
   int n_nodes, n_prims, n_lights, background;
   cudaTextureObject_t images[TPT_MAX_IMAGES];
   int image_w[TPT_MAX_IMAGES], image_h[TPT_MAX_IMAGES];
@@ -801,10 +805,90 @@ TPT_DEV bool closest_hit_flat(const SceneView &S, const Ray &r, float tmin, floa
   return best_prim >= 0;
 }
 
+// ------------------------------------------------------------------------------------------
+// PARITY mode, trees of any size whose hitable_lists hold no bvh_node (SceneLayout::tree_simple, e.g.
+// random_scene's 485-leaf tree): the same argument as closest_hit_flat, walked per lane over the
+// pre-order node array with skip pointers instead of a frame stack. Below the bvh_nodes every leaf /
+// list sees the caller's t_max, so the merged result is "smallest t, last in DFS order among equals":
+// a sequential scan in DFS order with `take unless best.t < t`; a list (nested lists concatenate) is
+// one run against its own closest_so_far; a failed box skips its sub-tree; a NaN candidate hands the
+// ray to the literal replay.
+// ------------------------------------------------------------------------------------------
+TPT_DEV bool closest_hit_skip(const SceneView &S, const Ray &r, float tmin, float tmax, float &t_out, int &prim_out) {
+  const float4 *N = S.blob + S.L->off_nodes;
+  const int n = S.L->n_nodes;
+  XRay x;
+  x.chain = -1;
+  float best_t = 0.f, run_t = tmax;
+  int best_prim = -1, run_prim = -1, list_end = -1;
+  bool unordered = false;
+  for (int i = 0; i < n;) {
+    if (i == list_end) { // the (outermost) list closes: its record goes up to the enclosing bvh_node
+      if (run_prim >= 0) {
+        unordered = unordered || isnan(run_t);
+        if (best_prim < 0 || !(best_t < run_t)) {
+          best_t = run_t;
+          best_prim = run_prim;
+        }
+      }
+      list_end = -1;
+    }
+    const float4 n0 = N[2 * i], n1 = N[2 * i + 1];
+    const int kind = __float_as_int(n0.w), k = kind & 0xff, payload = __float_as_int(n1.w);
+    if (kind & TPT_NODE_DUP) { // second visit of a one-element bvh_node's child: the same record twice
+      i = k == TPT_NODE_LEAF ? i + 1 : payload;
+      continue;
+    }
+    if (k == TPT_NODE_LEAF) {
+      to_chain<true>(S, r, kind >> 16, x);
+      float t;
+      if (list_end >= 0) {
+        if (prim_test<true>(S, payload, x, r.time, tmin, run_t, t)) {
+          run_t = t;
+          run_prim = payload;
+        }
+      } else if (prim_test<true>(S, payload, x, r.time, tmin, tmax, t)) {
+        unordered = unordered || isnan(t);
+        if (best_prim < 0 || !(best_t < t)) {
+          best_t = t;
+          best_prim = payload;
+        }
+      }
+      i++;
+    } else if (k == TPT_NODE_LIST) {
+      if (list_end < 0) {
+        list_end = payload;
+        run_t = tmax;
+        run_prim = -1;
+      }
+      i++;
+    } else {
+      to_chain<true>(S, r, kind >> 16, x);
+      i = aabb_hit<true>(x, n0, n1, tmin, tmax) ? i + 1 : payload;
+    }
+  }
+  if (list_end >= 0 && run_prim >= 0) {
+    unordered = unordered || isnan(run_t);
+    if (best_prim < 0 || !(best_t < run_t)) {
+      best_t = run_t;
+      best_prim = run_prim;
+    }
+  }
+  if (unordered) {
+    const float2 w = closest_hit_replay(S.blob, S.L, r.o.x, r.o.y, r.o.z, r.d.x, r.d.y, r.d.z, r.time, tmin, tmax);
+    best_t = w.x;
+    best_prim = __float_as_int(w.y);
+  }
+  t_out = best_t;
+  prim_out = best_prim;
+  return best_prim >= 0;
+}
+
 // world->hit: the root tree is nodes [0, n_nodes)
 template <bool PAR>
 TPT_DEV bool closest_hit(const SceneView &S, const Ray &r, float tmin, float tmax, float &t_out, int &prim_out,
                          Rng *g = nullptr) {
+  if (PAR && TPT_PAR_SKIP_WALK && g == nullptr && S.L->tree_simple) return closest_hit_skip(S, r, tmin, tmax, t_out, prim_out);
   return walk_range<PAR, true>(S, r, 0, S.L->n_nodes, tmin, tmax, t_out, prim_out, g);
 }
 
