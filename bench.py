@@ -240,6 +240,17 @@ def cpu_reference_sample(c, target_seconds, threads=0):
     rs = O.RefScene(c["scene"], det=False, image=scene_image(c))
     cam = ref_camera_args(c)
     nx, ny = c["nx"], c["ny"]
+    if threads == 0:
+        # "all the host threads it can use": std::thread::hardware_concurrency() reports the affinity mask, which on
+        # a container limited by CPU quota (or with SMT siblings outside the mask) is not the count that runs fastest
+        # (r02: the stock binary's 1200 row threads out-ran a 16-thread pool on the GPU box). Probe 1x / 2x / 4x.
+        base = os.cpu_count() or 1
+        best = None
+        for t in (base, 2 * base, 4 * base):
+            _, _, st = rs.render(cam, nx, ny, 1, c["depth"], deterministic=False, threads=t, count_rays=False)
+            if best is None or st["seconds"] < best[1]:
+                best = (t, st["seconds"])
+        threads = best[0]
     _, _, st = rs.render(cam, nx, ny, 1, c["depth"], deterministic=False, threads=threads, count_rays=False)
     per_spp = st["seconds"]
     spp = int(max(1, min(64, c["spp"], round(target_seconds / max(per_spp, 1e-3)))))
@@ -247,7 +258,7 @@ def cpu_reference_sample(c, target_seconds, threads=0):
     return {"value": st["paths"] / st["seconds"] / 1e6, "unit": "Mpaths/s", "cores": st["threads"], "kind": "reference",
             "sample": f"config {c['id']} ({c['scene']}) full {nx}x{ny} frame at {spp} spp ({st['paths']} paths, {st['seconds']:.1f} s): "
                       f"reference color()/hit/scatter (oracle/_ref/libtptref.so, mt19937 drand_r) on {st['threads']} threads",
-            "seconds": st["seconds"], "spp": spp, "_scene": rs, "_cam": cam}
+            "seconds": st["seconds"], "spp": spp, "_scene": rs, "_cam": cam, "_threads": threads}
 
 
 def stock_reference_fit(c, budget_s=40.0):
@@ -277,13 +288,14 @@ def stock_reference_fit(c, budget_s=40.0):
         finally:
             shutil.rmtree(d, ignore_errors=True)
 
-    s1 = 1
+    # Both points well above the program's fixed cost (about 2 s here: 1200 thread starts, 1.44 M string-keyed map
+    # inserts under a mutex, P3 output): at 1 spp that cost overlaps the rendering and T(spp) is not yet linear
+    # (r02 on the GPU box: 1 / 32 / 128 spp = 1.97 / 2.74 / 6.89 s).
+    s1 = min(32, c["spp"])
     t1, w1 = run(s1)
     if t1 is None:
         return None
-    # second point sized to the budget: w1 is mostly the program's fixed cost (1.44 M string-keyed map inserts,
-    # 1200 threads, P3 output), so w1 / 4 per spp is a safe over-estimate of the slope
-    s2 = int(max(2, min(256, c["spp"], (budget_s - 2 * w1) / max(w1 * 0.25, 0.05))))
+    s2 = int(max(2 * s1, min(4 * s1, c["spp"], s1 * (budget_s - w1) / max(w1, 0.05))))
     t2, w2 = run(s2)
     if t2 is None:
         return None
@@ -354,7 +366,7 @@ def run_reference_arm(args, rank, world):
     secs = []
     paths = nx * ny * spp
     for i in range(total):
-        _, _, st = rs.render(cam, nx, ny, spp, c["depth"], deterministic=False, threads=0, count_rays=False)
+        _, _, st = rs.render(cam, nx, ny, spp, c["depth"], deterministic=False, threads=first["_threads"], count_rays=False)
         if i >= args.warmup:
             secs.append(st["seconds"])
     t = sum(secs)
@@ -625,7 +637,13 @@ def run_ours(args, rank, local_rank, world):
         dist.barrier(group=cpu_group)
         if rank == 0:
             try:
-                scenes = [T.Scene(hs, device=g) for g in range(world)]
+                from concurrent.futures import ThreadPoolExecutor
+                pool = ThreadPoolExecutor(max_workers=world)
+
+                def make_scenes():  # one host thread per GPU (ctypes releases the GIL inside tpt_scene_create)
+                    return list(pool.map(lambda g: T.Scene(hs, device=g), range(world)))
+
+                scenes = make_scenes()
                 arr = (C.c_void_p * world)(*[sc._s for sc in scenes])
                 p1 = T.make_params(NX, NY, NS, c["depth"], mode=mode, seed=0x5EED, kernel=kernel, bundle_cull=args.bundle_cull)
                 secs, last = [], None
@@ -633,9 +651,8 @@ def run_ours(args, rank, local_rank, world):
                 for i in range((0 if big else 2) + reps):
                     t0 = time.perf_counter()
                     if i >= (0 if big else 2):  # timed iterations pay scene creation on every GPU too, like `e2e`
-                        for sc in scenes:
-                            sc.close()
-                        scenes = [T.Scene(hs, device=g) for g in range(world)]
+                        list(pool.map(lambda sc: sc.close(), scenes))
+                        scenes = make_scenes()
                         arr = (C.c_void_p * world)(*[sc._s for sc in scenes])
                     T._check(T.lib().tpt_render_multi(arr, world, C.byref(cam), C.byref(p1), C.byref(img)))
                     last = scenes[0].stats()

@@ -78,6 +78,13 @@ struct LaneBin {
   unsigned acc_index;
   V3 acc;
 };
+// tile owned by this launch: part `part_index` of `part_count` (tiles t with t % part_count == part_index), or --
+// tpt_render_multi's static share in ONE launch -- the union of `part_group` such parts, `part_stride` apart
+TPT_DEV unsigned part_tile(const RenderArgs &A, unsigned tile_local) {
+  if (A.part_group <= 1) return (unsigned)A.part_index + tile_local * (unsigned)A.part_count;
+  const unsigned q = tile_local / (unsigned)A.part_group, r = tile_local - q * (unsigned)A.part_group;
+  return (unsigned)A.part_index + r * (unsigned)A.part_stride + q * (unsigned)A.part_count;
+}
 // no ray of pixel (px, py) can reach the scene's bounds (RenderArgs::cull_*, computed in make_plan)
 TPT_DEV bool pixel_bundle_misses(const RenderArgs &A, int px, int py) {
   return px < A.cull_x0 || px > A.cull_x1 || py < A.cull_y0 || py > A.cull_y1;
@@ -112,7 +119,7 @@ TPT_DEV void lane_bin_refill(const RenderArgs &A, LaneBin &B, bool need, unsigne
         unsigned rem = bb - tile_local * bins_per_tile;
         unsigned range = rem / (unsigned)(TPT_TILE * TPT_TILE);
         unsigned pit = rem - range * (unsigned)(TPT_TILE * TPT_TILE);
-        unsigned tile = (unsigned)A.part_index + tile_local * (unsigned)A.part_count;
+        unsigned tile = part_tile(A, tile_local);
         unsigned ty = tile / (unsigned)A.tiles_x, tx = tile - ty * (unsigned)A.tiles_x;
         B.px = (int)(tx * TPT_TILE + (pit & (TPT_TILE - 1)));
         B.py = (int)(ty * TPT_TILE + (pit / TPT_TILE));
@@ -538,7 +545,7 @@ render_wave_kernel(const __grid_constant__ RenderArgs A) {
                 unsigned rem = bb - tile_local * bins_per_tile;
                 unsigned range = rem / (unsigned)(TPT_TILE * TPT_TILE);
                 unsigned pit = rem - range * (unsigned)(TPT_TILE * TPT_TILE);
-                unsigned tile = (unsigned)A.part_index + tile_local * (unsigned)A.part_count;
+                unsigned tile = part_tile(A, tile_local);
                 unsigned ty = tile / (unsigned)A.tiles_x, tx = tile - ty * (unsigned)A.tiles_x;
                 int px = (int)(tx * TPT_TILE + (pit & (TPT_TILE - 1)));
                 int py = (int)(ty * TPT_TILE + (pit / TPT_TILE));

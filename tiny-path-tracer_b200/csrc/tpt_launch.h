@@ -107,6 +107,7 @@ struct RenderArgs {
   int n_ranges;                          // sample ranges per pixel (slices x sub-ranges)
   int range_bounds[TPT_MAX_RANGES + 1];  // range r covers samples [bounds[r], bounds[r+1])
   int tiles_x, tiles_y, part_index, part_count;
+  int part_group, part_stride;           // > 1: this launch owns parts part_index + r * part_stride, r < part_group (one launch for a GPU's static share)
   unsigned long long n_bins;             // local tiles x TILE^2 x n_ranges
   float *acc;                            // [n_ranges][ny*nx][3] per-range radiance sums
   unsigned long long *counters;          // [0] next bin, [1] rays, [2] NaN samples, [3] paths, [4] paths resolved by the bundle test
