@@ -279,9 +279,9 @@ int tpt_render_fetch(tpt_scene *scene, tpt_image *out);
 
 /* In-process multi-GPU: `scenes[g]` is the same scene created on GPU g (tpt_scene_create with
  * device = g). The frame is cut into 8 x n batches of interleaved 16x16 tiles; every GPU renders a
- * static share and then steals the remaining batches from a shared counter (one host thread per
- * GPU inside the call); GPU 0 gathers the disjoint partial frames over NVLink and the image is
- * downloaded once. The result is bit-identical to a single-GPU tpt_render (Philox is keyed on
+ * static share (7 of its 8 batches, one launch) and then steals the remaining batches from a shared
+ * counter (one host thread per GPU inside the call); GPU 0 fetches every tile from the GPU that rendered
+ * it over NVLink (one kernel over peer memory, no NCCL) and the image is downloaded once. The result is bit-identical to a single-GPU tpt_render (Philox is keyed on
  * pixel and sample). params->part_index/part_count must be 0/1. Statistics are read from
  * scenes[0]. */
 int tpt_render_multi(tpt_scene *const *scenes, int n_scenes, const tpt_camera *cam, const tpt_render_params *params,

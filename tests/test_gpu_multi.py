@@ -25,13 +25,13 @@ def _multi_vs_single(T, n, mode, kernel):
     assert np.array_equal(multi.rgb8_slices, single.rgb8_slices)
     assert multi.stats["paths"] == nx * ny * ns == single.stats["paths"]
     assert multi.stats["rays"] == single.stats["rays"]
-    n_static = (8 * n * 3 // 4) // n * n
+    n_static = (8 * n * 7 // 8) // n * n
     assert multi.stats["kernel_launches"] == n + (8 * n - n_static) + n  # per GPU: ONE launch for its static share, the stolen batches, one resolve
     st = multi.stats
     assert st["multi_gpus"] == n and st["multi_batches_total"] == 8 * n
     assert sum(st["multi_batches"]) == 8 * n and len(st["multi_batches"]) == n
-    assert sum(st["multi_stolen"]) == 8 * n - (8 * n * 3 // 4) // n * n  # what the static shares leave over
-    assert all(b >= (8 * n * 3 // 4) // n for b in st["multi_batches"])  # nobody does less than its static share
+    assert sum(st["multi_stolen"]) == 8 * n - (8 * n * 7 // 8) // n * n  # what the static shares leave over
+    assert all(b >= (8 * n * 7 // 8) // n for b in st["multi_batches"])  # nobody does less than its static share
     return st
 
 
