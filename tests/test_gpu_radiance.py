@@ -203,3 +203,70 @@ def test_oneweek_final_vs_port(T, gpu):
         fast = sc.render(cam, T.make_params(c["nx"], c["ny"], 256, c["depth"], mode=T.MODE_FAST, seed=5, kernel=kernel))
         assert abs(fast.sum_rgb.mean() - slow.sum_rgb.mean()) < 0.03 * slow.sum_rgb.mean(), kernel
         assert fast.stats["paths"] == c["nx"] * c["ny"] * 256
+
+
+# BASELINE.json configurations at their FULL resolution: one or two samples per pixel of the
+# whole frame against the live reference under the injected stream. Configs 1-3 are black at the reference's HEAD
+# (no emitter; src/utils.cc:85-86), so for them the identical-zeros check is backed by the ray counts (the same
+# hit/miss decisions on every path) and by a sky-background run against the plain-C restatement.
+FULL_RES = {
+    "1": dict(scene="random_scene_list", cam=common.BOOK_CAM, nx=400, ny=400, ns=2),
+    "2": dict(scene="random_scene", cam=common.BOOK_CAM, nx=1600, ny=1600, ns=1),
+    "3a": dict(scene="two_perlin_spheres", cam=common.BOOK_CAM, nx=1600, ny=1600, ns=1),
+    "3b": dict(scene="earth", cam=common.BOOK_CAM, nx=1600, ny=1600, ns=1),
+    "4": dict(scene="cornell_box", cam=common.CORNELL_CAM, nx=1200, ny=1200, ns=2),
+}
+
+
+@pytest.mark.parametrize("config", list(FULL_RES))
+def test_parity_at_full_resolution_per_config(T, O, gpu, config):
+    c = FULL_RES[config]
+    img = common.earth_small() if c["scene"] == "earth" else None
+    rs = O.RefScene(c["scene"], image=img)
+    rv, px, py, pz = rs.perlin_tables()  # the live static tables of THIS reference scene
+    perlin = common.perlin_struct(T, dict(ranvec=rv, perm_x=px, perm_y=py, perm_z=pz))
+    depth, seed = 15, 4242
+    ref, _, st = rs.render(c["cam"], c["nx"], c["ny"], c["ns"], depth, seed=seed)
+    hs = T.HostScene(c["scene"], image=img, perlin=perlin)
+    sc = T.Scene(hs)
+    cam = common.product_camera(T, c["cam"], c["nx"], c["ny"])
+    for kernel in (T.KERNEL_WAVEFRONT, T.KERNEL_MEGA):
+        res = sc.render(cam, T.make_params(c["nx"], c["ny"], c["ns"], depth, mode=T.MODE_PARITY, seed=seed, kernel=kernel,
+                                           bundle_cull=False))
+        n_bad, n, worst = outliers(res.sum_rgb, ref, c["ns"])
+        assert n_bad == 0, f"config {config}: {n_bad}/{n} pixels beyond {REL_TOL}, worst {worst}"
+        assert res.stats["paths"] == c["nx"] * c["ny"] * c["ns"]
+        # the GPU stops NaN / zero-weight paths at once, the reference bounces them to max_depth (every
+        # path that samples the r = 120 light-shape sphere from inside it); everything else is the same sequence of
+        # world->hit calls, so the GPU never traces MORE rays
+        print(f"\nconfig {config} kernel {kernel}: rays {res.stats['rays']} vs reference {st['rays']}")
+        assert 0.3 * st["rays"] <= res.stats["rays"] <= st["rays"]
+    if config == "4":
+        assert ref.max() > 0  # the only configuration with an emitter
+
+
+@pytest.mark.parametrize("config", ["2", "3a", "3b"])
+def test_parity_at_full_resolution_sky_vs_port(T, gpu, config):
+    """the same frames with the sky gradient the reference has commented out (src/utils.cc:87-90): non-trivial
+    radiance through the whole frame, checked against the plain-C restatement (pinned to the reference bit for bit
+    on everything HEAD can render)."""
+    import oracle_port as P
+    if not P.available():
+        pytest.skip("oracle/_build/libtptoracle.so not built")
+    c = FULL_RES[config]
+    g = common.golden("textures")
+    hs = T.HostScene(c["scene"], image=common.earth_small() if c["scene"] == "earth" else None,
+                     perlin=common.perlin_struct(T, g), background=T.BG_SKY)
+    cam = common.product_camera(T, c["cam"], c["nx"], c["ny"])
+    p = T.make_params(c["nx"], c["ny"], 1, 15, mode=T.MODE_PARITY, seed=99, kernel=T.KERNEL_WAVEFRONT)
+    ref, _, st = P.render(T, hs, cam, p, threads=16)
+    res = T.Scene(hs).render(cam, p)
+    n_bad, n, worst = outliers(res.sum_rgb, ref, 1)
+    print(f"\nconfig {config} + sky, {n} pixels: {n_bad} beyond {REL_TOL}")
+    # OBSERVED (r02): 4 of 2 560 000 pixels on random_scene, 0 on the others. std::cos(float) / std::sin(float)
+    # in random_on_hemisphere are glibc's cosf / sinf (< 1 ulp, not correctly rounded); parity mode rounds the double
+    # result once. A one-ulp difference in a scattered direction is invisible in the pixel -- unless a later bounce
+    # lands within that ulp of a checker-square edge or a silhouette and takes the other branch (all four pixels are
+    # deep, dark paths whose radiance differs by the 0.9 / 0.1 checker ratio). Budget: 1e-5 of the pixels.
+    assert ref.mean() > 0.01 and n_bad <= 1e-5 * n, (config, n_bad, worst)
+    assert res.stats["rays"] <= st["rays"]

@@ -1732,6 +1732,8 @@ static int scene_create_impl(const tpt_scene_desc *d, int device, tpt_scene **ou
       if (k == TPT_NODE_BVH && list_until >= 0) simple = false;
       if (k == TPT_NODE_LIST && list_until < 0) list_until = d->nodes[i].end_or_prim;
     }
+    if (const char *e = std::getenv("TPT_PARITY_SKIP")) // TPT_PARITY_SKIP=0: keep the frame replay (A/B and test use)
+      if (e[0] == '0') simple = false;
     L.tree_simple = simple ? 1 : 0;
   }
   s->fbvh_has_moving = fb.has_moving;
