@@ -34,6 +34,9 @@ namespace tptd {
 #ifndef TPT_EXACT_DOUBLE_ROOTS
 #define TPT_EXACT_DOUBLE_ROOTS 1 // FAST mode, huge "wall" spheres: roots in double like the reference (0: IEEE fp32)
 #endif
+#ifndef TPT_CAMERA_BLOCK_LOOP
+#define TPT_CAMERA_BLOCK_LOOP 0 // 1: camera stage draws taken block by block from one Philox expansion site in a loop instead of Rng::next() + the out-of-line refill. Measured (r02, same box, Cornell A): +0.2 % unculled, -2.1 % with the pixel-bundle test (the library default), parity +-0: left off
+#endif
 #ifndef TPT_EAGER_CAMERA_BLOCK
 #define TPT_EAGER_CAMERA_BLOCK 2 // second Philox block of the camera stage expanded in line: 0 never, 1 always, 2 PARITY kernels only
 #endif
@@ -1607,8 +1610,63 @@ struct CamView {
   float lens_radius, time0, time1;
 };
 
+TPT_DEV float u01(uint32_t x) { return (float)(x >> 8) * 5.9604644775390625e-8f; } // Rng::next()'s mapping
+
 template <bool PAR>
 TPT_DEV Ray camera_sample(const CamView &C, int i, int j, int nx, int ny, Rng &g) {
+#if TPT_CAMERA_BLOCK_LOOP
+  // The camera stage's draws in stream order: jitter u, v; lens pairs (y, x) until one lies in the unit
+  // disk (random_in_unit_disk, src/utils.cc:13-19: vec3(drand_r(), drand_r(), 0) -> y drawn first); the
+  // shutter time when the shutter is open. They are taken block by block from ONE expansion site of the
+  // Philox function inside a loop: every lane runs the trip for block 0 (u, v, first pair), the 21 % whose
+  // first lens sample falls outside the disk -- or every lane, with an open shutter -- run another.
+  // Same draws at the same stream positions as g.next() would deliver (pairs never straddle a block).
+  // Meant to replace a block expansion plus an out-of-line refill that runs at 4.6 of 32 lanes in nearly
+  // every camera chunk (r02 capture: 4.3 % of the fast kernel's warp instructions, + 2.1 % in next()'s
+  // refill test); measured, it does not pay (see the macro) -- kept as the alternative it was tested as.
+  const bool need_time = C.time1 != C.time0;
+  float r_u = 0.f, r_v = 0.f, px = 0.f, py = 0.f, rt = 0.f;
+  int phase = 0; // 0: u, v and the first pair; 1: another pair; 2: the shutter time; 3: done
+  for (uint32_t blk = 0;; blk++) {
+    uint32_t o[4];
+    philox4x32_10_rk(g.pixel, g.sample, 0u, blk, g.rk, o);
+    int k = 0; // draws of this block consumed so far
+    if (phase == 0) {
+      r_u = u01(o[0]);
+      r_v = u01(o[1]);
+      py = 2.0f * u01(o[2]) - 1.0f;
+      px = 2.0f * u01(o[3]) - 1.0f;
+      k = 4;
+      phase = (px * px + py * py >= 1.0f) ? 1 : (need_time ? 2 : 3);
+    } else {
+      if (phase == 1) {
+        py = 2.0f * u01(o[0]) - 1.0f;
+        px = 2.0f * u01(o[1]) - 1.0f;
+        k = 2;
+        if (px * px + py * py >= 1.0f) {
+          py = 2.0f * u01(o[2]) - 1.0f;
+          px = 2.0f * u01(o[3]) - 1.0f;
+          k = 4;
+        }
+        phase = (px * px + py * py >= 1.0f) ? 1 : (need_time ? 2 : 3);
+      }
+      if (phase == 2 && k < 4) {
+        rt = u01(k == 0 ? o[0] : o[2]);
+        phase = 3;
+      }
+    }
+    if (phase == 3) break;
+  }
+  g.stage = 0u;
+  float s, t;
+  if (PAR) {
+    s = (float)(((double)(float)i + (double)r_u) / (double)(float)nx);
+    t = (float)(((double)(float)j + (double)r_v) / (double)(float)ny);
+  } else {
+    s = ((float)i + r_u) / (float)nx;
+    t = ((float)j + r_v) / (float)ny;
+  }
+#else
   g.set_stage(0u);
   float r_u = g.next();
   float r_v = g.next();
@@ -1628,9 +1686,6 @@ TPT_DEV Ray camera_sample(const CamView &C, int i, int j, int nx, int ny, Rng &g
     px = 2.0f * x - 1.0f;
     py = 2.0f * y - 1.0f;
   }
-  // Block 0 is used up. In nearly every warp some lane redraws its lens sample (21 % of the draws
-  // fall outside the disk) or draws a shutter time: the out-of-line refill then ran for ~6 of the 32
-  // lanes in every camera chunk (ncu, r01 capture). Block 1 is expanded here for all lanes instead.
   if (TPT_EAGER_CAMERA_BLOCK == 1 || (TPT_EAGER_CAMERA_BLOCK == 2 && PAR)) g.next_block_inline();
   while (px * px + py * py >= 1.0f) {
     float y = g.next();
@@ -1638,11 +1693,13 @@ TPT_DEV Ray camera_sample(const CamView &C, int i, int j, int nx, int ny, Rng &g
     px = 2.0f * x - 1.0f;
     py = 2.0f * y - 1.0f;
   }
+  const bool need_time = C.time1 != C.time0;
+  float rt = need_time ? g.next() : 0.f;
+#endif
   float rdx = C.lens_radius * px, rdy = C.lens_radius * py;
   V3 offset = C.u * rdx + C.v * rdy;
   Ray r;
-  if (C.time1 != C.time0) {
-    float rt = g.next();
+  if (need_time) {
     r.time = PAR ? (float)((double)C.time0 + (double)rt * (double)(C.time1 - C.time0))
                  : C.time0 + rt * (C.time1 - C.time0);
   } else {

@@ -15,6 +15,13 @@ for mode, spp in ((T.MODE_PARITY, 256), (T.MODE_FAST, 1024)):
             st = sc.render_device(cam, T.make_params(1200, 1200, spp, depth, mode=mode, seed=1, kernel=T.KERNEL_WAVEFRONT, bundle_cull=False))
             best = max(best, st["paths"] / st["render_ms"] / 1e3)
         out.append(f"{'parity' if mode == T.MODE_PARITY else 'fast'}{'A' if depth == 15 else 'B'} {best:.0f}")
+cam = T.cornell_camera(1200, 1200, fov=90.0)
+for mode, spp, name in ((T.MODE_FAST, 1024, "fastA+cull"), (T.MODE_PARITY, 256, "parityA+cull")):
+    best = 0
+    for i in range(3):
+        st = sc.render_device(cam, T.make_params(1200, 1200, spp, 15, mode=mode, seed=1, kernel=T.KERNEL_WAVEFRONT, bundle_cull=True))
+        best = max(best, st["paths"] / st["render_ms"] / 1e3)
+    out.append(f"{name} {best:.0f}")
 print("  ".join(out))
 PY
 for d in gpurun_variants/v*; do
