@@ -1676,6 +1676,19 @@ static int scene_create_impl(const tpt_scene_desc *d, int device, tpt_scene **ou
     fb = FastBvh();
     wide.clear();
   }
+  if (!TPT_FBVH_WIDE && !fb.nodes.empty()) {
+    // binary tree: the traversal defers at most one child per level. A tree deeper than the stack (binned SAH can
+    // split 1 : n-1 level after level on geometrically spaced primitives) falls back to the reference's own tree
+    // instead of overflowing the per-lane stack.
+    std::function<int(int32_t)> depth_of = [&](int32_t node) -> int {
+      if (node < 0) return 0;
+      int32_t c0, c1;
+      std::memcpy(&c0, &fb.nodes[(size_t)node * 16 + 12], 4);
+      std::memcpy(&c1, &fb.nodes[(size_t)node * 16 + 13], 4);
+      return 1 + std::max(depth_of(c0), depth_of(c1));
+    };
+    if (depth_of(0) + 2 > TPT_FBVH_STACK) fb = FastBvh();
+  }
   if (TPT_FBVH_WIDE) append(blob, wide.data(), wide.size());
   else append(blob, fb.nodes.data(), fb.nodes.size());
   L.off_fleaf = words();
