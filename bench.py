@@ -224,41 +224,50 @@ def ref_camera_args(c):
 
 
 # ---------------------------------------------------------------------------- CPU reference
-def oracle_ref_module():
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import oracle_ref as O
-    return O
+REF_BENCH = os.path.join(ROOT, "oracle", "_ref", "ref_bench")
+
+
+def ref_bench_run(c, spp, threads, repeats=1):
+    """One run of oracle/_ref/ref_bench (the reference's sources + the sample-loop harness as a non-PIC executable,
+    oracle/ref_bench_main.cc): [(seconds, paths, threads)] per repeat, scene built once per process."""
+    cmd = [REF_BENCH, c["scene"], str(c["nx"]), str(c["ny"]), str(spp), str(c["depth"]), str(c["fov"]), c["camera"], str(threads),
+           str(repeats)]
+    if c["scene"] == "earth":
+        cmd.append(os.path.join(ROOT, "tests", "golden", "earthmap.jpg"))
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=1800)
+    if r.returncode != 0:
+        raise RuntimeError(f"ref_bench failed: {r.stderr[-300:]}")
+    out = []
+    for line in r.stdout.splitlines():
+        m = re.match(r"seconds ([0-9.eE+-]+) paths (\d+) threads (\d+)", line)
+        if m:
+            out.append((float(m.group(1)), int(m.group(2)), int(m.group(3))))
+    return out
 
 
 def cpu_reference_sample(c, target_seconds, threads=0):
-    """The reference's own sample loop (unmodified color()/hit/scatter compiled from
-    /root/reference into oracle/_ref/libtptref.so, loop restated in oracle/ref_harness.cc from
-    main.cpp:115-134) on all host threads, full frame at a bounded spp."""
-    O = oracle_ref_module()
-    if not O.available(False):
+    """The reference's own sample loop (unmodified color()/hit/scatter compiled from /root/reference, loop restated in
+    oracle/ref_harness.cc from main.cpp:115-134) on all host threads, full frame at a bounded spp. Timed through
+    oracle/_ref/ref_bench, built non-PIC like the reference's own Release executable."""
+    if not os.path.exists(REF_BENCH):
         return None
-    rs = O.RefScene(c["scene"], det=False, image=scene_image(c))
-    cam = ref_camera_args(c)
-    nx, ny = c["nx"], c["ny"]
     if threads == 0:
-        # "all the host threads it can use": std::thread::hardware_concurrency() reports the affinity mask, which on
-        # a container limited by CPU quota (or with SMT siblings outside the mask) is not the count that runs fastest
-        # (r02: the stock binary's 1200 row threads out-ran a 16-thread pool on the GPU box). Probe 1x / 2x / 4x.
+        # "all the host threads it can use": probe 1x / 2x / 4x the visible core count, keep the fastest
         base = os.cpu_count() or 1
         best = None
         for t in (base, 2 * base, 4 * base):
-            _, _, st = rs.render(cam, nx, ny, 1, c["depth"], deterministic=False, threads=t, count_rays=False)
-            if best is None or st["seconds"] < best[1]:
-                best = (t, st["seconds"])
+            sec, _, _ = ref_bench_run(c, 1, t)[0]
+            if best is None or sec < best[1]:
+                best = (t, sec)
         threads = best[0]
-    _, _, st = rs.render(cam, nx, ny, 1, c["depth"], deterministic=False, threads=threads, count_rays=False)
-    per_spp = st["seconds"]
+    per_spp = ref_bench_run(c, 1, threads)[0][0]
     spp = int(max(1, min(64, c["spp"], round(target_seconds / max(per_spp, 1e-3)))))
-    _, _, st = rs.render(cam, nx, ny, spp, c["depth"], deterministic=False, threads=threads, count_rays=False)
-    return {"value": st["paths"] / st["seconds"] / 1e6, "unit": "Mpaths/s", "cores": st["threads"], "kind": "reference",
-            "sample": f"config {c['id']} ({c['scene']}) full {nx}x{ny} frame at {spp} spp ({st['paths']} paths, {st['seconds']:.1f} s): "
-                      f"reference color()/hit/scatter (oracle/_ref/libtptref.so, mt19937 drand_r) on {st['threads']} threads",
-            "seconds": st["seconds"], "spp": spp, "_scene": rs, "_cam": cam, "_threads": threads}
+    sec, paths, nthreads = ref_bench_run(c, spp, threads)[0]
+    return {"value": paths / sec / 1e6, "unit": "Mpaths/s", "cores": nthreads, "kind": "reference",
+            "sample": f"config {c['id']} ({c['scene']}) full {c['nx']}x{c['ny']} frame at {spp} spp ({paths} paths, {sec:.1f} s): "
+                      f"reference color()/hit/scatter (oracle/_ref/ref_bench: the reference's sources built like its Release "
+                      f"executable, mt19937 drand_r) on {nthreads} threads of {os.cpu_count()} cores",
+            "seconds": sec, "spp": spp, "_threads": threads}
 
 
 def stock_reference_fit(c, budget_s=40.0):
@@ -336,8 +345,11 @@ def program_e2e(c, mode):
                     return {"error": (r.stderr or r.stdout)[-300:]}
                 m = re.search(r"^time:\s*([0-9.eE+-]+)\s*s", r.stdout, re.M)  # not the bogus "estimate time:" line (main.cpp:160-172)
                 g = re.search(r"gpu render:\s*([0-9.eE+-]+)\s*s", r.stdout)
+                up = re.search(r"flatten \+ upload \+ render \+ download:\s*([0-9.eE+-]+)\s*s", r.stdout)
+                of = re.search(r"output files:\s*([0-9.eE+-]+)\s*s", r.stdout)
                 row = {"time_line_s": float(m.group(1)) if m else None, "process_wall_s": wall,
                        "gpu_render_s": float(g.group(1)) if g else None,
+                       "render_call_s": float(up.group(1)) if up else None, "output_files_s": float(of.group(1)) if of else None,
                        "ppm_bytes": os.path.getsize(os.path.join(d, "img.ppm")),
                        "jpg_bytes": os.path.getsize(os.path.join(d, "img.jpg")) if os.path.exists(os.path.join(d, "img.jpg")) else 0}
                 if best is None or (row["time_line_s"] or 1e9) < (best["time_line_s"] or 1e9):
@@ -346,8 +358,9 @@ def program_e2e(c, mode):
         finally:
             shutil.rmtree(d, ignore_errors=True)
     out["note"] = ("Path_tracer_b200 in a scratch directory, generated config.ini, best of 2 runs; time_line_s = the program's own "
-                   "`time:` line (flatten + scene upload + render + PPM write, as main.cpp:108-221 brackets it); process_wall_s adds "
-                   "process start, CUDA context creation and the JPEG contact sheet")
+                   "`time:` line (flatten + scene upload + render + PPM write, as main.cpp:108-221 brackets it; render_call_s and "
+                   "output_files_s are its two parts); process_wall_s adds process start, CUDA context creation (on a second host "
+                   "thread while the scene is built) and the JPEG contact sheet")
     return out
 
 
@@ -359,16 +372,13 @@ def run_reference_arm(args, rank, world):
     per_step = max(4.0, min(30.0, 150.0 / max(total, 1)))
     first = cpu_reference_sample(c, per_step)
     if first is None:
-        emit({"impl": "reference", "unavailable": "oracle/_ref/libtptref.so is not built"})
+        emit({"impl": "reference", "unavailable": "oracle/_ref/ref_bench is not built"})
         return
-    rs, cam, spp = first["_scene"], first["_cam"], first["spp"]
+    spp = first["spp"]
     nx, ny = c["nx"], c["ny"]
-    secs = []
     paths = nx * ny * spp
-    for i in range(total):
-        _, _, st = rs.render(cam, nx, ny, spp, c["depth"], deterministic=False, threads=first["_threads"], count_rays=False)
-        if i >= args.warmup:
-            secs.append(st["seconds"])
+    runs = ref_bench_run(c, spp, first["_threads"], repeats=total)  # scene built once, `total` renders
+    secs = [sec for sec, _, _ in runs[args.warmup:]]
     t = sum(secs)
     value = paths * len(secs) / t / 1e6
     cpu = {"value": value, "unit": "Mpaths/s", "cores": first["cores"], "kind": "reference", "sample": first["sample"]}

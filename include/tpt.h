@@ -260,6 +260,9 @@ typedef struct tpt_scene tpt_scene; /* opaque: owns the device copies */
 
 int tpt_api_version(void);
 int tpt_device_count(void);
+/* creates the CUDA context of `device` now instead of inside the first tpt_scene_create (a few hundred ms in a
+ * fresh process): a driver calls it from a second host thread while it parses config.ini and builds the scene */
+int tpt_device_warm(int device);
 const char *tpt_last_error(void);
 
 /* copies every array of `desc` (host and device side); the caller may free its arrays afterwards */

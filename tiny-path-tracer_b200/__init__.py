@@ -39,7 +39,7 @@ STATUS = {0: "TPT_OK", -1: "TPT_ERR_INVALID", -2: "TPT_ERR_CUDA", -3: "TPT_ERR_N
 
 # every symbol include/tpt.h declares (checked by tests/test_abi.py)
 C_ABI_SYMBOLS = [
-    "tpt_api_version", "tpt_device_count", "tpt_last_error", "tpt_scene_create", "tpt_scene_destroy",
+    "tpt_api_version", "tpt_device_count", "tpt_device_warm", "tpt_last_error", "tpt_scene_create", "tpt_scene_destroy",
     "tpt_intersect_batch", "tpt_render", "tpt_render_device", "tpt_render_fetch", "tpt_get_stats",
     "tpt_device_buffers", "tpt_render_multi",
     "tpt_debug_philox", "tpt_debug_texture", "tpt_debug_small_scene", "tpt_debug_fp32_peak",

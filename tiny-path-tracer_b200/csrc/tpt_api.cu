@@ -1511,6 +1511,18 @@ int tpt_device_count(void) {
 
 const char *tpt_last_error(void) { return g_error.c_str(); }
 
+int tpt_device_warm(int device) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(TPT_ERR_NO_DEVICE, "no CUDA device available (this library has no CPU path)");
+  }
+  if (device < 0 || device >= ndev) return fail(TPT_ERR_INVALID, "device ordinal out of range");
+  CK(cudaSetDevice(device));
+  CK(cudaFree(nullptr)); // forces context creation
+  return TPT_OK;
+}
+
 static int scene_create_impl(const tpt_scene_desc *d, int device, tpt_scene **out, tpt_scene **partial);
 
 int tpt_scene_create(const tpt_scene_desc *d, int device, tpt_scene **out) {
