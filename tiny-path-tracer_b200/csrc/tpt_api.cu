@@ -1070,7 +1070,7 @@ int run_plan(tpt_scene *s, Plan &plan, bool want_sum, bool want_rgb8, bool want_
   int bps = 0;
   const bool media = s->n_mediums > 0;
   const bool small = (plan.parity ? s->flat.enabled != 0 : s->small.enabled != 0) && !media;
-  const bool trace = TPT_TRACE_ENABLE && !plan.parity && media && A.scene.n_fbvh > 0 && A.scene.fbvh_time_ok; // SAH BVH + media: 2-CTA variant with dynamic ray hand-out
+  const bool trace = TPT_TRACE_ENABLE && !plan.parity && (media || TPT_TRACE_ALL) && A.scene.n_fbvh > 0 && A.scene.fbvh_time_ok; // SAH BVH + media: 2-CTA variant with dynamic ray hand-out
   if (plan.wavefront)
     CK(plan.parity ? wave_occupancy_parity(A, small, s->use_smem, media, trace, &bps) : wave_occupancy_fast(A, small, s->use_smem, media, trace, &bps));
   else
@@ -1251,7 +1251,7 @@ int launch_batch(tpt_scene *s, const tpt_camera *cam, const tpt_render_params *p
   int bps = 0;
   const bool media = s->n_mediums > 0;
   const bool small = (plan.parity ? s->flat.enabled != 0 : s->small.enabled != 0) && !media;
-  const bool trace = TPT_TRACE_ENABLE && !plan.parity && media && A.scene.n_fbvh > 0 && A.scene.fbvh_time_ok; // SAH BVH + media: 2-CTA variant with dynamic ray hand-out
+  const bool trace = TPT_TRACE_ENABLE && !plan.parity && (media || TPT_TRACE_ALL) && A.scene.n_fbvh > 0 && A.scene.fbvh_time_ok; // SAH BVH + media: 2-CTA variant with dynamic ray hand-out
   if (plan.wavefront)
     CK(plan.parity ? wave_occupancy_parity(A, small, s->use_smem, media, trace, &bps) : wave_occupancy_fast(A, small, s->use_smem, media, trace, &bps));
   else
@@ -1678,7 +1678,6 @@ static int scene_create_impl(const tpt_scene_desc *d, int device, tpt_scene **ou
   s->n_mediums = L.n_mediums;
   FastBvh fb;
   if (count_root_surface_prims(d, n_root) > TPT_SMALL_MAX_PRIMS) build_fast_bvh(d, n_root, fb);
-  L.off_fbvh = words();
   int fbvh_depth = 0;
   std::vector<float> wide;
   if (TPT_FBVH_WIDE) collapse_to_bvh4(fb, wide, fbvh_depth);
@@ -1701,18 +1700,23 @@ static int scene_create_impl(const tpt_scene_desc *d, int device, tpt_scene **ou
     };
     if (depth_of(0) + 2 > TPT_FBVH_STACK) fb = FastBvh();
   }
+  // nodes and leaf records are 64 bytes each and 64-byte aligned: a lane fetches one with two 256-bit loads
+  // (two L1 wavefronts instead of four: the BVH kernels' L1 data pipe was as busy as their issue slots)
+  while (words() % 4 != 0) blob.insert(blob.end(), 16, 0);
+  L.off_fbvh = words();
   if (TPT_FBVH_WIDE) append(blob, wide.data(), wide.size());
   else append(blob, fb.nodes.data(), fb.nodes.size());
+  while (words() % 4 != 0) blob.insert(blob.end(), 16, 0);
   L.off_fleaf = words();
   {
-    // leaf records in leaf order, 3 float4 each (read by closest_hit_fbvh):
+    // leaf records in leaf order, 4 float4 each (read by closest_hit_fbvh):
     //   q0 = primitive words p[0..3]; q1 = {kind | exact << 8, primitive id, chain, rect k or time0};
-    //   q2 = moving sphere {center1, time1}
-    std::vector<float> rec(fb.leaf_prims.size() * 12, 0.f);
+    //   q2 = moving sphere {center1, time1}; q3 = padding
+    std::vector<float> rec(fb.leaf_prims.size() * 16, 0.f);
     for (size_t i = 0; i < fb.leaf_prims.size(); i++) {
       const int32_t id = fb.leaf_prims[i];
       const tpt_prim &p = d->prims[id];
-      float *q = &rec[i * 12];
+      float *q = &rec[i * 16];
       std::memcpy(q, p.p, 16);
       const bool sph = p.kind == TPT_PRIM_SPHERE || p.kind == TPT_PRIM_MOVING_SPHERE;
       int32_t kf = p.kind | (sph && p.p[3] >= 500.0f ? 0x100 : 0); // huge "wall" spheres: exact roots

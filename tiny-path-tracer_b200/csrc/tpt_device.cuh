@@ -131,6 +131,7 @@ struct SceneView {
   const SceneLayout *L;    // offsets / counts / texture objects (constant bank)
   const SmallScene *small; // constant bank; valid when a FAST kernel is instantiated with SMALL
   const FlatTree *flat;    // constant bank; valid when a PARITY kernel is instantiated with SMALL
+  bool wide_loads = false; // blob is the GLOBAL copy: SAH BVH nodes / leaf records may be fetched with 256-bit loads
 };
 
 struct V3 {
@@ -1068,6 +1069,15 @@ TPT_DEV bool sphere_test_quick(V3 center, float radius, const XRay &x, float tmi
 #define TPT_FBVH_SORT 1 // BVH4: deferred children pushed far-to-near (0: in slot order)
 #endif
 #define TPT_FBVH_STACK (TPT_FBVH_WIDE ? 48 : 32)
+#ifndef TPT_FBVH_LD256
+#define TPT_FBVH_LD256 1 // 64-byte nodes / leaf records of the GLOBAL blob: two 256-bit loads (sm_100: LDG.E.256) instead of four 128-bit ones
+#endif
+// 32 bytes of the read-only scene blob, 32-byte aligned, global memory only
+TPT_DEV void ld256(const float4 *p, float4 &lo, float4 &hi) {
+  asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+      : "=f"(lo.x), "=f"(lo.y), "=f"(lo.z), "=f"(lo.w), "=f"(hi.x), "=f"(hi.y), "=f"(hi.z), "=f"(hi.w)
+      : "l"(p));
+}
 struct FbvhTrav {
   float ix, iy, iz, ox, oy, oz; // t = p * inv + (-o * inv)
   float best;
@@ -1083,6 +1093,69 @@ struct FbvhTrav {
     sp = 0;
   }
   TPT_DEV bool done() const { return node == TPT_FBVH_DONE; }
+  // one inner node of the binary tree: both children's boxes, nearer child first
+  TPT_DEV void inner_one(const float4 *N, float tmin, int *stack, bool wide) {
+    float4 a, b, c, d;
+    if (TPT_FBVH_LD256 && wide) {
+      ld256(N + 4 * node, a, b);
+      ld256(N + 4 * node + 2, c, d);
+    } else {
+      a = N[4 * node]; b = N[4 * node + 1]; c = N[4 * node + 2]; d = N[4 * node + 3];
+    }
+    // child 0: lo = (a.x,a.y,a.z) hi = (a.w,b.x,b.y) ; child 1: lo = (b.z,b.w,c.x) hi = (c.y,c.z,c.w)
+    float t0x = fmaf(a.x, ix, ox), t1x = fmaf(a.w, ix, ox);
+    float t0y = fmaf(a.y, iy, oy), t1y = fmaf(b.x, iy, oy);
+    float t0z = fmaf(a.z, iz, oz), t1z = fmaf(b.y, iz, oz);
+    float n0 = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), tmin));
+    float f0 = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), best));
+    t0x = fmaf(b.z, ix, ox); t1x = fmaf(c.y, ix, ox);
+    t0y = fmaf(b.w, iy, oy); t1y = fmaf(c.z, iy, oy);
+    t0z = fmaf(c.x, iz, oz); t1z = fmaf(c.w, iz, oz);
+    float n1 = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), tmin));
+    float f1 = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), best));
+    const bool h0 = n0 <= f0, h1 = n1 <= f1;
+    int i0 = __float_as_int(d.x), i1 = __float_as_int(d.y);
+    if (h0 && h1) {
+      if (n1 < n0) { int t = i0; i0 = i1; i1 = t; } // i0 = nearer
+      stack[sp++] = i1;
+      node = i0;
+    } else if (h0) node = i0;
+    else if (h1) node = i1;
+    else node = sp > 0 ? stack[--sp] : TPT_FBVH_DONE;
+  }
+  // the primitives of the leaf in `node`, then the next deferred node
+  TPT_DEV void leaf(const SceneView &S, const Ray &r, float tmin, int *stack) {
+    // leaf: ~node = first << 3 | (count - 1); records of 4 float4 (tpt_api.cu, off_fleaf)
+    const int code = ~node, count = (code & 7) + 1;
+    const float4 *Q = S.blob + S.L->off_fleaf + 4 * (code >> 3);
+    XRay x;
+    x.chain = -1;
+    for (int k = 0; k < count; k++, Q += 4) {
+      float4 g, h;
+      if (TPT_FBVH_LD256 && S.wide_loads) ld256(Q, g, h);
+      else { g = Q[0]; h = Q[1]; }
+      const int kf = __float_as_int(h.x), kind = kf & 0xff;
+      to_chain<false>(S, r, __float_as_int(h.z), x);
+      float t;
+      bool hit;
+      if (kind <= TPT_PRIM_MOVING_SPHERE) {
+        V3 cen = mk(g.x, g.y, g.z);
+        if (kind == TPT_PRIM_MOVING_SPHERE) {
+          const float4 m = Q[2];
+          cen = moving_center(g, make_float4(m.x, m.y, m.z, h.w), make_float4(m.w, 0.f, 0.f, 0.f), r.time);
+        }
+        hit = (kf & 0x100) ? sphere_test_exact_fast(cen, g.w, x, tmin, best, t)
+                           : sphere_test_quick(cen, g.w, x, tmin, best, t);
+      } else {
+        hit = rect_test<false>(kind - TPT_PRIM_XY_RECT, g, h.w, x, tmin, best, t);
+      }
+      if (hit) {
+        best = t;
+        best_prim = __float_as_int(h.y);
+      }
+    }
+    node = sp > 0 ? stack[--sp] : TPT_FBVH_DONE;
+  }
   // descend to the next leaf (or run out of nodes), then test that leaf's primitives
   TPT_DEV void step(const SceneView &S, const Ray &r, float tmin, int *stack) {
     const float4 *N = S.blob + S.L->off_fbvh;
@@ -1142,60 +1215,9 @@ struct FbvhTrav {
 #endif
     }
 #else
-    while ((unsigned)node < (unsigned)TPT_FBVH_DONE) {
-      const float4 a = N[4 * node], b = N[4 * node + 1], c = N[4 * node + 2], d = N[4 * node + 3];
-      // child 0: lo = (a.x,a.y,a.z) hi = (a.w,b.x,b.y) ; child 1: lo = (b.z,b.w,c.x) hi = (c.y,c.z,c.w)
-      float t0x = fmaf(a.x, ix, ox), t1x = fmaf(a.w, ix, ox);
-      float t0y = fmaf(a.y, iy, oy), t1y = fmaf(b.x, iy, oy);
-      float t0z = fmaf(a.z, iz, oz), t1z = fmaf(b.y, iz, oz);
-      float n0 = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), tmin));
-      float f0 = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), best));
-      t0x = fmaf(b.z, ix, ox); t1x = fmaf(c.y, ix, ox);
-      t0y = fmaf(b.w, iy, oy); t1y = fmaf(c.z, iy, oy);
-      t0z = fmaf(c.x, iz, oz); t1z = fmaf(c.w, iz, oz);
-      float n1 = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), tmin));
-      float f1 = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), best));
-      const bool h0 = n0 <= f0, h1 = n1 <= f1;
-      int i0 = __float_as_int(d.x), i1 = __float_as_int(d.y);
-      if (h0 && h1) {
-        if (n1 < n0) { int t = i0; i0 = i1; i1 = t; } // i0 = nearer
-        stack[sp++] = i1;
-        node = i0;
-      } else if (h0) node = i0;
-      else if (h1) node = i1;
-      else node = sp > 0 ? stack[--sp] : TPT_FBVH_DONE;
-    }
+    while ((unsigned)node < (unsigned)TPT_FBVH_DONE) inner_one(N, tmin, stack, S.wide_loads);
 #endif
-    if (node < 0) {
-      // leaf: ~node = first << 3 | (count - 1); records of 3 float4 (tpt_api.cu, off_fleaf)
-      const int code = ~node, count = (code & 7) + 1;
-      const float4 *Q = S.blob + S.L->off_fleaf + 3 * (code >> 3);
-      XRay x;
-      x.chain = -1;
-      for (int k = 0; k < count; k++, Q += 3) {
-        const float4 g = Q[0], h = Q[1];
-        const int kf = __float_as_int(h.x), kind = kf & 0xff;
-        to_chain<false>(S, r, __float_as_int(h.z), x);
-        float t;
-        bool hit;
-        if (kind <= TPT_PRIM_MOVING_SPHERE) {
-          V3 cen = mk(g.x, g.y, g.z);
-          if (kind == TPT_PRIM_MOVING_SPHERE) {
-            const float4 m = Q[2];
-            cen = moving_center(g, make_float4(m.x, m.y, m.z, h.w), make_float4(m.w, 0.f, 0.f, 0.f), r.time);
-          }
-          hit = (kf & 0x100) ? sphere_test_exact_fast(cen, g.w, x, tmin, best, t)
-                             : sphere_test_quick(cen, g.w, x, tmin, best, t);
-        } else {
-          hit = rect_test<false>(kind - TPT_PRIM_XY_RECT, g, h.w, x, tmin, best, t);
-        }
-        if (hit) {
-          best = t;
-          best_prim = __float_as_int(h.y);
-        }
-      }
-      node = sp > 0 ? stack[--sp] : TPT_FBVH_DONE;
-    }
+    if (node < 0) leaf(S, r, tmin, stack);
   }
 };
 
@@ -1204,6 +1226,45 @@ TPT_DEV bool closest_hit_fbvh(const SceneView &S, const Ray &r, float tmin, floa
   int stack[TPT_FBVH_STACK];
   tv.start(r, tmax);
   while (!tv.done()) tv.step(S, r, tmin, stack);
+  t_out = tv.best;
+  prim_out = tv.best_prim;
+  return tv.best_prim >= 0;
+}
+
+// Vote-scheduled traversal (binary tree). In the while-while form a warp's descent lasts as long as its
+// slowest lane's: the number of inner nodes between two leaves is close to geometrically distributed, the
+// maximum of 32 such draws is ~3.5 times their mean, and the descent loop of the BVH scenes ran at 9.8 of 32
+// lanes, the leaf tests at 5-8 (profiles/r02_ncu_full_random_scene_lines.txt). Here a lane that has reached a
+// leaf simply WAITS (node < 0 is its whole state) while the others keep descending, and the warp switches
+// to the leaf code once the waiting lanes outnumber the descending ones TPT_VOTE_NUM : TPT_VOTE_DEN; both
+// code paths then run with most of their lanes. Must be called by all 32 lanes (live = has a ray).
+#ifndef TPT_FBVH_VOTE
+#define TPT_FBVH_VOTE 0 // plain wavefront kernels of the SAH BVH scenes: 1 = vote-scheduled walk, 0 = per-lane while-while
+#endif
+#ifndef TPT_VOTE_NUM
+#define TPT_VOTE_NUM 1
+#endif
+#ifndef TPT_VOTE_DEN
+#define TPT_VOTE_DEN 2 // descend while more than NUM / (NUM + DEN) of the walking lanes still do
+#endif
+TPT_DEV bool closest_hit_fbvh_vote(const SceneView &S, const Ray &r, bool live, float tmin, float tmax, float &t_out, int &prim_out) {
+  FbvhTrav tv;
+  int stack[TPT_FBVH_STACK];
+  tv.start(r, tmax);
+  if (!live) tv.node = TPT_FBVH_DONE;
+  const float4 *N = S.blob + S.L->off_fbvh;
+  for (;;) {
+    const int live = __popc(__ballot_sync(0xffffffffu, !tv.done()));
+    if (live == 0) break;
+    // descend while more than this many lanes still do; the others wait at their leaf (or are done)
+    const int limit = live * TPT_VOTE_NUM / (TPT_VOTE_NUM + TPT_VOTE_DEN);
+    bool inner = (unsigned)tv.node < (unsigned)TPT_FBVH_DONE;
+    while (__popc(__ballot_sync(0xffffffffu, inner)) > limit) {
+      if (inner) tv.inner_one(N, tmin, stack, S.wide_loads);
+      inner = (unsigned)tv.node < (unsigned)TPT_FBVH_DONE;
+    }
+    if (tv.node < 0) tv.leaf(S, r, tmin, stack);
+  }
   t_out = tv.best;
   prim_out = tv.best_prim;
   return tv.best_prim >= 0;

@@ -27,6 +27,7 @@ __global__ void __launch_bounds__(128) intersect_kernel(const __grid_constant__ 
   extern __shared__ float4 sblob[];
   SceneView S;
   S.blob = stage_scene<SMEM>(A.scene, sblob);
+  S.wide_loads = !SMEM;
   S.L = &A.scene;
   S.small = &A.small;
   S.flat = &A.flat;
@@ -163,6 +164,7 @@ __global__ void __launch_bounds__(TPT_MEGA_THREADS) render_mega_kernel(const __g
   extern __shared__ float4 sblob[];
   SceneView S;
   S.blob = stage_scene<SMEM>(A.scene, sblob);
+  S.wide_loads = !SMEM;
   S.L = &A.scene;
   S.small = &A.small;
   S.flat = &A.flat;
@@ -289,6 +291,7 @@ render_wave_kernel(const __grid_constant__ RenderArgs A) {
   unsigned short *queue = reinterpret_cast<unsigned short *>(reinterpret_cast<char *>(sblob) + STATE_BYTES);
   SceneView S;
   S.blob = stage_scene<SMEM>(A.scene, sblob + (STATE_BYTES + QUEUE_BYTES) / 16); // > 64 KB: stays in global memory
+  S.wide_loads = !SMEM;
   S.L = &A.scene;
   S.small = &A.small;
   S.flat = &A.flat;
@@ -312,6 +315,8 @@ render_wave_kernel(const __grid_constant__ RenderArgs A) {
   const unsigned bins_per_tile = (unsigned)(TPT_TILE * TPT_TILE) * (unsigned)A.n_ranges;
   unsigned long long n_rays = 0, n_nan = 0, n_paths = 0, n_culled = 0;
 
+  int stack[TRACE ? TPT_FBVH_STACK + 3 : 1]; // TRACE: the lane's node stack + a parked walk (slot, node, stack pointer)
+  stack[TRACE ? TPT_FBVH_STACK : 0] = -1;
   for (int s = tid; s < NSLOT; s += THREADS) {
     SI(F_DEPTH, s) = -1;
     SI(F_K, s) = 0;
@@ -343,19 +348,43 @@ render_wave_kernel(const __grid_constant__ RenderArgs A) {
       // Measured (BVH scenes): the hand-out itself is worth 2-4 %; the variant's gain on
       // oneweek_final (+15 %) comes from running 2 CTAs/SM at 128 registers (no spills around the
       // media pass). random_scene is faster on the plain 3-CTA form, so only media scenes come here.
+      //
+      // TPT_TRACE_CARRY: a phase still ends with its longest rays, walked by a few lanes per warp while
+      // everybody else waits at the barrier (ray lengths spread over an order of magnitude, and a CTA
+      // has only three rays per lane to hand out). With the carry-over a warp LEAVES the phase once the
+      // counter is dry and fewer than TPT_TRACE_CARRY_K of its lanes still walk: those lanes park their
+      // walk (node, stack pointer and slot number in the tail of the lane's stack array, best hit so far
+      // in the slot) and resume it in the next iteration's extend phase, next to fresh rays. A parked
+      // slot carries TPT_SLOT_PARKED in its depth word and sits in no queue; TPT_SLOT_LATE marks one
+      // that finished in this phase, so that the hand-out does not give it away a second time.
       FbvhTrav tv;
-      int stack[TPT_FBVH_STACK];
       tv.node = TPT_FBVH_DONE;
       int ts = -1;
       Ray tr;
       tr.o = tr.d = mk(0, 0, 0);
       tr.time = 0.f;
-      bool dry = false;
+      bool dry = false, got_fresh = false;
+      if (TPT_TRACE_CARRY) {
+        ts = stack[TPT_FBVH_STACK];
+        if (ts >= 0) { // resume the parked walk
+          tr.o = mk(SF(F_OX, ts), SF(F_OY, ts), SF(F_OZ, ts));
+          tr.d = mk(SF(F_DX, ts), SF(F_DY, ts), SF(F_DZ, ts));
+          tr.time = SF(F_TIME, ts);
+          tv.start(tr, SF(F_HT, ts));
+          tv.best_prim = SI(F_HPRIM, ts);
+          tv.node = stack[TPT_FBVH_STACK + 1];
+          tv.sp = stack[TPT_FBVH_STACK + 2];
+        }
+      }
       for (;;) {
         const bool need = tv.done();
         if (need && ts >= 0) {
           SI(F_HPRIM, ts) = tv.best_prim;
           SF(F_HT, ts) = tv.best;
+          if (TPT_TRACE_CARRY) {
+            const int d = SI(F_DEPTH, ts);
+            if (d & TPT_SLOT_PARKED) SI(F_DEPTH, ts) = (d ^ TPT_SLOT_PARKED) | TPT_SLOT_LATE;
+          }
           ts = -1;
         }
         const unsigned m = __ballot_sync(FULL, need);
@@ -365,19 +394,53 @@ render_wave_kernel(const __grid_constant__ RenderArgs A) {
           if ((int)lane == leader) base = atomicAdd(&trace_next, __popc(m));
           base = __shfl_sync(FULL, base, leader);
           if (base >= NSLOT) dry = true;
+          bool took = false;
           if (need) {
             const int c = base + __popc(m & lt_mask);
-            if (c < NSLOT && SI(F_DEPTH, c) >= 0) {
+            if (c < NSLOT && (unsigned)SI(F_DEPTH, c) < (unsigned)TPT_SLOT_PARKED) {
               ts = c;
+              took = true;
               tr.o = mk(SF(F_OX, c), SF(F_OY, c), SF(F_OZ, c));
               tr.d = mk(SF(F_DX, c), SF(F_DY, c), SF(F_DZ, c));
               tr.time = SF(F_TIME, c);
               tv.start(tr, FLT_MAX);
             }
           }
+          if (TPT_TRACE_CARRY && !got_fresh) got_fresh = __ballot_sync(FULL, took) != 0u;
         }
-        if (dry && __ballot_sync(FULL, !tv.done()) == 0u) break;
+        if (dry) {
+          const unsigned walking = __ballot_sync(FULL, !tv.done());
+          // (a warp that received no fresh ray in this phase finishes what it has: the end of the launch)
+          if (walking == 0u || (TPT_TRACE_CARRY && got_fresh && __popc(walking) < TPT_TRACE_CARRY_K)) break;
+        }
+#if TPT_TRACE_VOTE
+        // vote-scheduled walk (closest_hit_fbvh_vote) between the hand-outs: lanes that reached a leaf wait
+        // while more than a share of the warp's walking lanes still descend, then the leaf tests run
+        // together; the loop returns to the hand-out above after every leaf pass
+        {
+          const float4 *N = S.blob + S.L->off_fbvh;
+          const int live = __popc(__ballot_sync(FULL, !tv.done()));
+          const int limit = live * TPT_VOTE_NUM / (TPT_VOTE_NUM + TPT_VOTE_DEN);
+          bool inner = (unsigned)tv.node < (unsigned)TPT_FBVH_DONE;
+          while (__popc(__ballot_sync(FULL, inner)) > limit) {
+            if (inner) tv.inner_one(N, A.t_min, stack, S.wide_loads);
+            inner = (unsigned)tv.node < (unsigned)TPT_FBVH_DONE;
+          }
+          if (tv.node < 0) tv.leaf(S, tr, A.t_min, stack);
+        }
+#else
         if (!tv.done()) tv.step(S, tr, A.t_min, stack);
+#endif
+      }
+      if (TPT_TRACE_CARRY) {
+        if (ts >= 0) { // park the walk
+          SI(F_DEPTH, ts) |= TPT_SLOT_PARKED;
+          SF(F_HT, ts) = tv.best;
+          SI(F_HPRIM, ts) = tv.best_prim;
+          stack[TPT_FBVH_STACK + 1] = tv.node;
+          stack[TPT_FBVH_STACK + 2] = tv.sp;
+        }
+        stack[TPT_FBVH_STACK] = ts;
       }
       __syncthreads();
     }
@@ -387,7 +450,23 @@ render_wave_kernel(const __grid_constant__ RenderArgs A) {
     for (int s0 = warp * 32; s0 < NSLOT; s0 += THREADS) {
       const int s = s0 + (int)lane;
       int cls = -2; // -2: nothing to do
-      const int depth_s = SI(F_DEPTH, s);
+      int depth_s = SI(F_DEPTH, s);
+      if (TRACE && TPT_TRACE_CARRY) {
+        if (depth_s >= 0 && (depth_s & TPT_SLOT_PARKED)) depth_s = -1; // its walk goes on in the next iteration
+        else if (depth_s >= 0 && (depth_s & TPT_SLOT_LATE)) SI(F_DEPTH, s) = depth_s ^= TPT_SLOT_LATE;
+      }
+      // SAH BVH scenes: the closest hit is found first, by all 32 lanes together (vote-scheduled walk)
+      constexpr bool VOTE = TPT_FBVH_VOTE && !PAR && !SMALL && !TRACE;
+      const bool voted = VOTE && A.scene.n_fbvh > 0 && A.scene.fbvh_time_ok;
+      float t_v = 0.f;
+      int prim_v = -1;
+      if (voted) {
+        Ray vr;
+        vr.o = mk(SF(F_OX, s), SF(F_OY, s), SF(F_OZ, s));
+        vr.d = mk(SF(F_DX, s), SF(F_DY, s), SF(F_DZ, s));
+        vr.time = SF(F_TIME, s);
+        closest_hit_fbvh_vote(S, vr, depth_s >= 0, A.t_min, FLT_MAX, t_v, prim_v);
+      }
       if (depth_s >= 0) {
         PathState ps;
         ps.ray.o = mk(SF(F_OX, s), SF(F_OY, s), SF(F_OZ, s));
@@ -406,6 +485,11 @@ render_wave_kernel(const __grid_constant__ RenderArgs A) {
         if (TRACE) {
           t = SF(F_HT, s);
           prim = SI(F_HPRIM, s);
+          if (MEDIA) rng.set_stage((uint32_t)ps.depth + 1u);
+          cls = extend_finish<PAR, MEDIA, TEX>(S, ps, A.max_depth, A.t_min, prim >= 0, t, prim, rad, rng, ndraw0);
+        } else if (voted) {
+          t = t_v;
+          prim = prim_v;
           if (MEDIA) rng.set_stage((uint32_t)ps.depth + 1u);
           cls = extend_finish<PAR, MEDIA, TEX>(S, ps, A.max_depth, A.t_min, prim >= 0, t, prim, rad, rng, ndraw0);
         } else {
@@ -646,6 +730,7 @@ render_wave_kernel(const __grid_constant__ RenderArgs A) {
 template <bool PAR> __global__ void texture_probe_kernel(const __grid_constant__ TextureProbeArgs A) {
   SceneView S;
   S.blob = A.scene.blob_global;
+  S.wide_loads = true;
   S.L = &A.scene;
   S.small = nullptr;
   S.flat = nullptr;

@@ -10,6 +10,23 @@
 #ifndef TPT_TRACE_ENABLE
 #define TPT_TRACE_ENABLE 1
 #endif
+#ifndef TPT_TRACE_ALL
+#define TPT_TRACE_ALL 0 // 1: every SAH BVH scene takes the "trace" variant in fast mode, 0: only scenes with participating media
+#endif
+#ifndef TPT_TRACE_VOTE
+#define TPT_TRACE_VOTE 1 // "trace" variant: vote-scheduled walk between the ray hand-outs (closest_hit_fbvh_vote; oneweek_final +5 %)
+#endif
+#ifndef TPT_TRACE_CARRY
+#define TPT_TRACE_CARRY 1 // "trace" variant: walks still running when the phase's rays are handed out carry over to the next iteration
+#endif
+#ifndef TPT_TRACE_CARRY_K
+#define TPT_TRACE_CARRY_K 8 // ... once fewer than this many lanes of the warp are still walking (8 / 16 / 24: 1 962 / 1 954 / 1 937 Mpaths/s on oneweek_final together with the vote)
+#endif
+#define TPT_SLOT_PARKED (1 << 20) // depth word of a slot whose walk is parked / finished after having been parked
+#define TPT_SLOT_LATE (1 << 21)
+#ifndef TPT_TRACE_THREADS
+#define TPT_TRACE_THREADS TPT_WAVE_THREADS
+#endif
 #ifndef TPT_TRACE_SLOTS
 #define TPT_TRACE_SLOTS 768    // path slots per CTA of the BVH ("trace") wavefront variant: 3 rays per lane to hand out
 #endif
@@ -70,7 +87,7 @@ namespace tptd {
 //    parity +6 %, and with three slots per thread the fast kernels gain another 3-5 % (fuller
 //    chunks, fewer barriers per path); parity prefers two slots per thread.
 //  * SAH-BVH / large scenes: 256 x 512 x 3 (r01 sweep), the media build 256 x 768 x 2 (128 registers).
-__host__ __device__ constexpr int wave_threads(bool small, bool trace) { return (small && !trace) ? TPT_SMALL_THREADS : TPT_WAVE_THREADS; }
+__host__ __device__ constexpr int wave_threads(bool small, bool trace) { return trace ? TPT_TRACE_THREADS : (small ? TPT_SMALL_THREADS : TPT_WAVE_THREADS); }
 // Two CTAs must fit the SM's 227 KB of shared memory together with their copies of the scene tables:
 // 1152 slots (108 KB of path state) leave room for the 4 KB tables of a constant-texture scene only; a
 // scene with Perlin tables (+7 KB) would drop to ONE resident CTA (r02: two_perlin_spheres 6 860 -> 4 720

@@ -21,6 +21,13 @@ for scene, spp in (("random_scene", 64), ("random_scene_list", 64), ("oneweek_fi
         st = sc.render_device(cam, T.make_params(1600, 1600, spp, 15, mode=T.MODE_FAST, seed=1, kernel=T.KERNEL_WAVEFRONT))
         best = max(best, st["paths"] / st["render_ms"] / 1e3)
     out.append(f"{scene} {best:.0f}")
+import hashlib
+for scene in ("random_scene", "oneweek_final"):
+    img = common.earth_jpg_decoded() if scene == "oneweek_final" else None
+    sc = T.Scene(T.HostScene(scene, image=img, perlin=perlin, background=T.BG_SKY if scene == "random_scene" else T.BG_BLACK))
+    cam = T.book_camera(256, 256, fov=20.0, t0=0.0, t1=1.0) if scene == "random_scene" else T.make_camera((478, 278, -600), (278, 278, 0), (0, 1, 0), 40.0, 1.0, 0.0, 10.0, 0.0, 1.0)
+    res = sc.render(cam, T.make_params(256, 256, 16, 15, mode=T.MODE_FAST, seed=1, kernel=T.KERNEL_WAVEFRONT))
+    out.append(f"{scene}_check {float(res.sum_rgb.mean()):.6f} {hashlib.sha1(res.sum_rgb.tobytes()).hexdigest()[:10]}")
 print("  ".join(out))
 PY
 for d in gpurun_variants/v*; do
