@@ -1764,6 +1764,58 @@ static int scene_create_impl(const tpt_scene_desc *d, int device, tpt_scene **ou
     if (const char *e = std::getenv("TPT_PARITY_SKIP")) // TPT_PARITY_SKIP=0: keep the frame replay (A/B and test use)
       if (e[0] == '0') simple = false;
     L.tree_simple = simple ? 1 : 0;
+    // margin of the skip walk's "behind the best hit" test: 1e-5 of the root box's largest extent (no culling
+    // without a finite root box, or with TPT_PARITY_SKIP_CULL=0)
+    L.skip_cull_abs = -1.f;
+    if (s->root_box_ok) {
+      float ext = 0.f;
+      for (int k = 0; k < 3; k++) ext = std::max(ext, s->root_hi[k] - s->root_lo[k]);
+      if (std::isfinite(ext)) L.skip_cull_abs = 1e-5f * ext;
+    }
+    if (const char *e = std::getenv("TPT_PARITY_SKIP_CULL"))
+      if (e[0] == '0') L.skip_cull_abs = -1.f;
+    // closest_hit_skip_ordered: nearest-child hints in the blob's copy of the bvh_node words (the caller's
+    // description is not touched) and the nesting depth of the bvh_nodes = the most children the walk defers
+    L.skip_ordered = 0;
+    if (simple && L.skip_cull_abs >= 0.f) {
+      int depth = 0, max_depth = 0;
+      std::vector<int> ends;
+      for (int i = 0; i < n_root; i++) {
+        while (!ends.empty() && i >= ends.back()) { ends.pop_back(); depth--; }
+        const tpt_node &nd = d->nodes[i];
+        if ((nd.kind & 0xff) != TPT_NODE_BVH) {
+          if ((nd.kind & 0xff) == TPT_NODE_LIST) i = nd.end_or_prim - 1; // nothing below a list is deferred
+          continue;
+        }
+        ends.push_back(nd.end_or_prim);
+        max_depth = std::max(max_depth, ++depth);
+        if (nd.kind & TPT_NODE_DUP) continue;
+        const int l = i + 1;
+        if (l >= nd.end_or_prim) continue;
+        const tpt_node &ln = d->nodes[l];
+        const int r = (ln.kind & 0xff) == TPT_NODE_LEAF ? l + 1 : ln.end_or_prim;
+        if (r >= nd.end_or_prim) continue;
+        const tpt_node &rn = d->nodes[r];
+        if ((rn.kind & TPT_NODE_DUP) || (ln.kind >> 16) != (nd.kind >> 16) || (rn.kind >> 16) != (nd.kind >> 16)) continue;
+        int axis = -1;
+        float sep = 0.f;
+        bool lower = true;
+        for (int k = 0; k < 3; k++) {
+          const float cl = 0.5f * (ln.bmin[k] + ln.bmax[k]), cr = 0.5f * (rn.bmin[k] + rn.bmax[k]);
+          if (!std::isfinite(cl) || !std::isfinite(cr)) { axis = -1; break; }
+          if (std::fabs(cl - cr) > sep) { sep = std::fabs(cl - cr); axis = k; lower = cl <= cr; }
+        }
+        if (axis < 0) continue;
+        int32_t kind;
+        unsigned char *w = blob.data() + (size_t)L.off_nodes * 16 + (size_t)i * sizeof(tpt_node) + offsetof(tpt_node, kind);
+        std::memcpy(&kind, w, 4);
+        kind |= 0x200 | (axis << 10) | (lower ? 0x1000 : 0); // TPT_NODE_HINT, axis, TPT_NODE_HINT_LOWER (tpt_device.cuh)
+        std::memcpy(w, &kind, 4);
+      }
+      L.skip_ordered = max_depth + 2 <= 32 ? 1 : 0; // TPT_SKIP_STACK
+      if (const char *e = std::getenv("TPT_PARITY_SKIP_ORDERED"))
+        if (e[0] == '0') L.skip_ordered = 0;
+    }
   }
   s->fbvh_has_moving = fb.has_moving;
   s->fbvh_t0 = fb.moving_t0;
