@@ -153,3 +153,25 @@ def test_open_block_equals_separate_rects(T, gpu, monkeypatch):
     assert differ.sum() <= max(2, len(rays) // 20000), int(differ.sum())
     same = ~differ & (a["hit"] == 1)
     assert np.allclose(a["t"][same], b["t"][same], rtol=4e-7, atol=0)
+
+
+@pytest.mark.parametrize("scene", ["random_scene", "random_scene_list"])
+def test_parity_walk_cull_changes_nothing(T, gpu, monkeypatch, scene):
+    """The parity walk of large trees (closest_hit_skip) does not enter a box that lies wholly behind the best
+    hit so far, plus a margin; the reference enters it (bvh_node::hit never shrinks t_max, src/hitable.cc:63-90)
+    and finds nothing closer there. With TPT_PARITY_SKIP_CULL=0 the walk tests every box against the caller's
+    t_max like the reference: the two must return the same record on every ray, bit for bit -- camera rays,
+    rays from inside the scene, the hand-made adversarial ones and two generations of secondary rays."""
+    hs = common.host_scene(T, scene)
+    rays = raygen.primary_batch(scene, 150000, 50000, seed=2024)
+    culled = T.Scene(hs)
+    monkeypatch.setenv("TPT_PARITY_SKIP_CULL", "0")
+    plain = T.Scene(hs)
+    for gen in range(3):
+        a = culled.intersect(rays, mode=T.MODE_PARITY)
+        b = plain.intersect(rays, mode=T.MODE_PARITY)
+        assert (a["hit"] == 1).sum() > len(rays) // 10
+        assert a.tobytes() == b.tobytes(), f"generation {gen}: {int((a != b).sum())} records differ"
+        rays = raygen.secondary_rays(a, np.random.default_rng(100 + gen))
+        if len(rays) == 0:
+            break
