@@ -177,6 +177,9 @@ int validate_desc(const tpt_scene_desc *d, int &depth_out) {
   if (d->n_chains <= 0 || !d->chains) return fail(TPT_ERR_INVALID, "chain 0 (identity) is required");
   if (d->n_materials <= 0 || !d->materials) return fail(TPT_ERR_INVALID, "scene has no materials");
   if (d->n_images > TPT_MAX_IMAGES) return fail(TPT_ERR_UNSUPPORTED, "too many image textures");
+  if (d->n_textures < 0 || (d->n_textures > 0 && !d->textures)) return fail(TPT_ERR_INVALID, "bad texture table");
+  if (d->n_xform_ops < 0 || (d->n_xform_ops > 0 && !d->xform_ops)) return fail(TPT_ERR_INVALID, "bad transform-op table");
+  if (d->n_images < 0 || (d->n_images > 0 && !d->images)) return fail(TPT_ERR_INVALID, "bad image table");
   if (d->n_lights < 0 || (d->n_lights > 0 && !d->lights)) return fail(TPT_ERR_INVALID, "bad light list");
   // structural walk: every group's end must nest properly (root tree, then medium boundaries)
   const int n_root = d->n_root_nodes > 0 ? d->n_root_nodes : d->n_nodes;
@@ -235,7 +238,7 @@ int validate_desc(const tpt_scene_desc *d, int &depth_out) {
   }
   for (int i = 0; i < d->n_chains; i++) {
     const tpt_chain &c = d->chains[i];
-    if (c.n_ops < 0 || c.first_op < 0 || c.first_op + c.n_ops > d->n_xform_ops)
+    if (c.n_ops < 0 || c.first_op < 0 || (long long)c.first_op + c.n_ops > d->n_xform_ops)
       return fail(TPT_ERR_INVALID, "chain ops out of range");
   }
   bool needs_perlin = false;
@@ -335,6 +338,13 @@ int32_t make_child(std::vector<BuildItem> &items, int begin, int end, FastBvh &o
   return build_fbvh_rec(items, begin, end, out, box);
 }
 
+// bin of a centroid along an axis of extent ext starting at lo; any non-finite quotient lands in bin 0
+static int bin_of(int nb, float cen, float lo, float ext) {
+  const float q = (float)nb * (cen - lo) / ext;
+  if (!(q > 0.f)) return 0;
+  return q >= (float)(nb - 1) ? nb - 1 : (int)q;
+}
+
 int32_t build_fbvh_rec(std::vector<BuildItem> &items, int begin, int end, FastBvh &out, Box3 &bounds_out) {
   Box3 cb, bb;
   cb.reset();
@@ -357,7 +367,7 @@ int32_t build_fbvh_rec(std::vector<BuildItem> &items, int begin, int end, FastBv
     int cnt[NB] = {0};
     for (auto &b : bins) b.reset();
     for (int i = begin; i < end; i++) {
-      int k = std::min(NB - 1, (int)(NB * (items[i].cen[axis] - cb.lo[axis]) / ext));
+      int k = bin_of(NB, items[i].cen[axis], cb.lo[axis], ext);
       bins[k].grow(items[i].box);
       cnt[k]++;
     }
@@ -388,8 +398,7 @@ int32_t build_fbvh_rec(std::vector<BuildItem> &items, int begin, int end, FastBv
   } else {
     float ext = cb.hi[best_axis] - cb.lo[best_axis];
     auto it = std::partition(items.begin() + begin, items.begin() + end, [&](const BuildItem &b) {
-      int k = std::min(NB - 1, (int)(NB * (b.cen[best_axis] - cb.lo[best_axis]) / ext));
-      return k <= best_split;
+      return bin_of(NB, b.cen[best_axis], cb.lo[best_axis], ext) <= best_split;
     });
     mid = (int)(it - items.begin());
     if (mid == begin || mid == end) mid = (begin + end) / 2;
@@ -495,6 +504,13 @@ void build_fast_bvh(const tpt_scene_desc *d, int n_root, FastBvh &out) {
     BuildItem it;
     it.box = world_box(d, nd);
     for (int c = 0; c < 3; c++) it.cen[c] = 0.5f * (it.box.lo[c] + it.box.hi[c]);
+    // a leaf box that is not a finite, ordered interval (a caller's NaN / infinite coordinates or transform)
+    // cannot be binned: no SAH tree for this scene, FAST mode walks the caller's own tree instead
+    for (int c = 0; c < 3; c++)
+      if (!std::isfinite(it.box.lo[c]) || !std::isfinite(it.box.hi[c]) || !(it.box.lo[c] <= it.box.hi[c]) || !std::isfinite(it.cen[c])) {
+        out = FastBvh();
+        return;
+      }
     it.prim = nd.end_or_prim;
     const tpt_prim &p = d->prims[it.prim];
     if (p.kind == TPT_PRIM_MOVING_SPHERE) {
