@@ -203,7 +203,7 @@ enum {
 };
 
 typedef struct tpt_render_params {
-  int32_t nx, ny, ns, max_depth; /* main.cpp:31-37 */
+  int32_t nx, ny, ns, max_depth; /* main.cpp:31-37; max_depth <= 65535 */
   int32_t slices;   /* bonus_pic when allow_bonus_pic, else 1 (main.cpp:111-114); must divide into ns>=slices */
   int32_t mode;     /* TPT_MODE_*   */
   int32_t kernel;   /* TPT_KERNEL_* */

@@ -868,6 +868,7 @@ int make_plan(tpt_scene *s, const tpt_camera *cam, const tpt_render_params *p, P
   if (!s || !cam || !p) return fail(TPT_ERR_INVALID, "null argument");
   if (p->nx <= 0 || p->ny <= 0 || p->ns <= 0 || p->max_depth < 0) return fail(TPT_ERR_INVALID, "bad image/sample parameters");
   if ((long long)p->nx * p->ny > (1LL << 28)) return fail(TPT_ERR_UNSUPPORTED, "image too large");
+  if (p->max_depth > 65535) return fail(TPT_ERR_UNSUPPORTED, "max_depth above 65535 (the slot's depth word carries flags above bit 20)");
   int slices = p->slices > 0 ? p->slices : 1;
   int per_slice = p->ns / slices;
   if (per_slice <= 0) return fail(TPT_ERR_INVALID, "ns < slices (the reference would divide by zero, main.cpp:113,127)");
