@@ -27,6 +27,16 @@
 #include <stdlib.h>
 #include <string.h>
 
+/* std::sin / std::cos of a float are the host libm's sinf / cosf: faithful (< 1 ulp) but not correctly rounded, and the
+ * last bit depends on the libm build. The CUDA parity path evaluates them in double and rounds once. Diagnostic switch
+ * (default 0 = the reference's calls): with tpto_set_rounded_trig(1) this restatement does the same, which attributes a
+ * residual pixel difference to that last bit or to something else (tools/gpu_diff_fuzz.py, profiles/r02_fuzz.txt). */
+static int g_rounded_trig = 0;
+void tpto_set_rounded_trig(int on) { g_rounded_trig = on; }
+#define SINF(x) (g_rounded_trig ? (float)sin((double)(x)) : sinf(x))
+#define COSF(x) (g_rounded_trig ? (float)cos((double)(x)) : cosf(x))
+
+
 #ifndef M_PI
 #define M_PI 3.14159265358979323846
 #endif
@@ -340,11 +350,11 @@ static v3 texture_value(const tpt_scene_desc *d, int id, float u, float v, v3 p)
   switch (t->kind) {
   case TPT_TEX_CONSTANT: return V(t->color[0], t->color[1], t->color[2]);
   case TPT_TEX_CHECKER: {
-    float s = sinf(10 * p.e[0]) * sinf(10 * p.e[1]) * sinf(10 * p.e[2]);
+    float s = SINF(10 * p.e[0]) * SINF(10 * p.e[1]) * SINF(10 * p.e[2]);
     return texture_value(d, isless(s, 0.0f) ? t->odd : t->even, u, v, p);
   }
   case TPT_TEX_PERLIN: {
-    float g = 0.5f * (1 + sinf(t->scale * p.e[2] + 10 * perlin_turb(d->perlin, p)));
+    float g = 0.5f * (1 + SINF(t->scale * p.e[2] + 10 * perlin_turb(d->perlin, p)));
     return V(g, g, g); /* vec3(1,1,1) * 0.5 * (1 + sin(...)) */
   }
   default: {
@@ -404,8 +414,8 @@ static v3 random_on_hemisphere(rng_t *g) {
   float r1 = (float)drand_r(g);
   float r2 = (float)drand_r(g);
   float phi = (float)(2 * M_PI * r1);
-  float x = cosf(phi) * sqrtf(r2);
-  float y = sinf(phi) * sqrtf(r2);
+  float x = COSF(phi) * sqrtf(r2);
+  float y = SINF(phi) * sqrtf(r2);
   float z = sqrtf(1 - r2);
   return V(x, y, z);
 }

@@ -34,6 +34,40 @@ def _clone(T, src):
     return d, keep
 
 
+def perturb_geometry(rng, keep, n_mut):
+    """benign mutations: scale / shift single floats of primitives, materials, transform ops"""
+    muts = []
+    for _ in range(n_mut):
+        aname = str(rng.choice([a for a in ("prims", "prims", "prims", "materials", "xform_ops") if a in keep]))
+        buf = keep[aname]
+        rec = C.sizeof(buf._type_) // 4
+        f = np.frombuffer(buf, dtype=np.float32)
+        n_rec = len(buf) - 1
+        r = int(rng.integers(n_rec))
+        if aname == "prims":
+            w = int(rng.integers(4, 13))  # p[0..8] live in words 4..12 of tpt_prim (kind, material, chain, flags first)
+            if int(np.frombuffer(buf, dtype=np.int32)[r * rec]) == 5 and w in (5, 6):
+                continue  # a medium's boundary range: node indices, not floats
+        elif aname == "materials":
+            w = int(rng.integers(2, 7))  # albedo, fuzz, ref_idx
+        else:
+            w = int(rng.integers(1, 4))
+        i = r * rec + w
+        old = float(f[i])
+        if not np.isfinite(old) or abs(old) > 1e6:
+            continue
+        mode = rng.integers(0, 3)
+        if mode == 0:
+            f[i] = np.float32(old * rng.uniform(0.5, 1.5))
+        elif mode == 1:
+            f[i] = np.float32(old + rng.normal(0, 0.05 * max(1.0, abs(old))))
+        else:  # snap onto another record's value: coincident planes / centres, the tie cases
+            f[i] = f[int(rng.integers(n_rec)) * rec + w]
+        muts.append((aname, r, w, old, float(f[i])))
+    return muts
+
+
+
 INTERESTING = [-1, 0, 1, 2, 3, 7, 8, 31, 32, 33, 48, 49, 255, 256, 0x100, 0x10000, 0x7fffffff, -0x80000000]
 
 

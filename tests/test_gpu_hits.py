@@ -164,6 +164,7 @@ def test_parity_walk_cull_changes_nothing(T, gpu, monkeypatch, scene):
     rays from inside the scene, the hand-made adversarial ones and two generations of secondary rays."""
     hs = common.host_scene(T, scene)
     rays = raygen.primary_batch(scene, 150000, 50000, seed=2024)
+    rays[::3, 6] = np.random.default_rng(5).uniform(-1.0, 2.0, size=len(rays[::3]))  # shutter times inside and OUTSIDE the moving spheres' [0, 1]: outside it they leave their boxes
     culled = T.Scene(hs)
     monkeypatch.setenv("TPT_PARITY_SKIP_CULL", "0")
     plain = T.Scene(hs)
@@ -175,3 +176,47 @@ def test_parity_walk_cull_changes_nothing(T, gpu, monkeypatch, scene):
         rays = raygen.secondary_rays(a, np.random.default_rng(100 + gen))
         if len(rays) == 0:
             break
+
+
+@pytest.mark.parametrize("scene", ["cornell_box", "sphere_cornell_box", "random_scene", "light_spheres"])
+def test_parity_hits_on_perturbed_scenes_vs_port(T, gpu, scene):
+    """Differential check away from the fixed fixtures: the flattened scene gets a few geometry / transform floats
+    scaled, shifted or snapped onto another record's value (coincident planes and centres: the tie cases), node
+    boxes left as they were -- both sides consume the same description, consistent or not. Parity-mode records
+    must equal the plain-C restatement's bit for bit on camera, interior, adversarial and secondary rays.
+    (tools/gpu_diff_fuzz.py is the long-running form of this test: profiles/r02_fuzz.txt.)"""
+    import ctypes as C
+
+    import oracle_port as P
+    import test_abi_fuzz as F
+    if not P.available():
+        pytest.skip("oracle/_build/libtptoracle.so not built")
+    hs = common.host_scene(T, scene)
+    src = hs.desc.contents if hasattr(hs.desc, "contents") else hs.desc
+    rng = np.random.default_rng(31 + len(scene))
+    checked = 0
+    for trial in range(8):
+        d, keep = F._clone(T, src)
+        muts = F.perturb_geometry(rng, keep, int(rng.integers(1, 6)))
+
+        class Holder:
+            desc = C.pointer(d)
+        try:
+            sc = T.Scene(Holder.desc)
+        except Exception:
+            continue  # a perturbation the validator refuses
+        rays = raygen.primary_batch(scene, 3000, 1500, seed=500 + trial)
+        for gen in range(2):
+            got = sc.intersect(rays, mode=T.MODE_PARITY)
+            exp = P.hit_batch(T, Holder, rays)
+            both = (got["hit"] == 1) & (exp["hit"] == 1)
+            differ = (got["hit"] != exp["hit"]) | (both & ((got["prim"] != exp["prim"]) | ~common.same_float(got["t"], exp["t"])
+                                                           | ~common.same_float(got["p"], exp["p"]).all(axis=1)
+                                                           | ~common.same_float(got["n"], exp["n"]).all(axis=1)))
+            assert differ.sum() == 0, f"trial {trial} generation {gen}: {int(differ.sum())} of {len(rays)} records differ after {muts!r}"
+            checked += len(rays)
+            rays = raygen.secondary_rays(got, np.random.default_rng(trial))
+            if len(rays) == 0:
+                break
+        sc.close()
+    assert checked > 20000

@@ -285,19 +285,19 @@ struct Box3 {
 struct FastBvh {
   std::vector<float> nodes; // 16 floats per node
   std::vector<int32_t> leaf_prims;
-  float moving_t0 = FLT_MAX, moving_t1 = -FLT_MAX; // ray times the moving-sphere boxes are valid for
+  float moving_t0 = -FLT_MAX, moving_t1 = FLT_MAX; // ray times ALL the moving-sphere boxes are valid for (intersection of the spheres' own intervals)
   bool has_moving = false;
 };
 
 // object-space box of a leaf -> world space through the inverse of its wrapper chain
 // (translate: +offset, rotate_y: x = c x' + s z', z = -s x' + c z'), innermost wrapper first
-Box3 world_box(const tpt_scene_desc *d, const tpt_node &leaf) {
-  const tpt_chain &ch = d->chains[leaf.kind >> 16];
+// a box in the object space of transform chain `chain` -> world space (the box of its eight corners)
+Box3 chain_to_world(const tpt_scene_desc *d, const Box3 &in, int chain) {
+  const tpt_chain &ch = d->chains[chain];
   Box3 out;
   out.reset();
   for (int corner = 0; corner < 8; corner++) {
-    double p[3] = {corner & 1 ? leaf.bmax[0] : leaf.bmin[0], corner & 2 ? leaf.bmax[1] : leaf.bmin[1],
-                   corner & 4 ? leaf.bmax[2] : leaf.bmin[2]};
+    double p[3] = {corner & 1 ? in.hi[0] : in.lo[0], corner & 2 ? in.hi[1] : in.lo[1], corner & 4 ? in.hi[2] : in.lo[2]};
     for (int k = ch.n_ops - 1; k >= 0; k--) {
       const tpt_xform_op &op = d->xform_ops[ch.first_op + k];
       if (op.kind == TPT_XF_TRANSLATE) {
@@ -311,6 +311,13 @@ Box3 world_box(const tpt_scene_desc *d, const tpt_node &leaf) {
     for (int c = 0; c < 3; c++) b.lo[c] = b.hi[c] = (float)p[c];
     out.grow(b);
   }
+  return out;
+}
+
+Box3 world_box(const tpt_scene_desc *d, const tpt_node &leaf) {
+  Box3 in;
+  for (int c = 0; c < 3; c++) { in.lo[c] = leaf.bmin[c]; in.hi[c] = leaf.bmax[c]; }
+  Box3 out = chain_to_world(d, in, leaf.kind >> 16);
   for (int c = 0; c < 3; c++) { // conservative padding: fp32 slab test vs the primitive's own arithmetic
     float pad = 1e-4f + 1e-5f * std::max(std::fabs(out.lo[c]), std::fabs(out.hi[c]));
     out.lo[c] -= pad;
@@ -322,6 +329,67 @@ Box3 world_box(const tpt_scene_desc *d, const tpt_node &leaf) {
 struct BuildItem { Box3 box; float cen[3]; int prim; };
 
 int32_t build_fbvh_rec(std::vector<BuildItem> &items, int begin, int end, FastBvh &out, Box3 &bounds_out);
+
+// object-space bounds of a surface primitive from its OWN parameters (sphere: centre +- radius; moving sphere: both end
+// positions, valid for ray times inside [time0, time1]; rects: the reference's 0.0002-thick slab, src/rect_box.cc)
+static bool prim_own_box(const tpt_prim &p, Box3 &b) {
+  b.reset();
+  auto add = [&b](float x, float y, float z) {
+    Box3 q;
+    q.lo[0] = q.hi[0] = x; q.lo[1] = q.hi[1] = y; q.lo[2] = q.hi[2] = z;
+    b.grow(q);
+  };
+  const float *q = p.p;
+  if (p.kind == TPT_PRIM_SPHERE || p.kind == TPT_PRIM_MOVING_SPHERE) {
+    const float r = std::fabs(q[3]);
+    add(q[0] - r, q[1] - r, q[2] - r);
+    add(q[0] + r, q[1] + r, q[2] + r);
+    if (p.kind == TPT_PRIM_MOVING_SPHERE) {
+      add(q[4] - r, q[5] - r, q[6] - r);
+      add(q[4] + r, q[5] + r, q[6] + r);
+    }
+  } else if (p.kind == TPT_PRIM_XY_RECT) {
+    add(q[0], q[2], q[4] - 1e-4f); add(q[1], q[3], q[4] + 1e-4f);
+  } else if (p.kind == TPT_PRIM_XZ_RECT) {
+    add(q[0], q[4] - 1e-4f, q[2]); add(q[1], q[4] + 1e-4f, q[3]);
+  } else if (p.kind == TPT_PRIM_YZ_RECT) {
+    add(q[4] - 1e-4f, q[0], q[2]); add(q[4] + 1e-4f, q[1], q[3]);
+  } else {
+    return false;
+  }
+  for (int c = 0; c < 3; c++)
+    if (!std::isfinite(b.lo[c]) || !std::isfinite(b.hi[c])) return false;
+  return true;
+}
+
+// closest_hit_skip's cull assumes what the reference's own bounding_box() guarantees and a hand-made description may
+// not: every primitive lies inside the box of every bvh_node above it. True iff that holds for the root tree (all
+// bvh_nodes in world space; primitive bounds carried out of their transform chains), with a slack of 1e-5 of the extent.
+static bool boxes_contain_their_prims(const tpt_scene_desc *d, int n_root) {
+  std::vector<int> open; // bvh_nodes whose sub-tree the scan is in
+  for (int i = 0; i < n_root; i++) {
+    while (!open.empty() && i >= d->nodes[open.back()].end_or_prim) open.pop_back();
+    const tpt_node &nd = d->nodes[i];
+    const int k = nd.kind & 0xff;
+    if (k == TPT_NODE_BVH) {
+      if ((nd.kind >> 16) != 0) return false;
+      open.push_back(i);
+    } else if (k == TPT_NODE_LEAF && !(nd.kind & TPT_NODE_DUP)) {
+      const tpt_prim &p = d->prims[nd.end_or_prim];
+      Box3 own;
+      if (!prim_own_box(p, own)) return false;
+      const Box3 w = chain_to_world(d, own, nd.kind >> 16);
+      for (int a : open) {
+        const tpt_node &an = d->nodes[a];
+        for (int c = 0; c < 3; c++) {
+          const float slack = 1e-5f * std::max(1.0f, std::max(std::fabs(an.bmin[c]), std::fabs(an.bmax[c])));
+          if (!(w.lo[c] >= an.bmin[c] - slack) || !(w.hi[c] <= an.bmax[c] + slack)) return false;
+        }
+      }
+    }
+  }
+  return true;
+}
 
 // returns the child reference: >= 0 inner node index, < 0 ~((first << 3) | (count - 1))
 int32_t make_child(std::vector<BuildItem> &items, int begin, int end, FastBvh &out, Box3 &box) {
@@ -515,8 +583,8 @@ void build_fast_bvh(const tpt_scene_desc *d, int n_root, FastBvh &out) {
     const tpt_prim &p = d->prims[it.prim];
     if (p.kind == TPT_PRIM_MOVING_SPHERE) {
       out.has_moving = true;
-      out.moving_t0 = std::min(out.moving_t0, std::min(p.p[7], p.p[8]));
-      out.moving_t1 = std::max(out.moving_t1, std::max(p.p[7], p.p[8]));
+      out.moving_t0 = std::max(out.moving_t0, std::min(p.p[7], p.p[8]));
+      out.moving_t1 = std::min(out.moving_t1, std::max(p.p[7], p.p[8]));
     }
     items.push_back(it);
   }
@@ -1757,13 +1825,13 @@ static int scene_create_impl(const tpt_scene_desc *d, int device, tpt_scene **ou
       s->root_hi[k] = root.bmax[k];
       if (!std::isfinite(root.bmin[k]) || !std::isfinite(root.bmax[k]) || !(root.bmin[k] <= root.bmax[k])) s->root_box_ok = false;
     }
-    s->moving_t0 = FLT_MAX;
-    s->moving_t1 = -FLT_MAX;
+    s->moving_t0 = -FLT_MAX; // intersection of the moving spheres' own [time0, time1]
+    s->moving_t1 = FLT_MAX;
     for (int i = 0; i < d->n_prims; i++)
       if (d->prims[i].kind == TPT_PRIM_MOVING_SPHERE) {
         s->any_moving = true;
-        s->moving_t0 = std::min(s->moving_t0, std::min(d->prims[i].p[7], d->prims[i].p[8]));
-        s->moving_t1 = std::max(s->moving_t1, std::max(d->prims[i].p[7], d->prims[i].p[8]));
+        s->moving_t0 = std::max(s->moving_t0, std::min(d->prims[i].p[7], d->prims[i].p[8]));
+        s->moving_t1 = std::min(s->moving_t1, std::max(d->prims[i].p[7], d->prims[i].p[8]));
       }
     s->background = d->background;
   }
@@ -1784,7 +1852,14 @@ static int scene_create_impl(const tpt_scene_desc *d, int device, tpt_scene **ou
     // margin of the skip walk's "behind the best hit" test: 1e-5 of the root box's largest extent (no culling
     // without a finite root box, or with TPT_PARITY_SKIP_CULL=0)
     L.skip_cull_abs = -1.f;
-    if (s->root_box_ok) {
+    L.skip_cull_t0 = -FLT_MAX;
+    L.skip_cull_t1 = FLT_MAX;
+    for (int i = 0; i < d->n_prims; i++)
+      if (d->prims[i].kind == TPT_PRIM_MOVING_SPHERE) { // a moving sphere stays inside its boxes for ray times within its own interval only
+        L.skip_cull_t0 = std::max(L.skip_cull_t0, std::min(d->prims[i].p[7], d->prims[i].p[8]));
+        L.skip_cull_t1 = std::min(L.skip_cull_t1, std::max(d->prims[i].p[7], d->prims[i].p[8]));
+      }
+    if (s->root_box_ok && simple && boxes_contain_their_prims(d, n_root)) {
       float ext = 0.f;
       for (int k = 0; k < 3; k++) ext = std::max(ext, s->root_hi[k] - s->root_lo[k]);
       if (std::isfinite(ext)) L.skip_cull_abs = 1e-5f * ext;

@@ -59,6 +59,7 @@ struct SceneLayout { // host-computed, lives in kernel parameter (constant) spac
   int off_fbvh, off_fleaf, n_fbvh, fbvh_time_ok; // FAST-mode SAH BVH over world-space leaf boxes (0 nodes = none)
   int tree_simple; // no medium and no bvh_node below a hitable_list: PARITY walks the tree with skip pointers (closest_hit_skip)
   int skip_ordered;    // closest_hit_skip may visit a bvh_node's children nearest first (hints in the blob's node words, tree shallow enough for the lane's stack)
+  float skip_cull_t0, skip_cull_t1; // ... for ray times in this interval (moving spheres leave their boxes outside their own [time0, time1])
   float skip_cull_abs; // closest_hit_skip: absolute part of the margin behind the best hit beyond which a box is not entered (< 0: never cull)
   int n_nodes, n_prims, n_lights, background;
   cudaTextureObject_t images[TPT_MAX_IMAGES];
@@ -840,7 +841,7 @@ TPT_DEV bool closest_hit_skip(const SceneView &S, const Ray &r, float tmin, floa
   // against best_t plus a margin (0.1 % + 1e-5 of the scene's extent) that is orders of magnitude wider than
   // the rounding of the slab test and of the primitives' own t, and narrow enough to cut the node visits.
   // With t_max' < t_max AABB::hit differs only by refusing boxes whose entry distance is >= t_max'.
-  const float cull_abs = S.L->skip_cull_abs;
+  const float cull_abs = (r.time >= S.L->skip_cull_t0 && r.time <= S.L->skip_cull_t1) ? S.L->skip_cull_abs : -1.f;
   float box_max = tmax;
 #define TPT_SKIP_TOOK() if (TPT_PAR_SKIP_CULL && cull_abs >= 0.f) box_max = fminf(tmax, fmaf(best_t, 1.001f, cull_abs))
   for (int i = 0; i < n;) {
@@ -925,7 +926,7 @@ TPT_DEV bool closest_hit_skip_ordered(const SceneView &S, const Ray &r, float tm
   float best_t = 0.f;
   int best_prim = -1, best_rank = -1;
   bool unordered = false;
-  const float cull_abs = S.L->skip_cull_abs;
+  const float cull_abs = (r.time >= S.L->skip_cull_t0 && r.time <= S.L->skip_cull_t1) ? S.L->skip_cull_abs : -1.f;
   float box_max = tmax;
   int stack[TPT_SKIP_STACK];
   int sp = 0, cur = 0;
