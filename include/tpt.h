@@ -53,6 +53,11 @@ typedef enum tpt_status {
  * flip_normal / translate / rotate_y are not nodes: a leaf carries its flip parity and the id of
  * its transform chain (the translate / rotate_y wrappers between the root and the leaf, outermost
  * first); BVH nodes that live under a transform carry the chain id too.
+ *
+ * Bounds are what the reference's bounding_box() returns, so every primitive lies inside the boxes of the
+ * nodes above it. PARITY mode honours the boxes exactly as given (a primitive is tested whenever the boxes
+ * above it are crossed, wherever it is), and speeds its walk up only after verifying that containment;
+ * FAST mode builds its own acceleration structure from the leaf bounds and relies on it.
  * ------------------------------------------------------------------------------------------- */
 enum { TPT_NODE_BVH = 0, TPT_NODE_LIST = 1, TPT_NODE_LEAF = 2 };
 enum { TPT_NODE_DUP = 0x100 }; /* or'ed into tpt_node.kind */
