@@ -47,7 +47,8 @@ def main():
     log = open(os.path.join(ROOT, "gpurun_out", f"diff_fuzz_{scene}_{seed}.log"), "w")
     for trial in range(trials):
         d, keep = F._clone(T, src)
-        muts = perturb(rng, keep, int(rng.integers(1, 6)))
+        # every third trial keeps the description as the flattener made it (boxes consistent: the parity walk's cull is on)
+        muts = perturb(rng, keep, int(rng.integers(1, 6))) if trial % 3 else []
         h = Holder(d, keep, hs.max_depth)
         try:
             sc = T.Scene(h.desc)
@@ -72,7 +73,13 @@ def main():
                 rays = raygen.secondary_rays(got, np.random.default_rng(trial))
                 if len(rays) == 0:
                     break
-        p = T.make_params(nx, ny, 4, 12, mode=T.MODE_PARITY, seed=77 + trial, kernel=T.KERNEL_WAVEFRONT if trial % 2 else T.KERNEL_MEGA)
+        if os.environ.get("FUZZ_CAMERA", "1") == "1":  # a different thin-lens camera per trial; shutters also OUTSIDE the moving spheres' [0, 1]
+            eye, lookat = raygen.SCENE_INFO.get(scene, raygen.SCENE_INFO["cornell_box"])[1:3]
+            eye = np.array(eye, np.float64) + rng.normal(0, 0.05 * np.linalg.norm(np.array(eye) - np.array(lookat)), 3)
+            t0 = float(rng.uniform(-0.5, 1.0))
+            cam = T.make_camera(tuple(eye), tuple(lookat), (0, 1, 0), float(rng.uniform(15, 90)), 1.0, float(rng.choice([0.0, 0.1, 0.3])),
+                                float(np.linalg.norm(eye - np.array(lookat))), t0, t0 + float(rng.uniform(0, 1.2)))
+        p = T.make_params(nx, ny, 4, int(rng.integers(1, 20)), mode=T.MODE_PARITY, seed=77 + trial, kernel=T.KERNEL_WAVEFRONT if trial % 2 else T.KERNEL_MEGA)
         ref, _, _ = P.render(T, h, cam, p, threads=8)
         res = sc.render(cam, p)
         rel = common.rel_err(res.sum_rgb, ref, 1e-3 * 4)
