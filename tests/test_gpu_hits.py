@@ -220,3 +220,53 @@ def test_parity_hits_on_perturbed_scenes_vs_port(T, gpu, scene):
                 break
         sc.close()
     assert checked > 20000
+
+
+def test_parity_honours_boxes_that_do_not_contain_their_primitive(T, gpu):
+    """The reference tests a primitive whenever the boxes of the bvh_nodes above it are crossed -- wherever the
+    primitive actually is. A hand-made description can put a sphere OUTSIDE those boxes (here: a small sphere of
+    random_scene moved in front of everything else, between the camera and the scene, its node boxes left where
+    they were): rays that cross its old boxes hit it first, the others never test it. Parity mode must follow the
+    boxes literally -- its walk's cull ("nothing in a box behind the best hit can be closer") does not hold for such
+    a description and has to stay off (found by tools/gpu_diff_fuzz.py, profiles/r02_fuzz.txt)."""
+    import ctypes as C
+
+    import oracle_port as P
+    import test_abi_fuzz as F
+    if not P.available():
+        pytest.skip("oracle/_build/libtptoracle.so not built")
+    hs = common.host_scene(T, "random_scene")
+    src = hs.desc.contents if hasattr(hs.desc, "contents") else hs.desc
+    extent, eye, lookat = raygen.SCENE_INFO["random_scene"]
+    eye = np.array(eye, np.float32)
+    rng = np.random.default_rng(3)
+    wide = raygen.camera_rays(100000, tuple(eye), lookat, 25.0, rng)
+    total_displaced_hits = 0
+    for victim in (40, 200, 333):
+        d, keep = F._clone(T, src)
+        prims = keep["prims"]
+        assert prims[victim].kind in (0, 1)  # a sphere / moving sphere
+        old_centre = np.array([prims[victim].p[k] for k in range(3)], np.float32)
+        new_centre = eye + 0.5 * (old_centre - eye)  # half way to the camera, on the line of sight of its old place
+        for k in range(3):
+            prims[victim].p[k] = float(new_centre[k])
+            if prims[victim].kind == 1:
+                prims[victim].p[4 + k] = float(new_centre[k])
+        prims[victim].p[3] = 0.3
+        # rays from the camera towards the sphere's OLD place: through the displaced sphere first, then through its old boxes
+        aimed = np.zeros((50000, 7), np.float32)
+        aimed[:, 0:3] = eye
+        aimed[:, 3:6] = old_centre + rng.normal(0, 0.12, size=(len(aimed), 3)).astype(np.float32) - eye
+        aimed[:, 6] = rng.uniform(0, 1, len(aimed)).astype(np.float32)
+        rays = np.concatenate([aimed, wide])
+
+        class Holder:
+            desc = C.pointer(d)
+        got = T.Scene(Holder.desc).intersect(rays, mode=T.MODE_PARITY)
+        exp = P.hit_batch(T, Holder, rays)
+        both = (got["hit"] == 1) & (exp["hit"] == 1)
+        differ = (got["hit"] != exp["hit"]) | (both & ((got["prim"] != exp["prim"]) | ~common.same_float(got["t"], exp["t"])))
+        assert differ.sum() == 0, f"victim {victim}: {int(differ.sum())} of {len(rays)} records differ"
+        total_displaced_hits += int(((exp["hit"] == 1) & (exp["prim"] == victim)).sum())
+    print("displaced-sphere hits:", total_displaced_hits)
+    assert total_displaced_hits > 1000, total_displaced_hits  # the displaced spheres are really hit through their old boxes
