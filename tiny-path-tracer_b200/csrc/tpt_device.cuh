@@ -1357,8 +1357,10 @@ TPT_DEV bool closest_hit_fbvh(const SceneView &S, const Ray &r, float tmin, floa
 // maximum of 32 such draws is ~3.5 times their mean, and the descent loop of the BVH scenes ran at 9.8 of 32
 // lanes, the leaf tests at 5-8 (profiles/r02_ncu_full_random_scene_lines.txt). Here a lane that has reached a
 // leaf simply WAITS (node < 0 is its whole state) while the others keep descending, and the warp switches
-// to the leaf code once the waiting lanes outnumber the descending ones TPT_VOTE_NUM : TPT_VOTE_DEN; both
-// code paths then run with most of their lanes. Must be called by all 32 lanes (live = has a ray).
+// to the leaf code once no more than TPT_VOTE_NUM / (TPT_VOTE_NUM + TPT_VOTE_DEN) of its walking lanes still
+// descend; both code paths then run with most of their lanes. Must be called by all 32 lanes (has_ray = the
+// lane brought a ray). Measured (sweep 9 of profiles/r02_tuning_sweeps.txt): the descent's lane occupancy
+// doubles, the kernel's time does not move on random_scene; the "trace" variant of the media scenes gains 5 %.
 #ifndef TPT_FBVH_VOTE
 #define TPT_FBVH_VOTE 0 // plain wavefront kernels of the SAH BVH scenes: 1 = vote-scheduled walk, 0 = per-lane while-while
 #endif
@@ -1368,17 +1370,17 @@ TPT_DEV bool closest_hit_fbvh(const SceneView &S, const Ray &r, float tmin, floa
 #ifndef TPT_VOTE_DEN
 #define TPT_VOTE_DEN 2 // descend while more than NUM / (NUM + DEN) of the walking lanes still do
 #endif
-TPT_DEV bool closest_hit_fbvh_vote(const SceneView &S, const Ray &r, bool live, float tmin, float tmax, float &t_out, int &prim_out) {
+TPT_DEV bool closest_hit_fbvh_vote(const SceneView &S, const Ray &r, bool has_ray, float tmin, float tmax, float &t_out, int &prim_out) {
   FbvhTrav tv;
   int stack[TPT_FBVH_STACK];
   tv.start(r, tmax);
-  if (!live) tv.node = TPT_FBVH_DONE;
+  if (!has_ray) tv.node = TPT_FBVH_DONE;
   const float4 *N = S.blob + S.L->off_fbvh;
   for (;;) {
-    const int live = __popc(__ballot_sync(0xffffffffu, !tv.done()));
-    if (live == 0) break;
+    const int walking = __popc(__ballot_sync(0xffffffffu, !tv.done()));
+    if (walking == 0) break;
     // descend while more than this many lanes still do; the others wait at their leaf (or are done)
-    const int limit = live * TPT_VOTE_NUM / (TPT_VOTE_NUM + TPT_VOTE_DEN);
+    const int limit = walking * TPT_VOTE_NUM / (TPT_VOTE_NUM + TPT_VOTE_DEN);
     bool inner = (unsigned)tv.node < (unsigned)TPT_FBVH_DONE;
     while (__popc(__ballot_sync(0xffffffffu, inner)) > limit) {
       if (inner) tv.inner_one(N, tmin, stack, S.wide_loads);

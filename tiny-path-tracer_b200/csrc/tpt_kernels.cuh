@@ -419,8 +419,8 @@ render_wave_kernel(const __grid_constant__ RenderArgs A) {
         // together; the loop returns to the hand-out above after every leaf pass
         {
           const float4 *N = S.blob + S.L->off_fbvh;
-          const int live = __popc(__ballot_sync(FULL, !tv.done()));
-          const int limit = live * TPT_VOTE_NUM / (TPT_VOTE_NUM + TPT_VOTE_DEN);
+          const int walking = __popc(__ballot_sync(FULL, !tv.done()));
+          const int limit = walking * TPT_VOTE_NUM / (TPT_VOTE_NUM + TPT_VOTE_DEN);
           bool inner = (unsigned)tv.node < (unsigned)TPT_FBVH_DONE;
           while (__popc(__ballot_sync(FULL, inner)) > limit) {
             if (inner) tv.inner_one(N, A.t_min, stack, S.wide_loads);
