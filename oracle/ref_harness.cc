@@ -28,10 +28,13 @@
 #include "texture.h"
 #include "utils.h"
 
+#include "../tiny-path-tracer_b200/host/tpt_scene_programs.h" // test scene family, compiled here against the reference's classes
+
 #include <atomic>
 #include <chrono>
 #include <memory>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <map>
@@ -211,6 +214,9 @@ hitable *build_named(const std::string &name, ref_scene *sc, const unsigned char
     l[4] = new sphere(vec3(5, -1, -2), 2, new lambertian(new perlin_noise_texture(2.0f)));
     return new hitable_list(l, 5);
   }
+  // TEST-ONLY scene family: random programs over the reference's own classes; the generator is the header the
+  // product's front end compiles against ITS classes, so both sides build the same tree from a seed
+  if (name.rfind("program:", 0) == 0) return scene_programs::build((uint32_t)std::strtoul(name.c_str() + 8, nullptr, 10));
   if (name == "earth") {
     // main.cpp:78-81 (commented alternative): sphere r=3 with image_texture(earthmap.jpg)
     unsigned char *copy = new unsigned char[(size_t)iw * ih * 3];

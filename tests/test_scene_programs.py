@@ -1,0 +1,87 @@
+"""Away from the handful of fixed scenes: random "scene programs" (tiny-path-tracer_b200/host/tpt_scene_programs.h).
+One generator header is compiled against the reference's own classes (oracle/ref_harness.cc) and against the
+product's front end, so both build the same hitable tree from a seed: spheres, moving spheres, rects, flip_normal,
+boxes, translate / rotate_y around primitives and around whole groups, hitable_lists and bvh_nodes nested in each
+other (one-element bvh_nodes, bvh_nodes under lists), all surface materials, checker textures.
+
+CPU part (here): the REFERENCE ITSELF (world->hit, color()) against the plain-C restatement running on the flattened
+description -- this pins the flattener and the restatement on tree shapes no fixed scene has. GPU part
+(test_gpu_scene_programs.py): the CUDA path against the restatement on the same programs."""
+import numpy as np
+import pytest
+
+import common
+import raygen
+
+SEEDS = list(range(1, 81))
+
+
+@pytest.fixture(scope="module")
+def P(T):
+    import oracle_port
+    if not oracle_port.available():
+        pytest.skip("oracle/_build/libtptoracle.so not built (run __graft_entry__.build())")
+    return oracle_port
+
+
+def program_rays(seed, n=2500):
+    """camera / interior / adversarial rays of the Cornell room plus rays between random points of the room (the objects
+    sit in [60, 495]^3), shutter times in [0, 1]"""
+    rng = np.random.default_rng(2000 + seed)
+    through = np.zeros((4 * n, 7), np.float32)
+    through[:, 0:3] = rng.uniform(-80, 635, size=(4 * n, 3))
+    through[:, 3:6] = rng.uniform(60, 495, size=(4 * n, 3)) - through[:, 0:3]
+    through[:, 6] = rng.uniform(0, 1, size=4 * n)
+    return np.concatenate([raygen.primary_batch("cornell_box", n, n, seed=1000 + seed), through])
+
+
+def test_programs_are_diverse(T):
+    """the family really covers the node kinds and wrappers it claims to"""
+    kinds, chains, dups, depth, prim_kinds = set(), 0, 0, 0, set()
+    for seed in SEEDS:
+        hs = T.HostScene(f"program:{seed}")
+        d = hs.desc.contents
+        open_ends = []
+        for i in range(d.n_nodes):
+            while open_ends and open_ends[-1] == i:
+                open_ends.pop()
+            k = d.nodes[i].kind
+            kinds.add(k & 0xff)
+            dups += bool(k & 0x100)
+            if (k & 0xff) != 2:
+                open_ends.append(d.nodes[i].end_or_prim)
+                depth = max(depth, len(open_ends))
+        chains = max(chains, d.n_chains)
+        prim_kinds |= {d.prims[i].kind for i in range(d.n_prims)}
+    assert kinds == {0, 1, 2} and dups > 0 and chains > 3 and depth >= 4 and prim_kinds >= {0, 1, 2, 3, 4}
+
+
+@pytest.mark.parametrize("seed", SEEDS)
+def test_reference_and_restatement_agree_on_hit_records(T, O, P, seed):
+    hs = T.HostScene(f"program:{seed}")
+    ref = O.RefScene(f"program:{seed}")
+    rays = program_rays(seed)
+    for gen in range(2):
+        exp = ref.hit_batch(rays)
+        got = P.hit_batch(T, hs, rays)
+        assert gen > 0 or (exp["hit"] == 1).sum() > 500
+        for f in ("hit", "prim", "mat"):
+            assert np.array_equal(got[f], exp[f]), (seed, gen, f, int((got[f] != exp[f]).sum()))
+        ok = exp["hit"] == 1
+        for f in ("t", "u", "v", "p", "n"):
+            assert common.same_float(got[f][ok], exp[f][ok]).all(), (seed, gen, f)
+        rays = raygen.secondary_rays(exp, np.random.default_rng(seed))
+        if len(rays) == 0:
+            break
+
+
+@pytest.mark.parametrize("seed", SEEDS[::2])
+def test_reference_and_restatement_agree_on_radiance_per_sample(T, O, P, seed):
+    nx, ny, ns, depth = 20, 20, 3, 12
+    ref, rsamples, rst = O.RefScene(f"program:{seed}").render(common.CORNELL_CAM, nx, ny, ns, depth, seed=900 + seed, per_sample=True)
+    hs = T.HostScene(f"program:{seed}")
+    out, samples, st = P.render(T, hs, common.product_camera(T, common.CORNELL_CAM, nx, ny),
+                                T.make_params(nx, ny, ns, depth, seed=900 + seed), threads=4, per_sample=True)
+    assert common.same_float(samples, rsamples).all(), int((~common.same_float(samples, rsamples)).sum())
+    assert common.same_float(out, ref).all()
+    assert st["rays"] == rst["rays"] and st["draws"] == rst["draws"]

@@ -4,6 +4,7 @@
 #include "tpt_flatten.h"
 #include "tpt_image_io.h"
 #include "tpt_scene.h"
+#include "tpt_scene_programs.h"
 
 #include <cstdlib>
 #include <cstring>
@@ -76,6 +77,7 @@ hitable *build_named(const std::string &name, const unsigned char *img, int iw, 
     l[2] = new xz_rect(-8, 8, -4, 4, -1.5f, new lambertian(new constant_texture({0.6, 0.6, 0.6})));
     return new hitable_list(l, 3);
   }
+  if (name.rfind("program:", 0) == 0) return scene_programs::build((uint32_t)std::strtoul(name.c_str() + 8, nullptr, 10)); // tpt_scene_programs.h
   if (name == "earth") { // main.cpp:78-81
     if (!img) return nullptr;
     unsigned char *copy = new unsigned char[(size_t)iw * ih * 3];
