@@ -8,7 +8,8 @@
 //
 // The header names the classes unqualified and is compiled twice: against this front end's classes
 // (host/tpt_scene.h, scene "program:<seed>" of tpt_host_build_scene) and, by the test harness, against the
-// reference's own headers (oracle/ref_harness.cc). Both then build the same tree from a seed, and the parity checks
+// reference's own headers (ref_harness.cc in the checkers' directory; the dependency points
+// from there to here, never the other way). Both then build the same tree from a seed, and the parity checks
 // can leave the handful of fixed scenes: reference vs restatement on the CPU, CUDA vs restatement on the GPU.
 // It draws from its own generator; bvh_node's constructor keeps taking its split axes from the thread's
 // default-seeded drand_r stream on both sides, in the same order.
