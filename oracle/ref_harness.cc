@@ -216,6 +216,7 @@ hitable *build_named(const std::string &name, ref_scene *sc, const unsigned char
   }
   // TEST-ONLY scene family: random programs over the reference's own classes; the generator is the header the
   // product's front end compiles against ITS classes, so both sides build the same tree from a seed
+  if (name.rfind("programm:", 0) == 0) return scene_programs::build((uint32_t)std::strtoul(name.c_str() + 9, nullptr, 10), true);
   if (name.rfind("program:", 0) == 0) return scene_programs::build((uint32_t)std::strtoul(name.c_str() + 8, nullptr, 10));
   if (name == "earth") {
     // main.cpp:78-81 (commented alternative): sphere r=3 with image_texture(earthmap.jpg)

@@ -92,3 +92,19 @@ def test_fast_mode_finds_the_same_objects(T, P, gpu):
     assert n > 300000
     assert bad <= FAST_ID_BUDGET * n, (bad, n)
     assert worst_t < 1e-3
+
+
+@pytest.mark.parametrize("seed", list(range(1, 21)))
+def test_parity_radiance_with_participating_media(T, P, gpu, seed):
+    """"programm:<seed>": programs with constant_medium objects (the stream is consumed inside world->hit)."""
+    nx, ny, ns, depth = 24, 24, 4, 12
+    hs = T.HostScene(f"programm:{seed}")
+    sc = make_scene(T, hs)
+    cam = common.product_camera(T, common.CORNELL_CAM, nx, ny)
+    for kernel in (T.KERNEL_MEGA, T.KERNEL_WAVEFRONT):
+        p = T.make_params(nx, ny, ns, depth, mode=T.MODE_PARITY, seed=900 + seed, kernel=kernel)
+        ref, _, _ = P.render(T, hs, cam, p, threads=4)
+        res = sc.render(cam, p)
+        rel = common.rel_err(res.sum_rgb, ref, 1e-3 * ns)
+        bad = int((rel > REL_TOL).any(axis=-1).sum())
+        assert bad == 0, f"seed {seed} kernel {kernel}: {bad} pixels beyond {REL_TOL}, worst {float(rel.max())}"

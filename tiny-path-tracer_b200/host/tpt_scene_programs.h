@@ -1,6 +1,6 @@
 // tpt_scene_programs.h -- a TEST scene family: random "programs" over the scene classes.
 //
-// "program:<seed>" builds a hitable tree out of everything the class API offers -- spheres, moving spheres, the three
+// "program:<seed>" (and "programm:<seed>", the same plus participating media) builds a hitable tree out of everything the class API offers -- spheres, moving spheres, the three
 // rects with and without flip_normal, boxes, translate / rotate_y wrappers around primitives AND around groups,
 // hitable_lists and bvh_nodes nested in each other (also bvh_nodes of one element, and bvh_nodes under lists), all
 // four surface materials, checker textures -- inside a Cornell-sized room with the lamp where the reference's
@@ -104,7 +104,7 @@ inline hitable *any_group(rng &g, int depth, bool under_list) {
 }
 
 // room (optional walls), the reference's lamp, and a few top-level groups; root = hitable_list or bvh_node
-inline hitable *build(uint32_t seed) {
+inline hitable *build(uint32_t seed, bool with_media = false) {
   rng g(seed);
   hitable **l = new hitable *[16];
   int n = 0;
@@ -118,6 +118,20 @@ inline hitable *build(uint32_t seed) {
   }
   const int groups = 1 + g.below(4);
   for (int i = 0; i < groups; i++) l[n++] = any_member(g, 3, false);
+  if (with_media) { // "programm:<seed>": one or two participating media (src/hitable.cc:92-128) with a sphere, a box or a moved box as boundary
+    const int media = 1 + g.below(2);
+    for (int i = 0; i < media; i++) {
+      const vec3 c = any_point(g);
+      const float r = g.range(40.f, 110.f);
+      hitable *boundary;
+      switch (g.below(3)) {
+      case 0: boundary = new sphere(c, r, new dielectric(1.5f)); break;
+      case 1: boundary = new box(c - vec3(r, r, r), c + vec3(r, r, r), new dielectric(1.5f)); break;
+      default: boundary = new translate(new rotate_y(new box(vec3(0, 0, 0), vec3(2 * r, 2 * r, 2 * r), new dielectric(1.5f)), g.range(-30.f, 30.f)), c - vec3(r, r, r)); break;
+      }
+      l[n++] = new constant_medium(boundary, g.range(0.002f, 0.02f), new constant_texture(vec3(g.range(0.1f, 1.f), g.range(0.1f, 1.f), g.range(0.1f, 1.f))));
+    }
+  }
   if (g.below(2)) return new bvh_node(l, n, 0.0f, 1.0f);
   return new hitable_list(l, n);
 }
