@@ -30,9 +30,12 @@
 #include "texture.h"
 #include "utils.h"
 
+#include "../tiny-path-tracer_b200/host/tpt_scene_programs.h" // test scene family, compiled here against the reference's classes
+
 #include "tpt.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <map>
@@ -345,6 +348,8 @@ hitable *build_on_this_thread(const std::string &name, unsigned char *img, int i
   if (name == "two_perlin_spheres") return two_perlin_spheres();
   if (name == "light_spheres") return light_spheres();
   if (name == "earth" && img) return new sphere(vec3(0, 0, 0), 3, new lambertian(new image_texture(img, iw, ih))); // main.cpp:78-81
+  // random programs over the reference's classes (test scene family)
+  if (name.rfind("program:", 0) == 0) return scene_programs::build((uint32_t)std::strtoul(name.c_str() + 8, nullptr, 10));
   return nullptr;
 }
 

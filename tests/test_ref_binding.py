@@ -59,6 +59,22 @@ def test_binding_describes_the_reference_scene_like_the_front_end(T, B, scene):
     assert bytes(out[:n]) == mine
 
 
+@pytest.mark.parametrize("seed", list(range(1, 61)))
+def test_binding_describes_random_scene_programs_like_the_front_end(T, B, seed):
+    """the same comparison on trees no fixed scene has (host/tpt_scene_programs.h compiled against the reference's
+    classes inside the binding): nested lists / bvh_nodes, transforms around groups, one-element bvh_nodes. (The
+    binding walks the surface classes; constant_medium is refused by name -- see its `hitable class outside this
+    binding` error -- and stays with the repo's front end.)"""
+    for name in (f"program:{seed}",):
+        out = (C.c_ubyte * (1 << 20))()
+        counts = (C.c_int32 * 8)()
+        n = B.tptbind_describe(name.encode(), None, 0, 0, out, len(out), counts)
+        assert n > 0, B.tptbind_last_error()
+        mine, my_counts = host_tables(T, T.HostScene(name))
+        assert list(counts) == my_counts, name
+        assert bytes(out[:n]) == mine, name
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("scene,cam", [("cornell_box", common.CORNELL_CAM), ("sphere_cornell_box", common.CORNELL_CAM),
                                        ("light_spheres", dict(common.BOOK_CAM, vfov=40.0))])
