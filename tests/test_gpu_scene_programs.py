@@ -108,3 +108,43 @@ def test_parity_radiance_with_participating_media(T, P, gpu, seed):
         rel = common.rel_err(res.sum_rgb, ref, 1e-3 * ns)
         bad = int((rel > REL_TOL).any(axis=-1).sum())
         assert bad == 0, f"seed {seed} kernel {kernel}: {bad} pixels beyond {REL_TOL}, worst {float(rel.max())}"
+
+
+@pytest.mark.parametrize("seed", list(range(1, 13)))
+def test_large_programs(T, P, gpu, seed):
+    """"programL:<seed>" (150-850 primitives: SAH BVH in fast mode, skip-pointer / replay walks in parity mode) and, every
+    third seed, "programLm:<seed>" with participating media (the "trace" wavefront variant in fast mode)."""
+    hs = T.HostScene(f"programL:{seed}")
+    sc = make_scene(T, hs)
+    rays = program_rays(seed, 1500)
+    exp = P.hit_batch(T, hs, rays)
+    got = sc.intersect(rays, mode=T.MODE_PARITY)
+    for f in ("hit", "prim", "mat"):
+        assert np.array_equal(got[f], exp[f]), (seed, f, int((got[f] != exp[f]).sum()))
+    ok = exp["hit"] == 1
+    for f in ("t", "p", "n"):
+        assert common.same_float(got[f][ok], exp[f][ok]).all(), (seed, f)
+    # fast mode: same closest object on the well-posed rays
+    n_adv = len(raygen.adversarial_rays(*raygen.SCENE_INFO["cornell_box"][:2]))
+    keep = np.isfinite(rays).all(axis=1)
+    keep[3000:3000 + n_adv] = False
+    fast = sc.intersect(rays, mode=T.MODE_FAST)
+    both = (fast["hit"] == 1) & (exp["hit"] == 1)
+    differ = ((fast["hit"] != exp["hit"]) | (both & (fast["prim"] != exp["prim"]))) & keep
+    assert differ.sum() <= 3, f"seed {seed}: {int(differ.sum())} of {int(keep.sum())} rays on another object in fast mode"
+    nx, ny, ns, depth = 24, 24, 4, 10
+    cam = common.product_camera(T, common.CORNELL_CAM, nx, ny)
+    for name in ([f"programL:{seed}"] + ([f"programLm:{seed}"] if seed % 3 == 0 else [])):
+        hs2 = T.HostScene(name)
+        sc2 = make_scene(T, hs2)
+        for kernel in (T.KERNEL_MEGA, T.KERNEL_WAVEFRONT):
+            p = T.make_params(nx, ny, ns, depth, mode=T.MODE_PARITY, seed=900 + seed, kernel=kernel)
+            ref, _, _ = P.render(T, hs2, cam, p, threads=4)
+            res = sc2.render(cam, p)
+            rel = common.rel_err(res.sum_rgb, ref, 1e-3 * ns)
+            bad = int((rel > REL_TOL).any(axis=-1).sum())
+            assert bad == 0, f"{name} kernel {kernel}: {bad} pixels beyond {REL_TOL}, worst {float(rel.max())}"
+            # fast mode runs the same frame without an error and with a comparable amount of light
+            pf = T.make_params(nx, ny, 16, depth, mode=T.MODE_FAST, seed=900 + seed, kernel=kernel)
+            fres = sc2.render(cam, pf)
+            assert np.isfinite(fres.sum_rgb).all()

@@ -100,3 +100,27 @@ def test_reference_and_restatement_agree_with_participating_media(T, O, P, seed)
                                 T.make_params(nx, ny, ns, depth, seed=900 + seed), threads=4, per_sample=True)
     assert common.same_float(samples, rsamples).all(), int((~common.same_float(samples, rsamples)).sum())
     assert st["rays"] == rst["rays"] and st["draws"] == rst["draws"]
+
+
+@pytest.mark.parametrize("seed", list(range(1, 13)))
+def test_reference_and_restatement_agree_on_large_programs(T, O, P, seed):
+    """"programL:<seed>" / "programLm:<seed>": 150-850 primitives, the size class of random_scene and oneweek_final
+    (SAH BVH, skip-pointer and replay walks on the CUDA side): hit records, and per-sample radiance with media."""
+    hs = T.HostScene(f"programL:{seed}")
+    assert hs.desc.contents.n_prims > 100
+    rays = program_rays(seed, 1500)
+    exp = O.RefScene(f"programL:{seed}").hit_batch(rays)
+    got = P.hit_batch(T, hs, rays)
+    for f in ("hit", "prim", "mat"):
+        assert np.array_equal(got[f], exp[f]), (seed, f)
+    ok = exp["hit"] == 1
+    for f in ("t", "u", "v", "p", "n"):
+        assert common.same_float(got[f][ok], exp[f][ok]).all(), (seed, f)
+    if seed % 3 == 0:
+        nx, ny, ns, depth = 16, 16, 2, 10
+        name = f"programLm:{seed}"
+        ref, rsamples, rst = O.RefScene(name).render(common.CORNELL_CAM, nx, ny, ns, depth, seed=900 + seed, per_sample=True)
+        out, samples, st = P.render(T, T.HostScene(name), common.product_camera(T, common.CORNELL_CAM, nx, ny),
+                                    T.make_params(nx, ny, ns, depth, seed=900 + seed), threads=4, per_sample=True)
+        assert common.same_float(samples, rsamples).all()
+        assert st["rays"] == rst["rays"] and st["draws"] == rst["draws"]

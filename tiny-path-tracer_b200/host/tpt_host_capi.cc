@@ -77,6 +77,8 @@ hitable *build_named(const std::string &name, const unsigned char *img, int iw, 
     l[2] = new xz_rect(-8, 8, -4, 4, -1.5f, new lambertian(new constant_texture({0.6, 0.6, 0.6})));
     return new hitable_list(l, 3);
   }
+  if (name.rfind("programLm:", 0) == 0) return scene_programs::build((uint32_t)std::strtoul(name.c_str() + 10, nullptr, 10), true, true);
+  if (name.rfind("programL:", 0) == 0) return scene_programs::build((uint32_t)std::strtoul(name.c_str() + 9, nullptr, 10), false, true);
   if (name.rfind("programm:", 0) == 0) return scene_programs::build((uint32_t)std::strtoul(name.c_str() + 9, nullptr, 10), true);
   if (name.rfind("program:", 0) == 0) return scene_programs::build((uint32_t)std::strtoul(name.c_str() + 8, nullptr, 10)); // tpt_scene_programs.h
   if (name == "earth") { // main.cpp:78-81

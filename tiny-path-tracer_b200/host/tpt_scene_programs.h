@@ -1,6 +1,7 @@
 // tpt_scene_programs.h -- a TEST scene family: random "programs" over the scene classes.
 //
-// "program:<seed>" (and "programm:<seed>", the same plus participating media) builds a hitable tree out of everything the class API offers -- spheres, moving spheres, the three
+// "program:<seed>" (and "programm:<seed>", the same plus participating media; "programL:<seed>" / "programLm:<seed>",
+// several times as many objects) builds a hitable tree out of everything the class API offers -- spheres, moving spheres, the three
 // rects with and without flip_normal, boxes, translate / rotate_y wrappers around primitives AND around groups,
 // hitable_lists and bvh_nodes nested in each other (also bvh_nodes of one element, and bvh_nodes under lists), all
 // four surface materials, checker textures -- inside a Cornell-sized room with the lamp where the reference's
@@ -104,9 +105,9 @@ inline hitable *any_group(rng &g, int depth, bool under_list) {
 }
 
 // room (optional walls), the reference's lamp, and a few top-level groups; root = hitable_list or bvh_node
-inline hitable *build(uint32_t seed, bool with_media = false) {
+inline hitable *build(uint32_t seed, bool with_media = false, bool large = false) {
   rng g(seed);
-  hitable **l = new hitable *[16];
+  hitable **l = new hitable *[48];
   int n = 0;
   l[n++] = new flip_normal(new xz_rect(213, 343, 227, 332, 554, new diffuse_light(new constant_texture(vec3(15, 15, 15)))));
   if (g.below(4) != 0) {
@@ -116,8 +117,9 @@ inline hitable *build(uint32_t seed, bool with_media = false) {
     if (g.below(2)) l[n++] = new flip_normal(new yz_rect(0, 555, 0, 555, 555, new lambertian(any_texture(g))));
     if (g.below(2)) l[n++] = new yz_rect(0, 555, 0, 555, 0, new lambertian(any_texture(g)));
   }
-  const int groups = 1 + g.below(4);
-  for (int i = 0; i < groups; i++) l[n++] = any_member(g, 3, false);
+  // "programL:<seed>": enough primitives (60-400) for the large-scene code paths (SAH BVH, skip-pointer / replay walks)
+  const int groups = large ? 8 + g.below(24) : 1 + g.below(4);
+  for (int i = 0; i < groups; i++) l[n++] = large ? any_group(g, 3, false) : any_member(g, 3, false);
   if (with_media) { // "programm:<seed>": one or two participating media (src/hitable.cc:92-128) with a sphere, a box or a moved box as boundary
     const int media = 1 + g.below(2);
     for (int i = 0; i < media; i++) {
