@@ -7,7 +7,7 @@ import pytest
 
 import common
 import raygen
-from test_scene_programs import program_rays
+from test_scene_programs import PROGRAM_CAM, PROGRAM_LIGHTS, program_rays
 
 pytestmark = pytest.mark.gpu
 SEEDS = list(range(1, 41))
@@ -53,9 +53,9 @@ def test_parity_hit_records_equal_restatement(T, P, gpu, seed):
 @pytest.mark.parametrize("seed", SEEDS[::2])
 def test_parity_radiance_equals_restatement(T, P, gpu, seed):
     nx, ny, ns, depth = 24, 24, 4, 12
-    hs = T.HostScene(f"program:{seed}")
+    hs = T.HostScene(f"program:{seed}", lights=PROGRAM_LIGHTS, background=T.BG_SKY if seed % 4 == 1 else T.BG_BLACK)
     sc = make_scene(T, hs)
-    cam = common.product_camera(T, common.CORNELL_CAM, nx, ny)
+    cam = common.product_camera(T, PROGRAM_CAM, nx, ny)
     for kernel in (T.KERNEL_MEGA, T.KERNEL_WAVEFRONT):
         p = T.make_params(nx, ny, ns, depth, mode=T.MODE_PARITY, seed=900 + seed, kernel=kernel)
         ref, _, _ = P.render(T, hs, cam, p, threads=4)
@@ -63,6 +63,7 @@ def test_parity_radiance_equals_restatement(T, P, gpu, seed):
         rel = common.rel_err(res.sum_rgb, ref, 1e-3 * ns)
         bad = int((rel > REL_TOL).any(axis=-1).sum())
         assert bad == 0, f"seed {seed} kernel {kernel}: {bad} pixels beyond {REL_TOL}, worst {float(rel.max())}"
+        assert (ref.sum(axis=-1) > 0).mean() > 0.3, "the frame should not be black"
 
 
 def test_fast_mode_finds_the_same_objects(T, P, gpu):
@@ -98,9 +99,9 @@ def test_fast_mode_finds_the_same_objects(T, P, gpu):
 def test_parity_radiance_with_participating_media(T, P, gpu, seed):
     """"programm:<seed>": programs with constant_medium objects (the stream is consumed inside world->hit)."""
     nx, ny, ns, depth = 24, 24, 4, 12
-    hs = T.HostScene(f"programm:{seed}")
+    hs = T.HostScene(f"programm:{seed}", lights=PROGRAM_LIGHTS, background=T.BG_SKY if seed % 4 == 1 else T.BG_BLACK)
     sc = make_scene(T, hs)
-    cam = common.product_camera(T, common.CORNELL_CAM, nx, ny)
+    cam = common.product_camera(T, PROGRAM_CAM, nx, ny)
     for kernel in (T.KERNEL_MEGA, T.KERNEL_WAVEFRONT):
         p = T.make_params(nx, ny, ns, depth, mode=T.MODE_PARITY, seed=900 + seed, kernel=kernel)
         ref, _, _ = P.render(T, hs, cam, p, threads=4)
@@ -133,9 +134,9 @@ def test_large_programs(T, P, gpu, seed):
     differ = ((fast["hit"] != exp["hit"]) | (both & (fast["prim"] != exp["prim"]))) & keep
     assert differ.sum() <= 3, f"seed {seed}: {int(differ.sum())} of {int(keep.sum())} rays on another object in fast mode"
     nx, ny, ns, depth = 24, 24, 4, 10
-    cam = common.product_camera(T, common.CORNELL_CAM, nx, ny)
+    cam = common.product_camera(T, PROGRAM_CAM, nx, ny)
     for name in ([f"programL:{seed}"] + ([f"programLm:{seed}"] if seed % 3 == 0 else [])):
-        hs2 = T.HostScene(name)
+        hs2 = T.HostScene(name, lights=PROGRAM_LIGHTS)
         sc2 = make_scene(T, hs2)
         for kernel in (T.KERNEL_MEGA, T.KERNEL_WAVEFRONT):
             p = T.make_params(nx, ny, ns, depth, mode=T.MODE_PARITY, seed=900 + seed, kernel=kernel)
@@ -148,3 +149,24 @@ def test_large_programs(T, P, gpu, seed):
             pf = T.make_params(nx, ny, 16, depth, mode=T.MODE_FAST, seed=900 + seed, kernel=kernel)
             fres = sc2.render(cam, pf)
             assert np.isfinite(fres.sum_rgb).all()
+
+
+@pytest.mark.parametrize("name", ["program:2", "program:3", "program:5", "program:21", "programm:2", "programL:2", "programLm:3"])
+def test_fast_mode_is_unbiased_on_programs(T, gpu, name):
+    """Converged frames (48 x 48, 2048 spp) in FAST and in PARITY mode: the image means agree far inside 1 % (two PARITY
+    frames with different seeds differ by 0.05-0.3 %). This is the check that found FAST mode 4.4 % dark on rooms whose x = 0
+    wall carried a checker_texture -- not a defect of its sampling but the checker's sin(10 x) evaluated AT its zero, where
+    the reference's answer is the sign of a rounding residue; the generator now keeps checkers off
+    that plane."""
+    nx = ny = 48
+    ns, depth = 2048, 12
+    cam = common.product_camera(T, PROGRAM_CAM, nx, ny)
+    sc = make_scene(T, T.HostScene(name, lights=PROGRAM_LIGHTS))
+
+    def mean(mode, seed):
+        r = sc.render(cam, T.make_params(nx, ny, ns, depth, mode=mode, seed=seed, kernel=T.KERNEL_WAVEFRONT))
+        return float(np.minimum(np.nan_to_num(r.sum_rgb[0] / ns), 10.0).mean())  # fireflies clamped for the comparison
+    a, a2, b = mean(T.MODE_PARITY, 11), mean(T.MODE_PARITY, 12), mean(T.MODE_FAST, 11)
+    print(f"\n{name}: parity {a:.5f} / {a2:.5f} (other seed), fast {b:.5f}: fast - parity = {(b - a) / a:+.2e} of the mean")
+    assert a > 0.02
+    assert abs(b - a) <= 0.01 * a, (a, b)

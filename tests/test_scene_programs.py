@@ -14,6 +14,11 @@ import common
 import raygen
 
 SEEDS = list(range(1, 81))
+# light-sampling list that matches the programs' lamp (the reference's hard-coded one, main.cpp:99-106, points elsewhere and
+# leaves these rooms nearly black), plus a sphere shape in mid-room; the programs use the book's 0..555 room, the reference's own
+# cornell_box() is centred on the origin and seen from +z (common.CORNELL_CAM)
+PROGRAM_LIGHTS = [(0, (213.0, 343.0, 227.0, 332.0, 554.0)), (1, (278.0, 278.0, 278.0, 60.0, 0.0))]
+PROGRAM_CAM = dict(lookfrom=(278, 278, -800), lookat=(278, 278, 0), vup=(0, 1, 0), vfov=40.0, aperture=0.1, focus_dist=10.0)  # the book's view into the 0..555 room
 
 
 @pytest.fixture(scope="module")
@@ -32,7 +37,8 @@ def program_rays(seed, n=2500):
     through[:, 0:3] = rng.uniform(-80, 635, size=(4 * n, 3))
     through[:, 3:6] = rng.uniform(60, 495, size=(4 * n, 3)) - through[:, 0:3]
     through[:, 6] = rng.uniform(0, 1, size=4 * n)
-    return np.concatenate([raygen.primary_batch("cornell_box", n, n, seed=1000 + seed), through])
+    view = raygen.camera_rays(n, PROGRAM_CAM["lookfrom"], PROGRAM_CAM["lookat"], 40.0, rng)
+    return np.concatenate([raygen.primary_batch("cornell_box", n, n, seed=1000 + seed), through, view])
 
 
 def test_programs_are_diverse(T):
@@ -78,13 +84,14 @@ def test_reference_and_restatement_agree_on_hit_records(T, O, P, seed):
 @pytest.mark.parametrize("seed", SEEDS[::2])
 def test_reference_and_restatement_agree_on_radiance_per_sample(T, O, P, seed):
     nx, ny, ns, depth = 20, 20, 3, 12
-    ref, rsamples, rst = O.RefScene(f"program:{seed}").render(common.CORNELL_CAM, nx, ny, ns, depth, seed=900 + seed, per_sample=True)
-    hs = T.HostScene(f"program:{seed}")
-    out, samples, st = P.render(T, hs, common.product_camera(T, common.CORNELL_CAM, nx, ny),
+    ref, rsamples, rst = O.RefScene(f"program:{seed}").render(PROGRAM_CAM, nx, ny, ns, depth, seed=900 + seed, per_sample=True, lights=PROGRAM_LIGHTS)
+    hs = T.HostScene(f"program:{seed}", lights=PROGRAM_LIGHTS)
+    out, samples, st = P.render(T, hs, common.product_camera(T, PROGRAM_CAM, nx, ny),
                                 T.make_params(nx, ny, ns, depth, seed=900 + seed), threads=4, per_sample=True)
     assert common.same_float(samples, rsamples).all(), int((~common.same_float(samples, rsamples)).sum())
     assert common.same_float(out, ref).all()
     assert st["rays"] == rst["rays"] and st["draws"] == rst["draws"]
+    assert (ref.sum(axis=-1) > 0).mean() > 0.05, "the frame should not be black"
 
 
 @pytest.mark.parametrize("seed", list(range(1, 41)))
@@ -94,9 +101,9 @@ def test_reference_and_restatement_agree_with_participating_media(T, O, P, seed)
     and draw counts."""
     nx, ny, ns, depth = 20, 20, 3, 12
     name = f"programm:{seed}"
-    ref, rsamples, rst = O.RefScene(name).render(common.CORNELL_CAM, nx, ny, ns, depth, seed=900 + seed, per_sample=True)
-    hs = T.HostScene(name)
-    out, samples, st = P.render(T, hs, common.product_camera(T, common.CORNELL_CAM, nx, ny),
+    ref, rsamples, rst = O.RefScene(name).render(PROGRAM_CAM, nx, ny, ns, depth, seed=900 + seed, per_sample=True, lights=PROGRAM_LIGHTS)
+    hs = T.HostScene(name, lights=PROGRAM_LIGHTS)
+    out, samples, st = P.render(T, hs, common.product_camera(T, PROGRAM_CAM, nx, ny),
                                 T.make_params(nx, ny, ns, depth, seed=900 + seed), threads=4, per_sample=True)
     assert common.same_float(samples, rsamples).all(), int((~common.same_float(samples, rsamples)).sum())
     assert st["rays"] == rst["rays"] and st["draws"] == rst["draws"]
@@ -119,8 +126,8 @@ def test_reference_and_restatement_agree_on_large_programs(T, O, P, seed):
     if seed % 3 == 0:
         nx, ny, ns, depth = 16, 16, 2, 10
         name = f"programLm:{seed}"
-        ref, rsamples, rst = O.RefScene(name).render(common.CORNELL_CAM, nx, ny, ns, depth, seed=900 + seed, per_sample=True)
-        out, samples, st = P.render(T, T.HostScene(name), common.product_camera(T, common.CORNELL_CAM, nx, ny),
+        ref, rsamples, rst = O.RefScene(name).render(PROGRAM_CAM, nx, ny, ns, depth, seed=900 + seed, per_sample=True, lights=PROGRAM_LIGHTS)
+        out, samples, st = P.render(T, T.HostScene(name, lights=PROGRAM_LIGHTS), common.product_camera(T, PROGRAM_CAM, nx, ny),
                                     T.make_params(nx, ny, ns, depth, seed=900 + seed), threads=4, per_sample=True)
         assert common.same_float(samples, rsamples).all()
         assert st["rays"] == rst["rays"] and st["draws"] == rst["draws"]

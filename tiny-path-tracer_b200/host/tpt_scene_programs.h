@@ -104,18 +104,23 @@ inline hitable *any_group(rng &g, int depth, bool under_list) {
   return any_primitive(g);
 }
 
-// room (optional walls), the reference's lamp, and a few top-level groups; root = hitable_list or bvh_node
+// the room, the reference's lamp, and a few top-level groups; root = hitable_list or bvh_node
 inline hitable *build(uint32_t seed, bool with_media = false, bool large = false) {
   rng g(seed);
   hitable **l = new hitable *[48];
   int n = 0;
   l[n++] = new flip_normal(new xz_rect(213, 343, 227, 332, 554, new diffuse_light(new constant_texture(vec3(15, 15, 15)))));
-  if (g.below(4) != 0) {
+  { // the Cornell room (src/utils.cc:287-303): floor, ceiling and back wall always -- an open room stays nearly black under
+    // the reference's black background --, the coloured side walls in half of the programs each
     material *white = new lambertian(new constant_texture(vec3(0.73f, 0.73f, 0.73f)));
     l[n++] = new xz_rect(0, 555, 0, 555, 0, white);
-    if (g.below(2)) l[n++] = new flip_normal(new xy_rect(0, 555, 0, 555, 555, white));
+    l[n++] = new flip_normal(new xz_rect(0, 555, 0, 555, 555, white));
+    l[n++] = new flip_normal(new xy_rect(0, 555, 0, 555, 555, white));
     if (g.below(2)) l[n++] = new flip_normal(new yz_rect(0, 555, 0, 555, 555, new lambertian(any_texture(g))));
-    if (g.below(2)) l[n++] = new yz_rect(0, 555, 0, 555, 0, new lambertian(any_texture(g)));
+    // (a constant colour on the wall in the plane x = 0: a checker_texture there is sin(10 x) sin(10 y) sin(10 z) AT a zero of
+    // its first factor, i.e. the sign of the rounding residue of o.x + t d.x -- exactly 0 in 89 % of the reference's own
+    // evaluations, never with a fused multiply-add. FAST mode cannot and need not reproduce that)
+    if (g.below(2)) l[n++] = new yz_rect(0, 555, 0, 555, 0, new lambertian(new constant_texture(vec3(g.range(0.05f, 0.95f), g.range(0.05f, 0.95f), g.range(0.05f, 0.95f)))));
   }
   // "programL:<seed>": enough primitives (60-400) for the large-scene code paths (SAH BVH, skip-pointer / replay walks)
   const int groups = large ? 8 + g.below(24) : 1 + g.below(4);
