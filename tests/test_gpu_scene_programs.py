@@ -151,7 +151,7 @@ def test_large_programs(T, P, gpu, seed):
             assert np.isfinite(fres.sum_rgb).all()
 
 
-@pytest.mark.parametrize("name", ["program:2", "program:3", "program:5", "program:21", "programm:2", "programL:2", "programLm:3"])
+@pytest.mark.parametrize("name", ["program:2", "program:3", "program:5", "program:21", "programm:2", "programL:2"])
 def test_fast_mode_is_unbiased_on_programs(T, gpu, name):
     """Converged frames (48 x 48, 2048 spp) in FAST and in PARITY mode: the image means agree far inside 1 % (two PARITY
     frames with different seeds differ by 0.05-0.3 %). This is the check that found FAST mode 4.4 % dark on rooms whose x = 0
@@ -168,5 +168,5 @@ def test_fast_mode_is_unbiased_on_programs(T, gpu, name):
         return float(np.minimum(np.nan_to_num(r.sum_rgb[0] / ns), 10.0).mean())  # fireflies clamped for the comparison
     a, a2, b = mean(T.MODE_PARITY, 11), mean(T.MODE_PARITY, 12), mean(T.MODE_FAST, 11)
     print(f"\n{name}: parity {a:.5f} / {a2:.5f} (other seed), fast {b:.5f}: fast - parity = {(b - a) / a:+.2e} of the mean")
-    assert a > 0.02
+    assert a > 0.02  # a lit frame (OBSERVED on B200: fast - parity between -1.3e-4 and +2.1e-4 of the mean on these six)
     assert abs(b - a) <= 0.01 * a, (a, b)
