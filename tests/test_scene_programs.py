@@ -131,3 +131,30 @@ def test_reference_and_restatement_agree_on_large_programs(T, O, P, seed):
                                     T.make_params(nx, ny, ns, depth, seed=900 + seed), threads=4, per_sample=True)
         assert common.same_float(samples, rsamples).all()
         assert st["rays"] == rst["rays"] and st["draws"] == rst["draws"]
+
+
+def test_every_program_passes_the_library_validator_and_the_folding(T):
+    """host-only parts of tpt_scene_create on all four families: validate_desc accepts the description (the call then ends
+    with TPT_ERR_NO_DEVICE here, or succeeds on a GPU box), and the small-scene folding (tpt_debug_small_scene) runs and
+    reports a layout that is consistent with the primitive count."""
+    import ctypes as C
+    lib = T.lib()
+    lib.tpt_debug_small_scene.argtypes = [C.POINTER(T.SceneDesc), C.POINTER(C.c_int32)]
+    lib.tpt_debug_small_scene.restype = C.c_int
+    small = large = 0
+    for fam, seeds in (("program", SEEDS), ("programm", range(1, 41)), ("programL", range(1, 13)), ("programLm", range(3, 13, 3))):
+        for seed in seeds:
+            hs = T.HostScene(f"{fam}:{seed}", lights=PROGRAM_LIGHTS)
+            out = C.c_void_p()
+            rc = lib.tpt_scene_create(hs.desc, 0, C.byref(out))
+            assert rc in (0, -3), (fam, seed, rc, lib.tpt_last_error())
+            if rc == 0:
+                lib.tpt_scene_destroy(out)
+            info = (C.c_int32 * 64)()
+            assert lib.tpt_debug_small_scene(hs.desc, info) == 0, (fam, seed, lib.tpt_last_error())
+            if info[0]:  # folded into the constant-bank layout: at most 48 primitives by construction
+                small += 1
+                assert 0 < info[1] <= 8 and hs.desc.contents.n_prims <= 600
+            else:
+                large += 1
+    assert small > 20 and large > 10, (small, large)
