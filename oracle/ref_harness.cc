@@ -216,6 +216,7 @@ hitable *build_named(const std::string &name, ref_scene *sc, const unsigned char
   }
   // TEST-ONLY scene family: random programs over the reference's own classes; the generator is the header the
   // product's front end compiles against ITS classes, so both sides build the same tree from a seed
+  if (name.rfind("programp:", 0) == 0) return scene_programs::build((uint32_t)std::strtoul(name.c_str() + 9, nullptr, 10), false, false, true);
   if (name.rfind("programLm:", 0) == 0) return scene_programs::build((uint32_t)std::strtoul(name.c_str() + 10, nullptr, 10), true, true);
   if (name.rfind("programL:", 0) == 0) return scene_programs::build((uint32_t)std::strtoul(name.c_str() + 9, nullptr, 10), false, true);
   if (name.rfind("programm:", 0) == 0) return scene_programs::build((uint32_t)std::strtoul(name.c_str() + 9, nullptr, 10), true);

@@ -158,3 +158,20 @@ def test_every_program_passes_the_library_validator_and_the_folding(T):
             else:
                 large += 1
     assert small > 20 and large > 10, (small, large)
+
+
+@pytest.mark.parametrize("seed", list(range(1, 21)))
+def test_reference_and_restatement_agree_with_perlin_textures(T, O, P, seed):
+    """"programp:<seed>": every third texture is the Perlin marble (src/texture.cc:18-25, src/utils.cc:160-225) on moved and
+    rotated objects at world coordinates of several hundred. The static noise tables of the reference-side build are read
+    back and forced on the other side (every perlin_noise ctor re-randomises them from the wall clock)."""
+    name = f"programp:{seed}"
+    rs = O.RefScene(name)
+    rv, px, py, pz = rs.perlin_tables()
+    hs = T.HostScene(name, perlin=common.perlin_struct(T, dict(ranvec=rv, perm_x=px, perm_y=py, perm_z=pz)), lights=PROGRAM_LIGHTS)
+    nx, ny, ns, depth = 16, 16, 2, 10
+    ref, rsamples, rst = rs.render(PROGRAM_CAM, nx, ny, ns, depth, seed=900 + seed, per_sample=True, lights=PROGRAM_LIGHTS)
+    out, samples, st = P.render(T, hs, common.product_camera(T, PROGRAM_CAM, nx, ny), T.make_params(nx, ny, ns, depth, seed=900 + seed),
+                                threads=4, per_sample=True)
+    assert common.same_float(samples, rsamples).all(), int((~common.same_float(samples, rsamples)).sum())
+    assert st["rays"] == rst["rays"] and st["draws"] == rst["draws"]

@@ -77,6 +77,7 @@ hitable *build_named(const std::string &name, const unsigned char *img, int iw, 
     l[2] = new xz_rect(-8, 8, -4, 4, -1.5f, new lambertian(new constant_texture({0.6, 0.6, 0.6})));
     return new hitable_list(l, 3);
   }
+  if (name.rfind("programp:", 0) == 0) return scene_programs::build((uint32_t)std::strtoul(name.c_str() + 9, nullptr, 10), false, false, true);
   if (name.rfind("programLm:", 0) == 0) return scene_programs::build((uint32_t)std::strtoul(name.c_str() + 10, nullptr, 10), true, true);
   if (name.rfind("programL:", 0) == 0) return scene_programs::build((uint32_t)std::strtoul(name.c_str() + 9, nullptr, 10), false, true);
   if (name.rfind("programm:", 0) == 0) return scene_programs::build((uint32_t)std::strtoul(name.c_str() + 9, nullptr, 10), true);

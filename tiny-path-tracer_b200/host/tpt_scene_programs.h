@@ -1,7 +1,7 @@
 // tpt_scene_programs.h -- a TEST scene family: random "programs" over the scene classes.
 //
 // "program:<seed>" (and "programm:<seed>", the same plus participating media; "programL:<seed>" / "programLm:<seed>",
-// several times as many objects) builds a hitable tree out of everything the class API offers -- spheres, moving spheres, the three
+// several times as many objects; "programp:<seed>", with Perlin marble textures) builds a hitable tree out of everything the class API offers -- spheres, moving spheres, the three
 // rects with and without flip_normal, boxes, translate / rotate_y wrappers around primitives AND around groups,
 // hitable_lists and bvh_nodes nested in each other (also bvh_nodes of one element, and bvh_nodes under lists), all
 // four surface materials, checker textures -- inside a Cornell-sized room with the lamp where the reference's
@@ -34,8 +34,14 @@ struct rng {
   float range(float a, float b) { return a + (b - a) * u(); }
 };
 
+// "programp:<seed>": every third texture is the marble of src/texture.cc:18-25 (Perlin turbulence at world coordinates of
+// several hundred, on moved and rotated objects). The noise tables are static and re-randomised by every perlin_noise
+// constructor from the wall clock: the test reads them back from the reference-side build and forces them on the other.
+static bool g_with_perlin = false;
+
 inline texture *any_texture(rng &g) {
   vec3 c(g.range(0.05f, 0.95f), g.range(0.05f, 0.95f), g.range(0.05f, 0.95f));
+  if (g_with_perlin && g.below(3) == 0) return new perlin_noise_texture(g.range(0.01f, 0.1f));
   if (g.below(5) == 0) return new checker_texture(new constant_texture(c), new constant_texture(vec3(0.9f, 0.9f, 0.9f)));
   return new constant_texture(c);
 }
@@ -105,8 +111,9 @@ inline hitable *any_group(rng &g, int depth, bool under_list) {
 }
 
 // the room, the reference's lamp, and a few top-level groups; root = hitable_list or bvh_node
-inline hitable *build(uint32_t seed, bool with_media = false, bool large = false) {
+inline hitable *build(uint32_t seed, bool with_media = false, bool large = false, bool with_perlin = false) {
   rng g(seed);
+  g_with_perlin = with_perlin;
   hitable **l = new hitable *[48];
   int n = 0;
   l[n++] = new flip_normal(new xz_rect(213, 343, 227, 332, 554, new diffuse_light(new constant_texture(vec3(15, 15, 15)))));
