@@ -12,7 +12,7 @@ from test_scene_programs import PROGRAM_CAM, PROGRAM_LIGHTS, program_rays
 pytestmark = pytest.mark.gpu
 SEEDS = list(range(1, 41))
 REL_TOL = 1e-4
-FAST_ID_BUDGET = 2e-4  # share of rays whose closest object may differ in FAST mode (ties at shared edges, grazing hits); OBSERVED on B200: 0 of 600 000
+FAST_ID_BUDGET = 2e-4  # share of rays whose closest object may differ in FAST mode (ties at shared edges, grazing hits); OBSERVED on B200: 0 of 700 000
 
 
 @pytest.fixture(scope="module")
