@@ -349,6 +349,7 @@ hitable *build_on_this_thread(const std::string &name, unsigned char *img, int i
   if (name == "light_spheres") return light_spheres();
   if (name == "earth" && img) return new sphere(vec3(0, 0, 0), 3, new lambertian(new image_texture(img, iw, ih))); // main.cpp:78-81
   // random programs over the reference's classes (test scene family)
+  if (name.rfind("programL:", 0) == 0) return scene_programs::build((uint32_t)std::strtoul(name.c_str() + 9, nullptr, 10), false, true);
   if (name.rfind("program:", 0) == 0) return scene_programs::build((uint32_t)std::strtoul(name.c_str() + 8, nullptr, 10));
   return nullptr;
 }

@@ -65,8 +65,8 @@ def test_binding_describes_random_scene_programs_like_the_front_end(T, B, seed):
     classes inside the binding): nested lists / bvh_nodes, transforms around groups, one-element bvh_nodes. (The
     binding walks the surface classes; constant_medium is refused by name -- see its `hitable class outside this
     binding` error -- and stays with the repo's front end.)"""
-    for name in (f"program:{seed}",):
-        out = (C.c_ubyte * (1 << 20))()
+    for name in (f"program:{seed}",) + ((f"programL:{seed}",) if seed % 6 == 0 else ()):
+        out = (C.c_ubyte * (1 << 22))()
         counts = (C.c_int32 * 8)()
         n = B.tptbind_describe(name.encode(), None, 0, 0, out, len(out), counts)
         assert n > 0, B.tptbind_last_error()
